@@ -1,0 +1,137 @@
+/*
+ * nemoflux_gpu.h -- C ABI of libnemoflux_gpu.so: the B200 (sm_100a) transect-flux hot path of
+ * pletzer/nemoflux behind the interface nemoflux binds today.
+ *
+ * What it replaces.  nemoflux reaches its native code through python-mint's ctypes bindings of
+ * libmint's C API (mnt_grid_*, mnt_polylineintegral_*; call sites /root/reference/nemoflux/
+ * horizgrid.py:23-24, field.py:45-48, field.py:102, fluxplot.py:56) and does the C-grid edge-flux
+ * assembly itself in numpy (field.py:145-234).  Each entry point below cites the call it stands for.
+ *
+ * Conventions (the same as libmint's): every function returns int, 0 = success, non-zero = error
+ * code (NFX_E_*), details through nfx_last_error(); objects are opaque and passed as T** like mint's
+ * handles; no exception crosses the boundary; the caller owns every array.  Arrays marked "host"
+ * are ordinary host memory, arrays marked "device" are CUDA device pointers that the library only
+ * borrows (e.g. torch tensor.data_ptr()); `stream` is a cudaStream_t passed as void* (NULL = the
+ * legacy default stream).  A handle is bound to the CUDA device that was current when it was
+ * created; calls on one handle must be serialised by the caller.
+ */
+#ifndef NEMOFLUX_GPU_H
+#define NEMOFLUX_GPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NFX_OK 0
+#define NFX_E_INVALID 1   /* bad argument / call order            */
+#define NFX_E_CUDA 2      /* a CUDA runtime call failed           */
+#define NFX_E_NOGPU 3     /* no usable CUDA device                */
+#define NFX_E_ALLOC 4     /* out of host or device memory         */
+#define NFX_E_INTERNAL 5
+
+/* mint.CELL_BY_CELL_DATA (field.py:102): data is (ncells, 4), one private datum per cell edge */
+#define NFX_CELL_BY_CELL_DATA 0
+
+/* storage type of uo/vo */
+#define NFX_F64 0   /* datagen.py:9 writes float64 */
+#define NFX_F32 1   /* real NEMO output            */
+
+/* summation order of the transect integral */
+#define NFX_ORDER_LIST 0  /* emission order: sub-segment by sub-segment, edges 0..3          */
+#define NFX_ORDER_MAP 1   /* mint's std::map<(cellId,edgeIndex),weight> order (default)     */
+
+/* edge-flux kernel variants (nfx_set_option NFX_OPT_K2_VARIANT) */
+#define NFX_K2_AUTO 0
+#define NFX_K2_LDG 1      /* direct vectorised global loads, widest legal (256-bit on sm_100a) */
+#define NFX_K2_TMA 2      /* TMA (cp.async.bulk.tensor) staged level tiles                    */
+#define NFX_K2_LDG128 3   /* direct loads capped at 128 bits                                  */
+#define NFX_OPT_K2_VARIANT 1
+#define NFX_OPT_K2_UNROLL 2   /* levels in flight per thread (0 = default) */
+#define NFX_OPT_K2_BLOCK 3    /* threads per CTA (0 = default)             */
+
+typedef struct nfx_grid nfx_grid;
+typedef struct nfx_pli nfx_pli;
+
+const char* nfx_last_error(void);
+int nfx_version(void);
+int nfx_set_option(int option, int value);
+int nfx_get_option(int option, int* value);
+/* number of kernels this library has launched since load (bench.py's gpu_launches) */
+int nfx_launch_count(int64_t* n);
+
+/* ---- mint.Grid: Grid(), setPoints(points), getNumberOfCells()  (horizgrid.py:23-24,30) ---------- */
+int nfx_grid_new(nfx_grid** self);
+int nfx_grid_del(nfx_grid** self);
+/* points: host (ncells,4,3) float64, vertices 0=SW 1=SE 2=NE 3=NW, (lon deg, lat deg, unused);
+ * copied to the device (mint borrows the pointer instead, horizgrid.py:24) */
+int nfx_grid_set_points(nfx_grid** self, int64_t ncells, const double* points);
+int nfx_grid_get_num_cells(nfx_grid** self, int64_t* ncells);
+/* the structured shape behind the cell ids (cell = j*nx + i, horizgrid.py:17-22); needed by the
+ * compact [eU|eV] flux layout (field.py:209-223), not by the mint-style calls */
+int nfx_grid_set_cgrid_shape(nfx_grid** self, int ny, int nx);
+
+/* ---- mint.PolylineIntegral  (field.py:45-48, field.py:102, fluxplot.py:56) ----------------------- */
+int nfx_pli_new(nfx_pli** self);
+int nfx_pli_del(nfx_pli** self);
+int nfx_pli_set_grid(nfx_pli** self, nfx_grid* grid);
+/* buildLocator(numCellsPerBucket=128, periodX=360., enableFolding=False), field.py:47.  Builds the
+ * device-side bounding-box hierarchy ONCE per grid, shared by all transects (the reference rebuilds
+ * a locator per transect).  numCellsPerBucket is accepted and ignored, enableFolding must be 0. */
+int nfx_pli_build_locator(nfx_pli** self, int num_cells_per_bucket, double period_x, int enable_folding);
+/* computeWeights(xyz (npoints,3) float64 host, counterclock=False), field.py:48: one transect */
+int nfx_pli_compute_weights(nfx_pli** self, int npoints, const double* xyz, int counterclock);
+/* the batched form: ntransects polylines; offsets (ntransects+1) indexes points in xyz (total,3) */
+int nfx_pli_compute_weights_batch(nfx_pli** self, int ntransects, const int* offsets, const double* xyz,
+                                  int counterclock);
+int nfx_pli_get_num_transects(nfx_pli** self, int* ntransects);
+/* sub-segments in emission order (transect, segment, ta, cell, image); every output is host memory
+ * and may be NULL; transect_offsets has ntransects+1 entries; xia/xib are (n,2), w is (n,4) */
+int nfx_pli_get_num_subsegments(nfx_pli** self, int64_t* n);
+int nfx_pli_get_subsegments(nfx_pli** self, int64_t* transect_offsets, int64_t* cell, int32_t* seg, int32_t* img,
+                            double* ta, double* tb, double* coeff, double* xia, double* xib, double* w);
+/* mint's map view: per transect the unique keys cell*4+edge (ascending) and accumulated weights */
+int nfx_pli_get_map_size(nfx_pli** self, int64_t* n);
+int nfx_pli_get_map(nfx_pli** self, int64_t* transect_offsets, int64_t* keys, double* w);
+/* getIntegral(data (ncells,4) float64 host, CELL_BY_CELL_DATA) -> result (field.py:102); for a batch
+ * `results` receives ntransects values */
+int nfx_pli_get_integral(nfx_pli** self, const double* data, int placement, double* result);
+int nfx_pli_get_integrals(nfx_pli** self, const double* data, int placement, int order, double* results);
+/* same with data already on the device: data device (nt, ncells, 4), results device (nt, ntransects) */
+int nfx_pli_get_integrals_device(nfx_pli** self, const double* data, int nt, int order, double* results,
+                                 void* stream);
+
+/* ---- Field.readField + Field.computeIntegratedFlux  (field.py:145-163, 183-234)  = kernel K2 ----- */
+/* u, v: device (nt, nz, ncell) of dtype; thickness device (nz) = deptht_bounds[:,1]-[:,0]
+ * (field.py:51); arc1/arc2 device (ncell) = arcLengths[:,1], arcLengths[:,2] (field.py:195-196);
+ * NaN (and values equal to `fill` when fill is not NaN) count as 0 (field.py:157); sverdrup
+ * multiplies by 6371000/1e6 (field.py:225-228).
+ * eflux: device (nt, 2*ncell): [t, 0:ncell] = signed eU, [t, ncell:2*ncell] = signed eV. */
+int nfx_edgeflux_assemble(const void* u, const void* v, int dtype, const double* thickness, const double* arc1,
+                          const double* arc2, int nt, int nz, int64_t ncell, int sverdrup, double fill,
+                          double* eflux, void* stream);
+/* the (ncell,4) mint layout of field.py:209-223 from the compact one: south edges of row 0 are 0,
+ * west edges x-periodic.  eflux device (nt, 2*ncell) -> iv device (nt, ncell, 4) */
+int nfx_edgeflux_to_cell_by_cell(const double* eflux, int nt, int ny, int nx, double* iv, void* stream);
+/* max |eU|, max |eV| over all nt steps (field.py:230-234); result host (1) */
+int nfx_edgeflux_absmax(const double* eflux, int nt, int64_t ncell, double* result, void* stream);
+
+/* ---- the fluxplot.py:51-59 loop = kernel K3, and K2+K3 in one call ------------------------------- */
+/* series device (nt, ntransects): sum_n w_n * eflux[t, index(cell_n, edge_n)]; needs
+ * nfx_grid_set_cgrid_shape before nfx_pli_compute_weights* */
+int nfx_pli_integrate(nfx_pli** self, const double* eflux, int nt, int order, double* series, void* stream);
+int nfx_flux_series(nfx_pli** self, const void* u, const void* v, int dtype, const double* thickness,
+                    const double* arc1, const double* arc2, int nt, int nz, int sverdrup, double fill, int order,
+                    double* eflux, double* series, void* stream);
+/* everything from HOST buffers (the call a non-CUDA host makes): u, v host (nt,nz,ny,nx), thickness
+ * host (nz), arc1/arc2 host (ncell); series host (nt, ntransects).  Streams time chunks through
+ * double-buffered device staging (host buffers may be pinned or pageable). chunk_steps <= 0 = auto */
+int nfx_flux_series_host(nfx_pli** self, const void* u, const void* v, int dtype, const double* thickness,
+                         const double* arc1, const double* arc2, int nt, int nz, int sverdrup, double fill,
+                         int order, int chunk_steps, double* series);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

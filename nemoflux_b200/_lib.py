@@ -1,0 +1,103 @@
+"""ctypes binding of libnemoflux_gpu.so (the C ABI declared in include/nemoflux_gpu.h).
+
+There is no CPU fallback: if the library is missing or no CUDA device is usable, every compute entry
+point raises.  Build the library with ``python -m nemoflux_b200.build`` (nvcc, sm_100a).
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libnemoflux_gpu.so')
+
+NFX_OK = 0
+NFX_CELL_BY_CELL_DATA = 0
+NFX_F64, NFX_F32 = 0, 1
+NFX_ORDER_LIST, NFX_ORDER_MAP = 0, 1
+NFX_K2_AUTO, NFX_K2_LDG, NFX_K2_TMA, NFX_K2_LDG128 = 0, 1, 2, 3
+NFX_OPT_K2_VARIANT, NFX_OPT_K2_UNROLL, NFX_OPT_K2_BLOCK = 1, 2, 3
+
+c_i64 = ctypes.c_int64
+c_int = ctypes.c_int
+c_dbl = ctypes.c_double
+c_vp = ctypes.c_void_p
+P = ctypes.POINTER
+
+# name -> argtypes; every function returns int except nfx_last_error
+SIGNATURES = {
+    'nfx_version': [],
+    'nfx_set_option': [c_int, c_int],
+    'nfx_get_option': [c_int, P(c_int)],
+    'nfx_launch_count': [P(c_i64)],
+    'nfx_grid_new': [P(c_vp)],
+    'nfx_grid_del': [P(c_vp)],
+    'nfx_grid_set_points': [P(c_vp), c_i64, c_vp],
+    'nfx_grid_get_num_cells': [P(c_vp), P(c_i64)],
+    'nfx_grid_set_cgrid_shape': [P(c_vp), c_int, c_int],
+    'nfx_pli_new': [P(c_vp)],
+    'nfx_pli_del': [P(c_vp)],
+    'nfx_pli_set_grid': [P(c_vp), c_vp],
+    'nfx_pli_build_locator': [P(c_vp), c_int, c_dbl, c_int],
+    'nfx_pli_compute_weights': [P(c_vp), c_int, c_vp, c_int],
+    'nfx_pli_compute_weights_batch': [P(c_vp), c_int, c_vp, c_vp, c_int],
+    'nfx_pli_get_num_transects': [P(c_vp), P(c_int)],
+    'nfx_pli_get_num_subsegments': [P(c_vp), P(c_i64)],
+    'nfx_pli_get_subsegments': [P(c_vp)] + [c_vp] * 10,
+    'nfx_pli_get_map_size': [P(c_vp), P(c_i64)],
+    'nfx_pli_get_map': [P(c_vp), c_vp, c_vp, c_vp],
+    'nfx_pli_get_integral': [P(c_vp), c_vp, c_int, P(c_dbl)],
+    'nfx_pli_get_integrals': [P(c_vp), c_vp, c_int, c_int, c_vp],
+    'nfx_pli_get_integrals_device': [P(c_vp), c_vp, c_int, c_int, c_vp, c_vp],
+    'nfx_edgeflux_assemble': [c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_int, c_i64, c_int, c_dbl, c_vp, c_vp],
+    'nfx_edgeflux_to_cell_by_cell': [c_vp, c_int, c_int, c_int, c_vp, c_vp],
+    'nfx_edgeflux_absmax': [c_vp, c_int, c_i64, P(c_dbl), c_vp],
+    'nfx_pli_integrate': [P(c_vp), c_vp, c_int, c_int, c_vp, c_vp],
+    'nfx_flux_series': [P(c_vp), c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_dbl, c_int, c_vp, c_vp,
+                        c_vp],
+    'nfx_flux_series_host': [P(c_vp), c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_dbl, c_int, c_int,
+                             c_vp],
+}
+
+_LIB = None
+
+
+class NemofluxGpuError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__(f'libnemoflux_gpu error {code}: {message}')
+        self.code = code
+
+
+def load():
+    """load the shared library (raises if it was not built -- there is no fallback)"""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f'{LIB_PATH} is missing: build it with `python -m nemoflux_b200.build` '
+                               '(nvcc -gencode arch=compute_100a,code=sm_100a); there is no CPU fallback')
+        L = ctypes.CDLL(LIB_PATH)
+        L.nfx_last_error.restype = ctypes.c_char_p
+        L.nfx_last_error.argtypes = []
+        for name, args in SIGNATURES.items():
+            f = getattr(L, name)
+            f.restype = c_int
+            f.argtypes = args
+        _LIB = L
+    return _LIB
+
+
+def check(ier):
+    if ier != NFX_OK:
+        raise NemofluxGpuError(ier, load().nfx_last_error().decode('utf-8', 'replace'))
+
+
+def call(name, *args):
+    check(getattr(load(), name)(*args))
+
+
+def launch_count():
+    n = c_i64()
+    call('nfx_launch_count', ctypes.byref(n))
+    return n.value
+
+
+def set_option(option, value):
+    call('nfx_set_option', option, value)

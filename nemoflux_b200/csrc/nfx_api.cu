@@ -1,0 +1,466 @@
+// extern "C" entry points of libnemoflux_gpu.so -- see include/nemoflux_gpu.h.
+#include <atomic>
+#include <cstring>
+
+#include "nfx_common.cuh"
+
+namespace nfx {
+
+static thread_local std::string g_last_error;
+static std::atomic<int64_t> g_launches{0};
+static K2Options g_k2opt;
+
+void set_last_error(const std::string& m) { g_last_error = m; }
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+static void require_gpu(int* dev) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        throw Error(NFX_E_NOGPU, std::string("no usable CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e)
+                                                                                           : "device count is 0"));
+    }
+    NFX_CUDA(cudaGetDevice(dev));
+}
+
+template <typename F>
+static int guarded(F&& f) {
+    try {
+        f();
+        return NFX_OK;
+    } catch (const Error& e) {
+        set_last_error(e.what());
+        return e.code;
+    } catch (const std::bad_alloc&) {
+        set_last_error("out of host memory");
+        return NFX_E_ALLOC;
+    } catch (const std::exception& e) {
+        set_last_error(e.what());
+        return NFX_E_INTERNAL;
+    } catch (...) {
+        set_last_error("unknown error");
+        return NFX_E_INTERNAL;
+    }
+}
+
+static void free_host_path(PliDev& p) {
+    for (int i = 0; i < 2; ++i) {
+        if (p.ev_ready[i]) cudaEventDestroy(p.ev_ready[i]);
+        if (p.ev_done[i]) cudaEventDestroy(p.ev_done[i]);
+        p.ev_ready[i] = p.ev_done[i] = nullptr;
+    }
+    if (p.copy_stream) cudaStreamDestroy(p.copy_stream);
+    if (p.compute_stream) cudaStreamDestroy(p.compute_stream);
+    p.copy_stream = p.compute_stream = nullptr;
+}
+
+static const Csr& pick_csr(PliDev& p, int order, int layout) {
+    NFX_REQUIRE(order == NFX_ORDER_LIST || order == NFX_ORDER_MAP, "order must be NFX_ORDER_LIST or NFX_ORDER_MAP");
+    NFX_REQUIRE(p.csr[order][0].rowptr.p != nullptr, "computeWeights was not called");
+    if (layout == 1)
+        NFX_REQUIRE(p.has_compact, "nfx_grid_set_cgrid_shape must be called before computeWeights for the flux path");
+    return p.csr[order][layout];
+}
+
+}  // namespace nfx
+
+using namespace nfx;
+
+struct nfx_grid {
+    GridDev d;
+};
+struct nfx_pli {
+    PliDev d;
+};
+
+template <typename T>
+static void d2h(T* dst, const T* src, size_t n) {
+    if (dst && n) NFX_CUDA(cudaMemcpy(dst, src, sizeof(T) * n, cudaMemcpyDeviceToHost));
+}
+
+extern "C" {
+
+const char* nfx_last_error(void) { return g_last_error.c_str(); }
+int nfx_version(void) { return 100; }
+
+int nfx_set_option(int option, int value) {
+    return guarded([&] {
+        switch (option) {
+            case NFX_OPT_K2_VARIANT:
+                NFX_REQUIRE(value >= NFX_K2_AUTO && value <= NFX_K2_LDG128, "bad K2 variant");
+                g_k2opt.variant = value;
+                break;
+            case NFX_OPT_K2_UNROLL: g_k2opt.unroll = value; break;
+            case NFX_OPT_K2_BLOCK: g_k2opt.block = value; break;
+            default: throw Error(NFX_E_INVALID, "unknown option");
+        }
+    });
+}
+
+int nfx_get_option(int option, int* value) {
+    return guarded([&] {
+        NFX_REQUIRE(value, "NULL value");
+        switch (option) {
+            case NFX_OPT_K2_VARIANT: *value = g_k2opt.variant; break;
+            case NFX_OPT_K2_UNROLL: *value = g_k2opt.unroll; break;
+            case NFX_OPT_K2_BLOCK: *value = g_k2opt.block; break;
+            default: throw Error(NFX_E_INVALID, "unknown option");
+        }
+    });
+}
+
+int nfx_launch_count(int64_t* n) {
+    if (!n) return NFX_E_INVALID;
+    *n = g_launches.load();
+    return NFX_OK;
+}
+
+// ---- grid -------------------------------------------------------------------------------------------
+int nfx_grid_new(nfx_grid** self) {
+    return guarded([&] {
+        NFX_REQUIRE(self, "NULL handle");
+        int dev;
+        require_gpu(&dev);
+        *self = new nfx_grid();
+        (*self)->d.device = dev;
+    });
+}
+
+int nfx_grid_del(nfx_grid** self) {
+    return guarded([&] {
+        NFX_REQUIRE(self, "NULL handle");
+        if (*self) {
+            DeviceGuard g((*self)->d.device);
+            delete *self;
+        }
+        *self = nullptr;
+    });
+}
+
+int nfx_grid_set_points(nfx_grid** self, int64_t ncells, const double* points) {
+    return guarded([&] {
+        NFX_REQUIRE(self && *self, "NULL handle");
+        DeviceGuard g((*self)->d.device);
+        grid_upload_points((*self)->d, ncells, points);
+    });
+}
+
+int nfx_grid_get_num_cells(nfx_grid** self, int64_t* ncells) {
+    return guarded([&] {
+        NFX_REQUIRE(self && *self && ncells, "NULL handle");
+        *ncells = (*self)->d.ncell;
+    });
+}
+
+int nfx_grid_set_cgrid_shape(nfx_grid** self, int ny, int nx) {
+    return guarded([&] {
+        NFX_REQUIRE(self && *self, "NULL handle");
+        NFX_REQUIRE(ny > 0 && nx > 0, "ny and nx must be positive");
+        NFX_REQUIRE((*self)->d.ncell == 0 || (int64_t)ny * nx == (*self)->d.ncell, "ny*nx differs from the cell count");
+        (*self)->d.ny = ny;
+        (*self)->d.nx = nx;
+    });
+}
+
+// ---- polyline integral -------------------------------------------------------------------------------
+int nfx_pli_new(nfx_pli** self) {
+    return guarded([&] {
+        NFX_REQUIRE(self, "NULL handle");
+        int dev;
+        require_gpu(&dev);
+        *self = new nfx_pli();
+    });
+}
+
+int nfx_pli_del(nfx_pli** self) {
+    return guarded([&] {
+        NFX_REQUIRE(self, "NULL handle");
+        if (*self) {
+            if ((*self)->d.grid) {
+                DeviceGuard g((*self)->d.grid->device);
+                free_host_path((*self)->d);
+                delete *self;
+            } else {
+                free_host_path((*self)->d);
+                delete *self;
+            }
+        }
+        *self = nullptr;
+    });
+}
+
+int nfx_pli_set_grid(nfx_pli** self, nfx_grid* grid) {
+    return guarded([&] {
+        NFX_REQUIRE(self && *self && grid, "NULL handle");
+        (*self)->d.grid = &grid->d;
+    });
+}
+
+int nfx_pli_build_locator(nfx_pli** self, int num_cells_per_bucket, double period_x, int enable_folding) {
+    return guarded([&] {
+        NFX_REQUIRE(self && *self, "NULL handle");
+        PliDev& p = (*self)->d;
+        NFX_REQUIRE(p.grid, "buildLocator: setGrid was not called");
+        NFX_REQUIRE(num_cells_per_bucket > 0, "buildLocator: numCellsPerBucket must be positive");
+        NFX_REQUIRE(enable_folding == 0, "buildLocator: enableFolding is not supported (nemoflux passes False)");
+        NFX_REQUIRE(period_x >= 0.0, "buildLocator: periodX must be >= 0");
+        DeviceGuard g(p.grid->device);
+        grid_build_locator(*p.grid, nullptr);
+        NFX_CUDA(cudaStreamSynchronize(nullptr));
+        p.period_x = period_x;
+        p.locator_requested = true;
+    });
+}
+
+int nfx_pli_compute_weights_batch(nfx_pli** self, int ntransects, const int* offsets, const double* xyz,
+                                  int counterclock) {
+    return guarded([&] {
+        NFX_REQUIRE(self && *self, "NULL handle");
+        PliDev& p = (*self)->d;
+        NFX_REQUIRE(p.grid, "computeWeights: setGrid was not called");
+        DeviceGuard g(p.grid->device);
+        pli_compute_weights(p, ntransects, offsets, xyz, counterclock, nullptr);
+    });
+}
+
+int nfx_pli_compute_weights(nfx_pli** self, int npoints, const double* xyz, int counterclock) {
+    if (npoints < 0) {
+        set_last_error("computeWeights: negative number of points");
+        return NFX_E_INVALID;
+    }
+    const int offsets[2] = {0, npoints};
+    return nfx_pli_compute_weights_batch(self, 1, offsets, xyz, counterclock);
+}
+
+int nfx_pli_get_num_transects(nfx_pli** self, int* ntransects) {
+    return guarded([&] {
+        NFX_REQUIRE(self && *self && ntransects, "NULL handle");
+        *ntransects = (*self)->d.ntransects;
+    });
+}
+
+int nfx_pli_get_num_subsegments(nfx_pli** self, int64_t* n) {
+    return guarded([&] {
+        NFX_REQUIRE(self && *self && n, "NULL handle");
+        *n = (*self)->d.nsub;
+    });
+}
+
+int nfx_pli_get_subsegments(nfx_pli** self, int64_t* transect_offsets, int64_t* cell, int32_t* seg, int32_t* img,
+                            double* ta, double* tb, double* coeff, double* xia, double* xib, double* w) {
+    return guarded([&] {
+        NFX_REQUIRE(self && *self, "NULL handle");
+        PliDev& p = (*self)->d;
+        NFX_REQUIRE(p.grid, "setGrid was not called");
+        DeviceGuard g(p.grid->device);
+        const size_t n = (size_t)p.nsub;
+        if (transect_offsets)
+            for (int m = 0; m <= p.ntransects; ++m) transect_offsets[m] = p.h_sub_offsets[m];
+        if (cell && n) {
+            std::vector<int32_t> tmp(n);
+            d2h(tmp.data(), p.cell.p, n);
+            for (size_t i = 0; i < n; ++i) cell[i] = tmp[i];
+        }
+        d2h(seg, p.seg.p, n);
+        d2h(img, p.img.p, n);
+        d2h(ta, p.ta.p, n);
+        d2h(tb, p.tb.p, n);
+        d2h(coeff, p.coeff.p, n);
+        d2h(xia, p.xia.p, 2 * n);
+        d2h(xib, p.xib.p, 2 * n);
+        d2h(w, p.w.p, 4 * n);
+    });
+}
+
+int nfx_pli_get_map_size(nfx_pli** self, int64_t* n) {
+    return guarded([&] {
+        NFX_REQUIRE(self && *self && n, "NULL handle");
+        *n = (*self)->d.nmap;
+    });
+}
+
+int nfx_pli_get_map(nfx_pli** self, int64_t* transect_offsets, int64_t* keys, double* w) {
+    return guarded([&] {
+        NFX_REQUIRE(self && *self, "NULL handle");
+        PliDev& p = (*self)->d;
+        NFX_REQUIRE(p.grid, "setGrid was not called");
+        DeviceGuard g(p.grid->device);
+        if (transect_offsets)
+            for (int m = 0; m <= p.ntransects; ++m) transect_offsets[m] = p.h_map_offsets[m];
+        d2h(keys, p.map_keys.p, (size_t)p.nmap);
+        d2h(w, p.map_w.p, (size_t)p.nmap);
+    });
+}
+
+int nfx_pli_get_integrals_device(nfx_pli** self, const double* data, int nt, int order, double* results,
+                                 void* stream) {
+    return guarded([&] {
+        NFX_REQUIRE(self && *self, "NULL handle");
+        PliDev& p = (*self)->d;
+        NFX_REQUIRE(p.grid, "setGrid was not called");
+        DeviceGuard g(p.grid->device);
+        const Csr& c = pick_csr(p, order, 0);
+        csr_integrate(c, p.ntransects, data, p.grid->ncell * 4, nt, results, (cudaStream_t)stream);
+    });
+}
+
+int nfx_pli_get_integrals(nfx_pli** self, const double* data, int placement, int order, double* results) {
+    return guarded([&] {
+        NFX_REQUIRE(self && *self && data && results, "NULL pointer");
+        NFX_REQUIRE(placement == NFX_CELL_BY_CELL_DATA, "only CELL_BY_CELL_DATA placement is supported");
+        PliDev& p = (*self)->d;
+        NFX_REQUIRE(p.grid, "setGrid was not called");
+        DeviceGuard g(p.grid->device);
+        const Csr& c = pick_csr(p, order, 0);
+        const size_t n = (size_t)p.grid->ncell * 4;
+        p.scratch_data.ensure(n);
+        p.scratch_res.ensure((size_t)std::max(p.ntransects, 1));
+        NFX_CUDA(cudaMemcpy(p.scratch_data.p, data, sizeof(double) * n, cudaMemcpyHostToDevice));
+        csr_integrate(c, p.ntransects, p.scratch_data.p, (int64_t)n, 1, p.scratch_res.p, nullptr);
+        NFX_CUDA(cudaMemcpy(results, p.scratch_res.p, sizeof(double) * p.ntransects, cudaMemcpyDeviceToHost));
+    });
+}
+
+int nfx_pli_get_integral(nfx_pli** self, const double* data, int placement, double* result) {
+    if (self && *self && (*self)->d.ntransects != 1) {
+        set_last_error("getIntegral: the handle holds a batch; use nfx_pli_get_integrals");
+        return NFX_E_INVALID;
+    }
+    return nfx_pli_get_integrals(self, data, placement, NFX_ORDER_MAP, result);
+}
+
+// ---- K2 / K3 on device buffers -------------------------------------------------------------------------
+int nfx_edgeflux_assemble(const void* u, const void* v, int dtype, const double* thickness, const double* arc1,
+                          const double* arc2, int nt, int nz, int64_t ncell, int sverdrup, double fill,
+                          double* eflux, void* stream) {
+    return guarded([&] {
+        int dev;
+        require_gpu(&dev);
+        edgeflux_assemble(u, v, dtype, thickness, arc1, arc2, nt, nz, ncell, sverdrup, fill, eflux, g_k2opt,
+                          (cudaStream_t)stream);
+    });
+}
+
+int nfx_edgeflux_to_cell_by_cell(const double* eflux, int nt, int ny, int nx, double* iv, void* stream) {
+    return guarded([&] {
+        int dev;
+        require_gpu(&dev);
+        edgeflux_to_cell_by_cell(eflux, nt, ny, nx, iv, (cudaStream_t)stream);
+    });
+}
+
+int nfx_edgeflux_absmax(const double* eflux, int nt, int64_t ncell, double* result, void* stream) {
+    return guarded([&] {
+        int dev;
+        require_gpu(&dev);
+        edgeflux_absmax(eflux, nt, ncell, result, (cudaStream_t)stream);
+    });
+}
+
+int nfx_pli_integrate(nfx_pli** self, const double* eflux, int nt, int order, double* series, void* stream) {
+    return guarded([&] {
+        NFX_REQUIRE(self && *self, "NULL handle");
+        PliDev& p = (*self)->d;
+        NFX_REQUIRE(p.grid, "setGrid was not called");
+        DeviceGuard g(p.grid->device);
+        const Csr& c = pick_csr(p, order, 1);
+        csr_integrate(c, p.ntransects, eflux, p.grid->ncell * 2, nt, series, (cudaStream_t)stream);
+    });
+}
+
+int nfx_flux_series(nfx_pli** self, const void* u, const void* v, int dtype, const double* thickness,
+                    const double* arc1, const double* arc2, int nt, int nz, int sverdrup, double fill, int order,
+                    double* eflux, double* series, void* stream) {
+    return guarded([&] {
+        NFX_REQUIRE(self && *self, "NULL handle");
+        PliDev& p = (*self)->d;
+        NFX_REQUIRE(p.grid, "setGrid was not called");
+        DeviceGuard g(p.grid->device);
+        const Csr& c = pick_csr(p, order, 1);
+        edgeflux_assemble(u, v, dtype, thickness, arc1, arc2, nt, nz, p.grid->ncell, sverdrup, fill, eflux, g_k2opt,
+                          (cudaStream_t)stream);
+        csr_integrate(c, p.ntransects, eflux, p.grid->ncell * 2, nt, series, (cudaStream_t)stream);
+    });
+}
+
+// ---- everything from host buffers: double-buffered H2D staging, K2+K3 per chunk --------------------------
+int nfx_flux_series_host(nfx_pli** self, const void* u, const void* v, int dtype, const double* thickness,
+                         const double* arc1, const double* arc2, int nt, int nz, int sverdrup, double fill, int order,
+                         int chunk_steps, double* series) {
+    return guarded([&] {
+        NFX_REQUIRE(self && *self, "NULL handle");
+        NFX_REQUIRE(u && v && thickness && arc1 && arc2 && series, "NULL pointer");
+        NFX_REQUIRE(nt >= 0 && nz > 0, "bad sizes");
+        NFX_REQUIRE(dtype == NFX_F64 || dtype == NFX_F32, "dtype must be NFX_F64 or NFX_F32");
+        PliDev& p = (*self)->d;
+        NFX_REQUIRE(p.grid, "setGrid was not called");
+        DeviceGuard g(p.grid->device);
+        const Csr& c = pick_csr(p, order, 1);
+        const int64_t ncell = p.grid->ncell;
+        const int M = p.ntransects;
+        if (nt == 0 || M == 0) return;
+        const size_t esize = dtype == NFX_F64 ? 8 : 4;
+        const size_t step_bytes = esize * (size_t)nz * (size_t)ncell;
+        if (chunk_steps <= 0) {
+            const size_t target = (size_t)256 << 20;  // per variable and slot
+            chunk_steps = (int)std::max<size_t>(1, target / step_bytes);
+        }
+        chunk_steps = std::min(chunk_steps, nt);
+        if (!p.copy_stream) {
+            NFX_CUDA(cudaStreamCreateWithFlags(&p.copy_stream, cudaStreamNonBlocking));
+            NFX_CUDA(cudaStreamCreateWithFlags(&p.compute_stream, cudaStreamNonBlocking));
+            for (int i = 0; i < 2; ++i) {
+                NFX_CUDA(cudaEventCreateWithFlags(&p.ev_ready[i], cudaEventDisableTiming));
+                NFX_CUDA(cudaEventCreateWithFlags(&p.ev_done[i], cudaEventDisableTiming));
+            }
+        }
+        for (int i = 0; i < 2; ++i) {
+            p.stage_u[i].ensure(step_bytes * chunk_steps);
+            p.stage_v[i].ensure(step_bytes * chunk_steps);
+            p.stage_eflux[i].ensure((size_t)chunk_steps * 2 * ncell);
+        }
+        p.stage_series.ensure((size_t)nt * M);
+        p.stage_thick.ensure(nz);
+        p.stage_arc1.ensure(ncell);
+        p.stage_arc2.ensure(ncell);
+        cudaStream_t cs = p.copy_stream, ks = p.compute_stream;
+        NFX_CUDA(cudaMemcpyAsync(p.stage_thick.p, thickness, sizeof(double) * nz, cudaMemcpyHostToDevice, ks));
+        NFX_CUDA(cudaMemcpyAsync(p.stage_arc1.p, arc1, sizeof(double) * ncell, cudaMemcpyHostToDevice, ks));
+        NFX_CUDA(cudaMemcpyAsync(p.stage_arc2.p, arc2, sizeof(double) * ncell, cudaMemcpyHostToDevice, ks));
+        int slot = 0;
+        bool used[2] = {false, false};
+        for (int t0 = 0; t0 < nt; t0 += chunk_steps, slot ^= 1) {
+            const int n = std::min(chunk_steps, nt - t0);
+            if (used[slot]) NFX_CUDA(cudaStreamWaitEvent(cs, p.ev_done[slot], 0));
+            const unsigned char* hu = (const unsigned char*)u + (size_t)t0 * step_bytes;
+            const unsigned char* hv = (const unsigned char*)v + (size_t)t0 * step_bytes;
+            NFX_CUDA(cudaMemcpyAsync(p.stage_u[slot].p, hu, step_bytes * n, cudaMemcpyHostToDevice, cs));
+            NFX_CUDA(cudaMemcpyAsync(p.stage_v[slot].p, hv, step_bytes * n, cudaMemcpyHostToDevice, cs));
+            NFX_CUDA(cudaEventRecord(p.ev_ready[slot], cs));
+            NFX_CUDA(cudaStreamWaitEvent(ks, p.ev_ready[slot], 0));
+            edgeflux_assemble(p.stage_u[slot].p, p.stage_v[slot].p, dtype, p.stage_thick.p, p.stage_arc1.p,
+                              p.stage_arc2.p, n, nz, ncell, sverdrup, fill, p.stage_eflux[slot].p, g_k2opt, ks);
+            csr_integrate(c, M, p.stage_eflux[slot].p, ncell * 2, n, p.stage_series.p + (size_t)t0 * M, ks);
+            NFX_CUDA(cudaEventRecord(p.ev_done[slot], ks));
+            used[slot] = true;
+        }
+        NFX_CUDA(cudaMemcpyAsync(series, p.stage_series.p, sizeof(double) * (size_t)nt * M, cudaMemcpyDeviceToHost, ks));
+        NFX_CUDA(cudaStreamSynchronize(ks));
+        NFX_CUDA(cudaStreamSynchronize(cs));
+    });
+}
+
+}  // extern "C"

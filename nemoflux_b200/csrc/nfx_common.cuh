@@ -1,0 +1,135 @@
+// Shared declarations of libnemoflux_gpu.so (sm_100a).  See include/nemoflux_gpu.h for the ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/nemoflux_gpu.h"
+
+namespace nfx {
+
+struct Error : public std::runtime_error {
+    int code;
+    Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+void set_last_error(const std::string& m);
+void count_launch(int n = 1);
+
+#define NFX_CUDA(call)                                                                              \
+    do {                                                                                            \
+        cudaError_t e__ = (call);                                                                   \
+        if (e__ != cudaSuccess)                                                                     \
+            throw nfx::Error(NFX_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));     \
+    } while (0)
+
+#define NFX_REQUIRE(cond, msg)                                      \
+    do {                                                            \
+        if (!(cond)) throw nfx::Error(NFX_E_INVALID, (msg));        \
+    } while (0)
+
+// owning device buffer
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { release(); }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    void alloc(size_t count) {
+        release();
+        if (count == 0) count = 1;
+        cudaError_t e = cudaMalloc((void**)&p, count * sizeof(T));
+        if (e != cudaSuccess) {
+            p = nullptr;
+            throw Error(NFX_E_ALLOC, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+        }
+        n = count;
+    }
+    void ensure(size_t count) {
+        if (count > n) alloc(count);
+    }
+};
+
+// ---- K1 data ------------------------------------------------------------------------------------
+constexpr int kFan = 32;  // bounding-box hierarchy fan-out = warp width
+
+struct GridDev {
+    int device = 0;
+    int64_t ncell = 0;
+    int ny = 0, nx = 0;          // optional structured shape (0 = unknown)
+    DevBuf<double2> verts;       // (ncell*4) lon,lat
+    // locator (built by nfx_pli_build_locator, cached on the grid so every pli shares it)
+    bool locator_built = false;
+    int64_t nl1 = 0, nl2 = 0;
+    DevBuf<double4> box1, box2;  // xmin, xmax, ymin, ymax
+};
+
+// CSR of (flux index, weight) per transect
+struct Csr {
+    int64_t nnz = 0;
+    DevBuf<int64_t> rowptr;  // (M+1)
+    DevBuf<int32_t> idx;
+    const double* w = nullptr;  // borrowed: PliDev::w (list order) or PliDev::map_w (map order)
+};
+
+struct PliDev {
+    GridDev* grid = nullptr;
+    double period_x = 360.0;
+    bool locator_requested = false;
+    int ntransects = 0;
+    int64_t nsub = 0;
+    // sub-segments, emission order
+    DevBuf<int64_t> sub_offsets;  // (M+1) per transect
+    DevBuf<int32_t> cell, seg, img;
+    DevBuf<double> ta, tb, coeff, xia, xib, w;  // xia/xib (n,2), w (n,4)
+    // mint map view
+    int64_t nmap = 0;
+    DevBuf<int64_t> map_offsets;  // (M+1)
+    DevBuf<int64_t> map_keys;     // cell*4+edge
+    DevBuf<double> map_w;
+    // CSRs: [order][layout]; layout 0 = (ncell,4) cell-by-cell data, 1 = compact [eU|eV]
+    Csr csr[2][2];
+    bool has_compact = false;
+    std::vector<int64_t> h_sub_offsets, h_map_offsets;
+    // scratch reused by the host-buffer entry points
+    DevBuf<double> scratch_data, scratch_res;
+    // persistent staging of nfx_flux_series_host (two slots)
+    DevBuf<unsigned char> stage_u[2], stage_v[2];
+    DevBuf<double> stage_eflux[2], stage_series, stage_thick, stage_arc1, stage_arc2;
+    cudaStream_t copy_stream = nullptr, compute_stream = nullptr;
+    cudaEvent_t ev_ready[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+};
+
+// K1 (nfx_k1_intersect.cu)
+void grid_upload_points(GridDev& g, int64_t ncells, const double* points_host);
+void grid_build_locator(GridDev& g, cudaStream_t s);
+void pli_compute_weights(PliDev& p, int ntransects, const int* offsets, const double* xyz, int counterclock,
+                         cudaStream_t s);
+
+// K2 (nfx_k2_edgeflux.cu)
+struct K2Options {
+    int variant = NFX_K2_AUTO;
+    int unroll = 0;   // 0 = default
+    int block = 0;    // 0 = default
+};
+void edgeflux_assemble(const void* u, const void* v, int dtype, const double* thickness, const double* arc1,
+                       const double* arc2, int nt, int nz, int64_t ncell, int sverdrup, double fill, double* eflux,
+                       const K2Options& opt, cudaStream_t s);
+void edgeflux_to_cell_by_cell(const double* eflux, int nt, int ny, int nx, double* iv, cudaStream_t s);
+void edgeflux_absmax(const double* eflux, int nt, int64_t ncell, double* result_host, cudaStream_t s);
+
+// K3 (nfx_k3_reduce.cu)
+void csr_integrate(const Csr& c, int ntransects, const double* data, int64_t stride_t, int nt, double* series,
+                   cudaStream_t s);
+
+}  // namespace nfx

@@ -1,0 +1,365 @@
+// K2: C-grid edge-flux assembly (sm_100a), HBM-bound streaming kernel.
+//
+// Replaces Field.readField (NaN -> 0, sum over z of thickness*field, /root/reference/nemoflux/
+// field.py:145-163) and Field.computeIntegratedFlux (eU = +U*arc1, eV = -V*arc2, optional Sverdrup
+// factor, field.py:183-228) for ALL time steps of a chunk in one launch.
+//
+//   eflux[t, c]         = (sum_k dz[k]*u[t,k,c]) * arc1[c] (* 6.371)
+//   eflux[t, ncell + c] = -(sum_k dz[k]*v[t,k,c]) * arc2[c] (* 6.371)
+//
+// The (ncell,4) array of field.py:209-223 is NOT materialised on the fast path: K1 remaps
+// (cell, edge) to an index into this compact [eU | eV] layout.  nfx_edgeflux_to_cell_by_cell builds
+// it on request for the mint-style getIntegral(data) call.
+//
+// The z-sum runs k = 0..nz-1 per column with separate multiply and add (no FMA), fp64, so the result
+// is bit-identical to the sequential CPU restatement (oracle/nfx_oracle.c orc_edgeflux_step).
+//
+// Algorithmic bytes: 2 * sizeof(T) * nz per cell and time step (u and v read once).  Roofline: HBM.
+#include <cuda.h>
+
+#include "nfx_common.cuh"
+
+namespace nfx {
+
+namespace {
+
+__device__ __forceinline__ double2 ld_stream(const double2* p) {
+    double2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];"
+                 : "=d"(r.x), "=d"(r.y)
+                 : "l"(p));
+    return r;
+}
+// 256-bit global load (sm_100+): 4 doubles per instruction, with the L2 evict-first hint that only
+// this width accepts -- the u/v stream is read exactly once
+struct __align__(32) double4x {
+    double x, y, z, w;
+};
+struct __align__(32) float8x {
+    float a[8];
+};
+__device__ __forceinline__ double4x ld_stream(const double4x* p) {
+    double4x r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v4.f64 {%0, %1, %2, %3}, [%4];"
+                 : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w)
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ float8x ld_stream(const float8x* p) {
+    float8x r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=f"(r.a[0]), "=f"(r.a[1]), "=f"(r.a[2]), "=f"(r.a[3]), "=f"(r.a[4]), "=f"(r.a[5]), "=f"(r.a[6]),
+                   "=f"(r.a[7])
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ double ld_stream(const double* p) {
+    double r;
+    asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(r) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ float4 ld_stream(const float4* p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ float ld_stream(const float* p) {
+    float r;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
+    return r;
+}
+
+// Register fence: every load of a batch is issued (volatile asm keeps program order) before the
+// first value is consumed, so UNROLL*2 wide loads are in flight per thread instead of one.
+__device__ __forceinline__ void pin(double& x) { asm volatile("" : "+d"(x)); }
+__device__ __forceinline__ void pin(float& x) { asm volatile("" : "+f"(x)); }
+__device__ __forceinline__ void pin(double2& r) { asm volatile("" : "+d"(r.x), "+d"(r.y)); }
+__device__ __forceinline__ void pin(float4& r) { asm volatile("" : "+f"(r.x), "+f"(r.y), "+f"(r.z), "+f"(r.w)); }
+__device__ __forceinline__ void pin(double4x& r) { asm volatile("" : "+d"(r.x), "+d"(r.y), "+d"(r.z), "+d"(r.w)); }
+__device__ __forceinline__ void pin(float8x& r) {
+    asm volatile(""
+                 : "+f"(r.a[0]), "+f"(r.a[1]), "+f"(r.a[2]), "+f"(r.a[3]), "+f"(r.a[4]), "+f"(r.a[5]), "+f"(r.a[6]),
+                   "+f"(r.a[7]));
+}
+
+template <typename T, int VEC>
+struct Pack;
+template <>
+struct Pack<double, 2> {
+    using type = double2;
+    __device__ static void unpack(const double2& p, double (&o)[2]) {
+        o[0] = p.x;
+        o[1] = p.y;
+    }
+};
+template <>
+struct Pack<double, 4> {
+    using type = double4x;
+    __device__ static void unpack(const double4x& p, double (&o)[4]) {
+        o[0] = p.x;
+        o[1] = p.y;
+        o[2] = p.z;
+        o[3] = p.w;
+    }
+};
+template <>
+struct Pack<float, 8> {
+    using type = float8x;
+    __device__ static void unpack(const float8x& p, float (&o)[8]) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = p.a[i];
+    }
+};
+template <>
+struct Pack<double, 1> {
+    using type = double;
+    __device__ static void unpack(const double& p, double (&o)[1]) { o[0] = p; }
+};
+template <>
+struct Pack<float, 4> {
+    using type = float4;
+    __device__ static void unpack(const float4& p, float (&o)[4]) {
+        o[0] = p.x;
+        o[1] = p.y;
+        o[2] = p.z;
+        o[3] = p.w;
+    }
+};
+template <>
+struct Pack<float, 1> {
+    using type = float;
+    __device__ static void unpack(const float& p, float (&o)[1]) { o[0] = p; }
+};
+
+// land / missing values count as zero: NaN (xarray-decoded _FillValue, field.py:157) or == fill
+template <typename T>
+__device__ __forceinline__ double clean(T x, T fill, bool has_fill) {
+    const bool bad = (x != x) || (has_fill && x == fill);
+    return bad ? 0.0 : (double)x;
+}
+
+// One thread owns VEC adjacent columns of one time step; blockIdx.y = time step.
+template <typename T, int VEC, int UNROLL, int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
+k2_edgeflux_ldg(const T* __restrict__ u, const T* __restrict__ v, const double* __restrict__ dz,
+                const double* __restrict__ arc1, const double* __restrict__ arc2, double* __restrict__ eflux, int nz,
+                int64_t ncell, double scale, int use_scale, T fill, int has_fill) {
+    extern __shared__ double s_dz[];
+    for (int k = threadIdx.x; k < nz; k += BLOCK) s_dz[k] = dz[k];
+    __syncthreads();
+    using P = Pack<T, VEC>;
+    using V = typename P::type;
+    const int64_t t = blockIdx.y;
+    const int64_t c0 = ((int64_t)blockIdx.x * BLOCK + threadIdx.x) * VEC;
+    if (c0 >= ncell) return;  // VEC divides ncell on the vector path, so c0+VEC <= ncell
+    const T* pu = u + t * nz * ncell + c0;
+    const T* pv = v + t * nz * ncell + c0;
+    double su[VEC], sv[VEC];
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+        su[e] = 0.0;
+        sv[e] = 0.0;
+    }
+    int k = 0;
+    for (; k + UNROLL <= nz; k += UNROLL) {
+        V ru[UNROLL], rv[UNROLL];
+#pragma unroll
+        for (int q = 0; q < UNROLL; ++q) {
+            ru[q] = ld_stream(reinterpret_cast<const V*>(pu + (int64_t)(k + q) * ncell));
+            rv[q] = ld_stream(reinterpret_cast<const V*>(pv + (int64_t)(k + q) * ncell));
+        }
+#pragma unroll
+        for (int q = 0; q < UNROLL; ++q) {
+            pin(ru[q]);
+            pin(rv[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < UNROLL; ++q) {
+            T a[VEC], b[VEC];
+            P::unpack(ru[q], a);
+            P::unpack(rv[q], b);
+            const double d = s_dz[k + q];
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) {
+                su[e] = __dadd_rn(su[e], __dmul_rn(d, clean<T>(a[e], fill, has_fill)));
+                sv[e] = __dadd_rn(sv[e], __dmul_rn(d, clean<T>(b[e], fill, has_fill)));
+            }
+        }
+    }
+    for (; k < nz; ++k) {
+        T a[VEC], b[VEC];
+        P::unpack(ld_stream(reinterpret_cast<const V*>(pu + (int64_t)k * ncell)), a);
+        P::unpack(ld_stream(reinterpret_cast<const V*>(pv + (int64_t)k * ncell)), b);
+        const double d = s_dz[k];
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+            su[e] = __dadd_rn(su[e], __dmul_rn(d, clean<T>(a[e], fill, has_fill)));
+            sv[e] = __dadd_rn(sv[e], __dmul_rn(d, clean<T>(b[e], fill, has_fill)));
+        }
+    }
+    double* ou = eflux + t * 2 * ncell + c0;
+    double* ov = ou + ncell;
+    double fu[VEC], fv[VEC];
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+        fu[e] = __dmul_rn(su[e], arc1[c0 + e]);
+        fv[e] = __dmul_rn(-sv[e], arc2[c0 + e]);
+        if (use_scale) {
+            fu[e] = __dmul_rn(fu[e], scale);
+            fv[e] = __dmul_rn(fv[e], scale);
+        }
+    }
+    if constexpr (VEC % 2 == 0) {  // ncell even on this path -> 16-byte aligned stores
+#pragma unroll
+        for (int e = 0; e < VEC; e += 2) {
+            *reinterpret_cast<double2*>(ou + e) = make_double2(fu[e], fu[e + 1 < VEC ? e + 1 : e]);
+            *reinterpret_cast<double2*>(ov + e) = make_double2(fv[e], fv[e + 1 < VEC ? e + 1 : e]);
+        }
+    } else {
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+            ou[e] = fu[e];
+            ov[e] = fv[e];
+        }
+    }
+}
+
+template <typename T, int VEC, int UNROLL, int BLOCK>
+void launch_ldg(const T* u, const T* v, const double* dz, const double* arc1, const double* arc2, double* eflux, int nt,
+                int nz, int64_t ncell, double scale, int use_scale, T fill, int has_fill, cudaStream_t s) {
+    const int64_t nthreads = (ncell + VEC - 1) / VEC;
+    dim3 grid((unsigned)((nthreads + BLOCK - 1) / BLOCK), (unsigned)nt);
+    k2_edgeflux_ldg<T, VEC, UNROLL, BLOCK><<<grid, BLOCK, sizeof(double) * nz, s>>>(u, v, dz, arc1, arc2, eflux, nz,
+                                                                                    ncell, scale, use_scale, fill,
+                                                                                    has_fill);
+}
+
+template <typename T, int VEC>
+void dispatch_ldg(const T* u, const T* v, const double* dz, const double* arc1, const double* arc2, double* eflux, int nt,
+                  int nz, int64_t ncell, double scale, int use_scale, T fill, int has_fill, const K2Options& opt,
+                  cudaStream_t s) {
+    const int unroll = opt.unroll > 0 ? opt.unroll : 5;
+    const int block = opt.block > 0 ? opt.block : 256;
+#define NFX_K2_CASE(U, B)                                                                                          \
+    if (unroll == U && block == B) {                                                                               \
+        launch_ldg<T, VEC, U, B>(u, v, dz, arc1, arc2, eflux, nt, nz, ncell, scale, use_scale, fill, has_fill, s); \
+        return;                                                                                                    \
+    }
+    NFX_K2_CASE(5, 256)
+    NFX_K2_CASE(3, 256)
+    NFX_K2_CASE(8, 256)
+    NFX_K2_CASE(15, 256)
+    NFX_K2_CASE(5, 128)
+    NFX_K2_CASE(8, 128)
+    NFX_K2_CASE(15, 128)
+    NFX_K2_CASE(5, 512)
+    NFX_K2_CASE(3, 512)
+#undef NFX_K2_CASE
+    throw Error(NFX_E_INVALID, "edgeflux: unsupported (unroll, block) option pair");
+}
+
+// ---- (ncell,4) layout of field.py:209-223 -------------------------------------------------------------
+__global__ void k_to_cell_by_cell(const double* __restrict__ eflux, int ny, int nx, double* __restrict__ iv) {
+    const int64_t ncell = (int64_t)ny * nx;
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncell) return;
+    const int64_t t = blockIdx.y;
+    const double* eU = eflux + t * 2 * ncell;
+    const double* eV = eU + ncell;
+    const int64_t j = c / nx, i = c - j * nx;
+    const double south = j >= 1 ? eV[c - nx] : 0.0;          // row 0 never written (field.py:61,219)
+    const double west = i >= 1 ? eU[c - 1] : eU[c + nx - 1];  // x-periodic (field.py:223)
+    double2* o = reinterpret_cast<double2*>(iv + (t * ncell + c) * 4);
+    o[0] = make_double2(south, eU[c]);
+    o[1] = make_double2(eV[c], west);
+}
+
+__global__ void k_absmax(const double* __restrict__ x, int64_t n, unsigned long long* __restrict__ out) {
+    double m = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double a = fabs(x[i]);
+        if (a > m) m = a;  // NaN never wins
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(out, (unsigned long long)__double_as_longlong(m));
+}
+
+}  // namespace
+
+void edgeflux_assemble(const void* u, const void* v, int dtype, const double* thickness, const double* arc1,
+                       const double* arc2, int nt, int nz, int64_t ncell, int sverdrup, double fill, double* eflux,
+                       const K2Options& opt, cudaStream_t s) {
+    NFX_REQUIRE(u && v && thickness && arc1 && arc2 && eflux, "edgeflux: NULL pointer");
+    NFX_REQUIRE(nt >= 0 && nz > 0 && ncell > 0, "edgeflux: bad sizes");
+    NFX_REQUIRE(dtype == NFX_F64 || dtype == NFX_F32, "edgeflux: dtype must be NFX_F64 or NFX_F32");
+    NFX_REQUIRE(nt <= 65535, "edgeflux: at most 65535 time steps per call");
+    NFX_REQUIRE(nz <= 6000, "edgeflux: at most 6000 levels");
+    if (nt == 0) return;
+    const double scale = 6371000.0 / 1.e6;  // field.py:12,226
+    const int has_fill = !(fill != fill);
+    const uintptr_t addr_bits = ((uintptr_t)u) | ((uintptr_t)v) | ((uintptr_t)eflux);
+    const bool aligned16 = (addr_bits & 15) == 0;
+    const bool aligned32 = (addr_bits & 31) == 0 && opt.variant != NFX_K2_LDG128;
+    if (dtype == NFX_F64) {
+        const double* pu = (const double*)u;
+        const double* pv = (const double*)v;
+        if (aligned32 && ncell % 4 == 0)
+            dispatch_ldg<double, 4>(pu, pv, thickness, arc1, arc2, eflux, nt, nz, ncell, scale, sverdrup, fill,
+                                    has_fill, opt, s);
+        else if (aligned16 && ncell % 2 == 0)
+            dispatch_ldg<double, 2>(pu, pv, thickness, arc1, arc2, eflux, nt, nz, ncell, scale, sverdrup, fill,
+                                    has_fill, opt, s);
+        else
+            dispatch_ldg<double, 1>(pu, pv, thickness, arc1, arc2, eflux, nt, nz, ncell, scale, sverdrup, fill,
+                                    has_fill, opt, s);
+    } else {
+        const float* pu = (const float*)u;
+        const float* pv = (const float*)v;
+        if (aligned32 && ncell % 8 == 0)
+            dispatch_ldg<float, 8>(pu, pv, thickness, arc1, arc2, eflux, nt, nz, ncell, scale, sverdrup, (float)fill,
+                                   has_fill, opt, s);
+        else if (aligned16 && ncell % 4 == 0)
+            dispatch_ldg<float, 4>(pu, pv, thickness, arc1, arc2, eflux, nt, nz, ncell, scale, sverdrup, (float)fill,
+                                   has_fill, opt, s);
+        else
+            dispatch_ldg<float, 1>(pu, pv, thickness, arc1, arc2, eflux, nt, nz, ncell, scale, sverdrup, (float)fill,
+                                   has_fill, opt, s);
+    }
+    count_launch();
+    NFX_CUDA(cudaGetLastError());
+}
+
+void edgeflux_to_cell_by_cell(const double* eflux, int nt, int ny, int nx, double* iv, cudaStream_t s) {
+    NFX_REQUIRE(eflux && iv, "to_cell_by_cell: NULL pointer");
+    NFX_REQUIRE(nt >= 0 && ny > 0 && nx > 0 && nt <= 65535, "to_cell_by_cell: bad sizes");
+    if (nt == 0) return;
+    const int64_t ncell = (int64_t)ny * nx;
+    dim3 grid((unsigned)((ncell + 255) / 256), (unsigned)nt);
+    k_to_cell_by_cell<<<grid, 256, 0, s>>>(eflux, ny, nx, iv);
+    count_launch();
+    NFX_CUDA(cudaGetLastError());
+}
+
+void edgeflux_absmax(const double* eflux, int nt, int64_t ncell, double* result_host, cudaStream_t s) {
+    NFX_REQUIRE(eflux && result_host, "absmax: NULL pointer");
+    DevBuf<unsigned long long> d;
+    d.alloc(1);
+    NFX_CUDA(cudaMemsetAsync(d.p, 0, sizeof(unsigned long long), s));
+    const int64_t n = (int64_t)nt * 2 * ncell;
+    if (n > 0) {
+        k_absmax<<<148 * 8, 256, 0, s>>>(eflux, n, d.p);
+        count_launch();
+        NFX_CUDA(cudaGetLastError());
+    }
+    unsigned long long bits = 0;
+    NFX_CUDA(cudaMemcpyAsync(&bits, d.p, sizeof bits, cudaMemcpyDeviceToHost, s));
+    NFX_CUDA(cudaStreamSynchronize(s));
+    double r;
+    memcpy(&r, &bits, sizeof r);
+    *result_host = r;
+}
+
+}  // namespace nfx

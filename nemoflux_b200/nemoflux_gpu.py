@@ -1,0 +1,362 @@
+"""nemoflux_gpu -- the B200 replacement for the pieces of ``mint`` nemoflux uses, plus the batched
+transect-flux path.
+
+Mirrors the reference's operator interface (same method names, argument meaning and error behaviour):
+
+    reference (mint)                                  here
+    ------------------------------------------------  ------------------------------------------------
+    g = mint.Grid(); g.setPoints(points)              g = Grid(); g.setPoints(points)   horizgrid.py:23-24
+    g.getNumberOfCells()                              g.getNumberOfCells()              horizgrid.py:30
+    p = mint.PolylineIntegral(); p.setGrid(g)         p = PolylineIntegral(); p.setGrid(g)    field.py:45-46
+    p.buildLocator(numCellsPerBucket=128,             p.buildLocator(...)  (or p.build(g))    field.py:47
+                   periodX=360., enableFolding=False)
+    p.computeWeights(xyz, counterclock=False)         p.computeWeights(xyz, counterclock=False) field.py:48
+    p.getIntegral(data, mint.CELL_BY_CELL_DATA)       p.getIntegral(data, CELL_BY_CELL_DATA)  field.py:102
+                                                      p.computeIntegral(edgeData)  (same thing)
+
+New, batched (what the fluxplot.py:51-59 loop does, for all transects and time steps at once):
+
+    p.computeWeights([xyz0, xyz1, ...])      many transects, one locator
+    p.fluxSeries(u, v, thickness, arc1, arc2, sverdrup) -> (nt, M)
+
+All compute runs in libnemoflux_gpu.so (hand-written sm_100a CUDA) through ctypes; torch only owns
+device buffers and streams.  There is no CPU fallback.
+"""
+import ctypes
+
+import numpy
+
+from . import _lib
+from ._lib import NFX_CELL_BY_CELL_DATA as CELL_BY_CELL_DATA  # noqa: F401  (mint.CELL_BY_CELL_DATA)
+
+_ORDERS = {'list': _lib.NFX_ORDER_LIST, 'map': _lib.NFX_ORDER_MAP}
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def _np_ptr(a):
+    return ctypes.c_void_p(a.ctypes.data)
+
+
+def _t_ptr(t):
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _stream_ptr():
+    return ctypes.c_void_p(_torch().cuda.current_stream().cuda_stream)
+
+
+def _dtype_code(dtype_name):
+    if dtype_name in ('float64', 'torch.float64'):
+        return _lib.NFX_F64
+    if dtype_name in ('float32', 'torch.float32'):
+        return _lib.NFX_F32
+    raise TypeError(f'uo/vo must be float64 or float32, got {dtype_name}')
+
+
+class Grid(object):
+    """mint.Grid: an unstructured collection of quads, 4 private vertices per cell"""
+
+    def __init__(self):
+        self._h = ctypes.c_void_p()
+        _lib.call('nfx_grid_new', ctypes.byref(self._h))
+        self._points = None
+
+    def __del__(self):
+        try:
+            if self._h:
+                _lib.load().nfx_grid_del(ctypes.byref(self._h))
+        except Exception:
+            pass
+
+    def setPoints(self, points):
+        """points: (ncells, 4, 3) float64, vertices SW, SE, NE, NW as (lon deg, lat deg, ignored)"""
+        pts = numpy.ascontiguousarray(points, numpy.float64)
+        if pts.ndim != 3 or pts.shape[1:] != (4, 3):
+            raise ValueError(f'points must have shape (ncells, 4, 3), got {pts.shape}')
+        _lib.call('nfx_grid_set_points', ctypes.byref(self._h), pts.shape[0], _np_ptr(pts))
+        self._points = pts
+
+    def setCGridShape(self, ny, nx):
+        """structured shape behind the cell ids (cell = j*nx + i); enables the compact flux layout"""
+        _lib.call('nfx_grid_set_cgrid_shape', ctypes.byref(self._h), int(ny), int(nx))
+
+    def getNumberOfCells(self):
+        n = ctypes.c_int64()
+        _lib.call('nfx_grid_get_num_cells', ctypes.byref(self._h), ctypes.byref(n))
+        return n.value
+
+    def getPoints(self):
+        return self._points
+
+
+class PolylineIntegral(object):
+    """mint.PolylineIntegral for one transect or a batch of transects sharing one locator"""
+
+    def __init__(self):
+        self._h = ctypes.c_void_p()
+        _lib.call('nfx_pli_new', ctypes.byref(self._h))
+        self._grid = None
+        self._batched = False
+
+    def __del__(self):
+        try:
+            if self._h:
+                _lib.load().nfx_pli_del(ctypes.byref(self._h))
+        except Exception:
+            pass
+
+    # -- mint interface -----------------------------------------------------------------------------
+    def setGrid(self, grid):
+        if not isinstance(grid, Grid):
+            raise TypeError('setGrid expects a nemoflux_gpu.Grid')
+        _lib.call('nfx_pli_set_grid', ctypes.byref(self._h), grid._h)
+        self._grid = grid
+
+    def buildLocator(self, numCellsPerBucket=128, periodX=360., enableFolding=False):
+        _lib.call('nfx_pli_build_locator', ctypes.byref(self._h), int(numCellsPerBucket), float(periodX),
+                  int(bool(enableFolding)))
+
+    def build(self, grid, periodX=360.):
+        """setGrid + buildLocator, once per grid; every transect shares the locator"""
+        self.setGrid(grid)
+        self.buildLocator(numCellsPerBucket=128, periodX=periodX, enableFolding=False)
+
+    def computeWeights(self, xyz, counterclock=False):
+        """xyz: one polyline (npoints, 3), or a sequence of polylines [(n0,3), (n1,3), ...]"""
+        try:
+            single = numpy.asarray(xyz, numpy.float64).ndim == 2
+        except ValueError:      # ragged sequence of polylines
+            single = False
+        lines = [xyz] if single else list(xyz)
+        arrs = []
+        for ln in lines:
+            a = numpy.ascontiguousarray(ln, numpy.float64)
+            if a.ndim != 2 or a.shape[1] != 3:
+                raise ValueError(f'a polyline must have shape (npoints, 3), got {a.shape}')
+            arrs.append(a)
+        offsets = numpy.zeros(len(arrs) + 1, numpy.int32)
+        for i, a in enumerate(arrs):
+            offsets[i + 1] = offsets[i] + a.shape[0]
+        allpts = numpy.concatenate(arrs, axis=0) if arrs else numpy.zeros((0, 3))
+        allpts = numpy.ascontiguousarray(allpts, numpy.float64)
+        _lib.call('nfx_pli_compute_weights_batch', ctypes.byref(self._h), len(arrs), _np_ptr(offsets),
+                  _np_ptr(allpts), int(bool(counterclock)))
+        self._batched = not single
+        return 0
+
+    def getIntegral(self, data, placement=CELL_BY_CELL_DATA, order='map'):
+        """data: (ncells, 4) float64 host array.  One transect -> float; a batch -> (M,) array"""
+        d = numpy.ascontiguousarray(data, numpy.float64)
+        ncell = self._grid.getNumberOfCells() if self._grid else -1
+        if d.size != ncell * 4:
+            raise ValueError(f'data must hold ncells*4 = {ncell * 4} values, got {d.size}')
+        m = self.getNumberOfTransects()
+        res = numpy.zeros(max(m, 1), numpy.float64)
+        _lib.call('nfx_pli_get_integrals', ctypes.byref(self._h), _np_ptr(d), int(placement), _ORDERS[order],
+                  _np_ptr(res))
+        if self._batched:
+            return res[:m]
+        return float(res[0])
+
+    computeIntegral = getIntegral
+
+    # -- inspection -----------------------------------------------------------------------------------
+    def getNumberOfTransects(self):
+        n = ctypes.c_int()
+        _lib.call('nfx_pli_get_num_transects', ctypes.byref(self._h), ctypes.byref(n))
+        return n.value
+
+    def getSubsegments(self):
+        """dict of arrays in emission order (transect, segment, ta, cell, image) + 'offsets' (M+1)"""
+        n = ctypes.c_int64()
+        _lib.call('nfx_pli_get_num_subsegments', ctypes.byref(self._h), ctypes.byref(n))
+        n = n.value
+        m = self.getNumberOfTransects()
+        out = dict(offsets=numpy.zeros(m + 1, numpy.int64), cell=numpy.zeros(n, numpy.int64),
+                   seg=numpy.zeros(n, numpy.int32), img=numpy.zeros(n, numpy.int32), ta=numpy.zeros(n),
+                   tb=numpy.zeros(n), coeff=numpy.zeros(n), xia=numpy.zeros((n, 2)), xib=numpy.zeros((n, 2)),
+                   w=numpy.zeros((n, 4)))
+        _lib.call('nfx_pli_get_subsegments', ctypes.byref(self._h),
+                  *[_np_ptr(out[k]) for k in ('offsets', 'cell', 'seg', 'img', 'ta', 'tb', 'coeff', 'xia', 'xib', 'w')])
+        return out
+
+    def getWeights(self, transect=0):
+        """(cellIds, edgeIndices, weights) of one transect, 4 entries per sub-segment, emission order"""
+        s = self.getSubsegments()
+        a, b = s['offsets'][transect], s['offsets'][transect + 1]
+        cells = numpy.repeat(s['cell'][a:b], 4)
+        edges = numpy.tile(numpy.arange(4, dtype=numpy.int32), b - a)
+        return cells, edges, s['w'][a:b].reshape(-1).copy()
+
+    def getMap(self):
+        """mint's std::map view: dict(offsets (M+1), keys = cell*4+edge ascending per transect, w)"""
+        n = ctypes.c_int64()
+        _lib.call('nfx_pli_get_map_size', ctypes.byref(self._h), ctypes.byref(n))
+        m = self.getNumberOfTransects()
+        out = dict(offsets=numpy.zeros(m + 1, numpy.int64), keys=numpy.zeros(n.value, numpy.int64),
+                   w=numpy.zeros(n.value))
+        _lib.call('nfx_pli_get_map', ctypes.byref(self._h), _np_ptr(out['offsets']), _np_ptr(out['keys']),
+                  _np_ptr(out['w']))
+        return out
+
+    # -- batched device path ----------------------------------------------------------------------------
+    def integrate(self, eflux, order='map', out=None):
+        """K3: eflux cuda tensor (nt, 2*ncell) float64 -> (nt, M) cuda tensor"""
+        torch = _torch()
+        _require_cuda(eflux, torch.float64, 'eflux')
+        nt = eflux.shape[0]
+        m = self.getNumberOfTransects()
+        if out is None:
+            out = torch.empty((nt, m), dtype=torch.float64, device=eflux.device)
+        with torch.cuda.device(eflux.device):
+            _lib.call('nfx_pli_integrate', ctypes.byref(self._h), _t_ptr(eflux), nt, _ORDERS[order], _t_ptr(out),
+                      _stream_ptr())
+        return out
+
+    def integrateCellByCell(self, data, order='map', out=None):
+        """data cuda tensor (nt, ncell, 4) float64 -> (nt, M) cuda tensor (getIntegral for every step)"""
+        torch = _torch()
+        _require_cuda(data, torch.float64, 'data')
+        nt = data.shape[0]
+        m = self.getNumberOfTransects()
+        if out is None:
+            out = torch.empty((nt, m), dtype=torch.float64, device=data.device)
+        with torch.cuda.device(data.device):
+            _lib.call('nfx_pli_get_integrals_device', ctypes.byref(self._h), _t_ptr(data), nt, _ORDERS[order],
+                      _t_ptr(out), _stream_ptr())
+        return out
+
+    def fluxSeries(self, u, v, thickness, arc1, arc2, sverdrup=False, fill=float('nan'), order='map', eflux=None,
+                   out=None, chunk_steps=0):
+        """flux time series of every transect: (nt, M).
+
+        u, v: (nt, nz, ny, nx) [or (nz, ny, nx)] float64/float32, either cuda tensors (device path: K2+K3 on
+        the current stream, returns a cuda tensor) or host numpy arrays / CPU tensors (streams time chunks
+        through double-buffered device staging, returns a numpy array).  thickness (nz), arc1/arc2 (ncell)
+        on the same side as u, v.  Needs Grid.setCGridShape before computeWeights."""
+        torch = _torch()
+        if isinstance(u, torch.Tensor) and u.is_cuda:
+            return self._flux_series_device(u, v, thickness, arc1, arc2, sverdrup, fill, order, eflux, out)
+        return self._flux_series_host(u, v, thickness, arc1, arc2, sverdrup, fill, order, chunk_steps)
+
+    def _flux_series_device(self, u, v, thickness, arc1, arc2, sverdrup, fill, order, eflux, out):
+        torch = _torch()
+        if u.dim() == 3:
+            u, v = u.unsqueeze(0), v.unsqueeze(0)
+        if u.dim() != 4 or u.shape != v.shape:
+            raise ValueError("uo/vo shape does not match (t, z, y, x) or (z, y, x)")
+        for name, t in (('u', u), ('v', v)):
+            _require_cuda(t, u.dtype, name)
+        nt, nz, ny, nx = u.shape
+        ncell = ny * nx
+        for name, t, n in (('thickness', thickness, nz), ('arc1', arc1, ncell), ('arc2', arc2, ncell)):
+            _require_cuda(t, torch.float64, name)
+            if t.numel() != n:
+                raise ValueError(f'{name} must hold {n} values, got {t.numel()}')
+        m = self.getNumberOfTransects()
+        if eflux is None:
+            eflux = torch.empty((nt, 2 * ncell), dtype=torch.float64, device=u.device)
+        if out is None:
+            out = torch.empty((nt, m), dtype=torch.float64, device=u.device)
+        with torch.cuda.device(u.device):
+            _lib.call('nfx_flux_series', ctypes.byref(self._h), _t_ptr(u), _t_ptr(v), _dtype_code(str(u.dtype)),
+                      _t_ptr(thickness), _t_ptr(arc1), _t_ptr(arc2), nt, nz, int(bool(sverdrup)), float(fill),
+                      _ORDERS[order], _t_ptr(eflux), _t_ptr(out), _stream_ptr())
+        return out
+
+    def _flux_series_host(self, u, v, thickness, arc1, arc2, sverdrup, fill, order, chunk_steps):
+        torch = _torch()
+        keep = (u, v)  # keep pinned tensors alive while numpy views are in use
+        if isinstance(u, torch.Tensor):
+            u, v = u.numpy(), v.numpy()
+        u = numpy.asarray(u)
+        v = numpy.asarray(v)
+        if u.ndim == 3:
+            u, v = u[None], v[None]
+        if u.ndim != 4 or u.shape != v.shape or u.dtype != v.dtype:
+            raise ValueError("uo/vo shape does not match (t, z, y, x) or (z, y, x)")
+        if not (u.flags.c_contiguous and v.flags.c_contiguous):
+            u, v = numpy.ascontiguousarray(u), numpy.ascontiguousarray(v)
+        nt, nz, ny, nx = u.shape
+        ncell = ny * nx
+        th = numpy.ascontiguousarray(_to_numpy(thickness), numpy.float64)
+        a1 = numpy.ascontiguousarray(_to_numpy(arc1), numpy.float64).reshape(-1)
+        a2 = numpy.ascontiguousarray(_to_numpy(arc2), numpy.float64).reshape(-1)
+        if th.size != nz or a1.size != ncell or a2.size != ncell:
+            raise ValueError('thickness/arc1/arc2 sizes do not match uo')
+        m = self.getNumberOfTransects()
+        out = numpy.zeros((nt, m), numpy.float64)
+        _lib.call('nfx_flux_series_host', ctypes.byref(self._h), _np_ptr(u), _np_ptr(v), _dtype_code(str(u.dtype)),
+                  _np_ptr(th), _np_ptr(a1), _np_ptr(a2), nt, nz, int(bool(sverdrup)), float(fill), _ORDERS[order],
+                  int(chunk_steps), _np_ptr(out))
+        del keep
+        return out
+
+
+def _to_numpy(x):
+    torch = _torch()
+    if isinstance(x, torch.Tensor):
+        return x.detach().cpu().numpy()
+    return numpy.asarray(x)
+
+
+def _require_cuda(t, dtype, name):
+    torch = _torch()
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise TypeError(f'{name} must be a CUDA tensor (there is no CPU fallback)')
+    if t.dtype != dtype:
+        raise TypeError(f'{name} must have dtype {dtype}, got {t.dtype}')
+    if not t.is_contiguous():
+        raise ValueError(f'{name} must be contiguous')
+
+
+# -- K2 as a free function (Field.readField + Field.computeIntegratedFlux for many time steps) ------------
+def edgeFluxAssemble(u, v, thickness, arc1, arc2, sverdrup=False, fill=float('nan'), out=None):
+    """u, v cuda (nt, nz, ny, nx) or (nt, nz, ncell); returns eflux cuda (nt, 2*ncell): [eU | eV] signed"""
+    torch = _torch()
+    for name, t in (('u', u), ('v', v)):
+        _require_cuda(t, u.dtype, name)
+    if u.shape != v.shape or u.dim() not in (3, 4):
+        raise ValueError('u and v must both be (nt, nz, ny, nx) or (nt, nz, ncell)')
+    nt, nz = u.shape[0], u.shape[1]
+    ncell = int(numpy.prod(u.shape[2:]))
+    for name, t, n in (('thickness', thickness, nz), ('arc1', arc1, ncell), ('arc2', arc2, ncell)):
+        _require_cuda(t, torch.float64, name)
+        if t.numel() != n:
+            raise ValueError(f'{name} must hold {n} values, got {t.numel()}')
+    if out is None:
+        out = torch.empty((nt, 2 * ncell), dtype=torch.float64, device=u.device)
+    with torch.cuda.device(u.device):
+        _lib.call('nfx_edgeflux_assemble', _t_ptr(u), _t_ptr(v), _dtype_code(str(u.dtype)), _t_ptr(thickness),
+                  _t_ptr(arc1), _t_ptr(arc2), nt, nz, ncell, int(bool(sverdrup)), float(fill), _t_ptr(out),
+                  _stream_ptr())
+    return out
+
+
+def edgeFluxToCellByCell(eflux, ny, nx, out=None):
+    """compact (nt, 2*ncell) -> mint's (nt, ncell, 4) integratedVelocity layout (field.py:209-223)"""
+    torch = _torch()
+    _require_cuda(eflux, torch.float64, 'eflux')
+    nt = eflux.shape[0]
+    if eflux.shape[1] != 2 * ny * nx:
+        raise ValueError('eflux must be (nt, 2*ny*nx)')
+    if out is None:
+        out = torch.empty((nt, ny * nx, 4), dtype=torch.float64, device=eflux.device)
+    with torch.cuda.device(eflux.device):
+        _lib.call('nfx_edgeflux_to_cell_by_cell', _t_ptr(eflux), nt, ny, nx, _t_ptr(out), _stream_ptr())
+    return out
+
+
+def edgeFluxAbsMax(eflux):
+    """max |edge flux| over everything in eflux (Field.maxAbsFlux, field.py:230-234)"""
+    torch = _torch()
+    _require_cuda(eflux, torch.float64, 'eflux')
+    r = ctypes.c_double()
+    with torch.cuda.device(eflux.device):
+        _lib.call('nfx_edgeflux_absmax', _t_ptr(eflux), eflux.shape[0], eflux.shape[1] // 2, ctypes.byref(r),
+                  _stream_ptr())
+    return r.value

@@ -1,0 +1,31 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, 'tests', 'golden')
+
+
+def pytest_configure(config):
+    config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box with -m gpu)')
+
+
+@pytest.fixture(scope='session')
+def oracle():
+    """the CPU oracle (test infrastructure): builds oracle/libnfx_oracle.so on first use"""
+    from oracle import oracle as O
+    O.lib()
+    return O
+
+
+@pytest.fixture(scope='session')
+def gpu():
+    """the product module; fails loudly when the CUDA library or a device is missing"""
+    import torch
+    assert torch.cuda.is_available(), 'a CUDA device is required for -m gpu tests'
+    from nemoflux_b200 import nemoflux_gpu
+    return nemoflux_gpu

@@ -1,0 +1,316 @@
+"""-m gpu: the CUDA path (through the C ABI) against the CPU oracle on the same inputs.
+
+Bars: intersected-edge lists bit-exact (cell, segment, image ids equal; ta, tb, coefficient, parametric
+coordinates and weights equal bit for bit); K2 bit-exact against the sequential C restatement and
+<= 1e-12 against the reference's numpy formulation; flux series <= 1e-12 relative to sum |w*f|.
+"""
+import os
+
+import numpy
+import pytest
+
+from helpers import (README_C1, README_C2, README_LOOP, README_SINGULAR, SF_C2, assert_bitwise, random_transects, tr)
+
+pytestmark = pytest.mark.gpu
+
+FLUX_RTOL = 1.e-12      # north star: fluxes agree to fp64 relative error <= 1e-12
+
+
+def _build(gpu, points, ny=None, nx=None, periodX=360.):
+    g = gpu.Grid()
+    g.setPoints(points)
+    if ny:
+        g.setCGridShape(ny, nx)
+    p = gpu.PolylineIntegral()
+    p.build(g, periodX=periodX)
+    return g, p
+
+
+def _check_lists(oracle, gpu_pli, ogrid, transects, periodX=360., counterclock=False):
+    s = gpu_pli.getSubsegments()
+    mp = gpu_pli.getMap()
+    assert len(s['offsets']) == len(transects) + 1
+    total = 0
+    for m, xyz in enumerate(transects):
+        op = oracle.PolylineIntegral(ogrid, periodX)
+        op.computeWeights(xyz, counterclock=counterclock)
+        o = op.subsegs
+        a, b = s['offsets'][m], s['offsets'][m + 1]
+        assert b - a == len(o), f'transect {m}: {b - a} sub-segments on the GPU, {len(o)} in the oracle'
+        assert numpy.array_equal(s['cell'][a:b], o['cell']), f'transect {m}: cell ids differ'
+        assert numpy.array_equal(s['seg'][a:b], o['seg'])
+        assert numpy.array_equal(s['img'][a:b], o['img'])
+        for k in ('ta', 'tb', 'coeff', 'xia', 'xib', 'w'):
+            assert_bitwise(s[k][a:b], o[k], f'transect {m} {k}')
+        keys, ws = op.merged_map()
+        ma, mb = mp['offsets'][m], mp['offsets'][m + 1]
+        assert numpy.array_equal(mp['keys'][ma:mb], keys), f'transect {m}: map keys differ'
+        assert_bitwise(mp['w'][ma:mb], ws, f'transect {m} map weights')
+        # getWeights view
+        cells, edges, w = gpu_pli.getWeights(m)
+        oc, oe, ow = op.emission_list()
+        assert numpy.array_equal(cells, oc) and numpy.array_equal(edges, oe)
+        assert_bitwise(w, ow, 'emission weights')
+        total += len(o)
+    return total
+
+
+# ---------------------------------------------------------------------------------------------------
+# K1
+# ---------------------------------------------------------------------------------------------------
+def test_k1_c1_list_bit_exact(gpu, oracle):
+    g = oracle.DataGen()
+    P = g.points()
+    _, p = _build(gpu, P, g.ny, g.nx)
+    xyz = tr(README_C1)
+    p.computeWeights(xyz)
+    n = _check_lists(oracle, p, oracle.Grid(P), [xyz])
+    assert n == 59
+    s = p.getSubsegments()
+    assert list(numpy.bincount(s['seg'])) == [6, 15, 14, 12, 12]
+    assert list(s['cell'][:6]) == [72, 108, 144, 181, 217, 253]
+
+
+@pytest.mark.parametrize('delta', [(0., 0.), (20., 30.)])
+def test_k1_random_transects_bit_exact(gpu, oracle, delta):
+    g = oracle.DataGen(nx=90, ny=45, deltaDeg=delta)
+    P = g.points()
+    rng = numpy.random.default_rng(1234)
+    nodes = numpy.stack([g.xx, g.yy], -1) if delta == (0., 0.) else None
+    transects = random_transects(rng, 24, nodes=nodes)
+    transects += [tr(README_C1), tr(README_SINGULAR), tr(README_LOOP), tr(README_C2)]
+    # along grid lines (duplicate sub-segments, coefficient 0/1), across the date line, degenerate pieces
+    transects += [tr([(-180, -40), (180, -40)]), tr([(-60, -80), (-60, 80)]), tr([(170, 10), (190, 20)]),
+                  tr([(-190, -10), (-170, 5)]), tr([(10, 10), (10, 10)]), tr([(10, 10)]), tr([(0, 0), (4, 4), (4, 4), (8, 0)])]
+    _, p = _build(gpu, P, g.ny, g.nx)
+    p.computeWeights(transects)
+    n = _check_lists(oracle, p, oracle.Grid(P), transects)
+    assert n > 1000
+
+
+def test_k1_counterclock_and_no_period(gpu, oracle):
+    g = oracle.DataGen(nx=36, ny=18)
+    P = g.points()
+    xyz = tr(README_C1)
+    _, p = _build(gpu, P, periodX=0.)
+    p.computeWeights(xyz, counterclock=True)
+    _check_lists(oracle, p, oracle.Grid(P), [xyz], periodX=0., counterclock=True)
+
+
+def test_k1_filter_is_superset(gpu, oracle):
+    """the oracle's brute force (no candidate filter) agrees with the GPU's bounding-box traversal"""
+    g = oracle.DataGen(nx=48, ny=24, deltaDeg=(20., 30.))
+    P = g.points()
+    rng = numpy.random.default_rng(7)
+    transects = random_transects(rng, 6)
+    _, p = _build(gpu, P)
+    p.computeWeights(transects)
+    s = p.getSubsegments()
+    og = oracle.Grid(P)
+    for m, xyz in enumerate(transects):
+        ob = oracle.PolylineIntegral(og, 360., filter_mode=0)
+        ob.computeWeights(xyz)
+        a, b = s['offsets'][m], s['offsets'][m + 1]
+        assert numpy.array_equal(s['cell'][a:b], ob.subsegs['cell'])
+        assert_bitwise(s['w'][a:b], ob.subsegs['w'], 'weights vs brute force')
+
+
+def test_k1_empty_and_errors(gpu, oracle):
+    g = oracle.DataGen()
+    grid, p = _build(gpu, g.points())
+    p.computeWeights([])
+    assert p.getNumberOfTransects() == 0
+    assert p.getSubsegments()['cell'].size == 0
+    # a transect entirely outside the grid gives no sub-segments and integral 0
+    p.computeWeights(tr([(0, 100), (10, 120)]))
+    assert p.getSubsegments()['cell'].size == 0
+    assert p.getIntegral(numpy.ones((grid.getNumberOfCells(), 4))) == 0.0
+    with pytest.raises(ValueError):
+        p.computeWeights(numpy.zeros((3, 2)))
+    with pytest.raises(ValueError):
+        p.getIntegral(numpy.ones(5))
+    q = gpu.PolylineIntegral()
+    with pytest.raises(RuntimeError):
+        q.computeWeights(tr(README_C1))          # setGrid/buildLocator missing
+    with pytest.raises(RuntimeError):
+        q.buildLocator()
+
+
+# ---------------------------------------------------------------------------------------------------
+# K2
+# ---------------------------------------------------------------------------------------------------
+def _rand_uv(rng, nt, nz, ny, nx, dtype, nan_frac=0.2):
+    u = rng.standard_normal((nt, nz, ny, nx)).astype(dtype)
+    v = rng.standard_normal((nt, nz, ny, nx)).astype(dtype)
+    u[rng.random(u.shape) < nan_frac] = numpy.nan
+    v[rng.random(v.shape) < nan_frac] = numpy.nan
+    return u, v
+
+
+@pytest.mark.parametrize('shape', [(3, 7, 9, 11), (2, 75, 12, 20), (2, 5, 10, 13), (4, 10, 16, 32), (1, 1, 3, 5)])
+@pytest.mark.parametrize('dtype', [numpy.float64, numpy.float32])
+@pytest.mark.parametrize('sverdrup', [False, True])
+def test_k2_bit_exact_vs_sequential_oracle(gpu, oracle, shape, dtype, sverdrup):
+    import torch
+    nt, nz, ny, nx = shape
+    rng = numpy.random.default_rng(nt * 1000 + nz * 10 + nx)
+    u, v = _rand_uv(rng, nt, nz, ny, nx, dtype)
+    th = rng.uniform(0.5, 20., nz)
+    arc1 = rng.uniform(1e-3, 2e-2, ny * nx)
+    arc2 = rng.uniform(1e-3, 2e-2, ny * nx)
+    d = 'cuda'
+    ef = gpu.edgeFluxAssemble(torch.from_numpy(u).to(d), torch.from_numpy(v).to(d), torch.from_numpy(th).to(d),
+                              torch.from_numpy(arc1).to(d), torch.from_numpy(arc2).to(d), sverdrup=sverdrup)
+    iv = gpu.edgeFluxToCellByCell(ef, ny, nx).cpu().numpy()
+    efh = ef.cpu().numpy()
+    for t in range(nt):
+        iV, eU, eV = oracle.edgeflux_step_c(u[t], v[t], th, arc1, arc2, sverdrup)
+        assert_bitwise(efh[t, :ny * nx], eU, f'eU t={t}')
+        assert_bitwise(efh[t, ny * nx:], eV, f'eV t={t}')
+        assert_bitwise(iv[t], iV, f'iV t={t}')
+        # the reference's numpy formulation (tensordot) differs only by summation order
+        U = oracle.read_field(u[t].astype(numpy.float64), th)
+        V = oracle.read_field(v[t].astype(numpy.float64), th)
+        arc = numpy.zeros((ny * nx, 4))
+        arc[:, 1], arc[:, 2] = arc1, arc2
+        iVn, _, _ = oracle.integrated_flux(U, V, arc, sverdrup)
+        scale = numpy.abs(iVn).max() + 1e-300
+        assert numpy.abs(iv[t] - iVn).max() <= 1e-13 * scale * nz
+    assert gpu.edgeFluxAbsMax(ef) == numpy.abs(efh).max()
+
+
+def test_k2_fill_value(gpu, oracle):
+    import torch
+    rng = numpy.random.default_rng(5)
+    u, v = _rand_uv(rng, 2, 6, 8, 10, numpy.float64, nan_frac=0.)
+    u[rng.random(u.shape) < 0.3] = 1.e20       # raw _FillValue of datagen.py:191
+    v[rng.random(v.shape) < 0.3] = 1.e20
+    th = rng.uniform(1., 2., 6)
+    a1 = rng.uniform(.01, .02, 80)
+    a2 = rng.uniform(.01, .02, 80)
+    d = 'cuda'
+    ef = gpu.edgeFluxAssemble(torch.from_numpy(u).to(d), torch.from_numpy(v).to(d), torch.from_numpy(th).to(d),
+                              torch.from_numpy(a1).to(d), torch.from_numpy(a2).to(d), fill=1.e20).cpu().numpy()
+    for t in range(2):
+        _, eU, eV = oracle.edgeflux_step_c(u[t], v[t], th, a1, a2, False, fill=1.e20)
+        assert_bitwise(ef[t, :80], eU)
+        assert_bitwise(ef[t, 80:], eV)
+    assert numpy.abs(ef).max() < 1e3
+
+
+def test_k2_golden_reference_outputs(gpu):
+    """inputs/outputs produced by the reference's own Field.readField/computeIntegratedFlux code"""
+    import torch
+    from conftest import GOLDEN
+    d = 'cuda'
+    for ti in (0, 1):
+        for sv in (0, 1):
+            g = numpy.load(os.path.join(GOLDEN, f'rot24x12_t{ti}_sv{sv}.npz'))
+            u, v = g['u'], g['v']                      # (nt, nz, ny, nx) with NaN land
+            nt, nz, ny, nx = u.shape
+            th = g['thickness']
+            arc = g['arcLengths']
+            ef = gpu.edgeFluxAssemble(torch.from_numpy(u).to(d), torch.from_numpy(v).to(d),
+                                      torch.from_numpy(th).to(d), torch.from_numpy(arc[:, 1].copy()).to(d),
+                                      torch.from_numpy(arc[:, 2].copy()).to(d), sverdrup=bool(sv))
+            iv = gpu.edgeFluxToCellByCell(ef, ny, nx).cpu().numpy()[ti]
+            ref = g['iV']
+            assert numpy.abs(iv - ref).max() <= 1e-13 * numpy.abs(ref).max()
+            efh = ef.cpu().numpy()[ti]
+            assert numpy.allclose(numpy.abs(efh[:ny * nx]), g['absEU'], rtol=1e-13, atol=0)
+            assert abs(gpu.edgeFluxAbsMax(ef[ti:ti + 1]) - float(g['maxAbsFlux'])) <= 1e-13 * float(g['maxAbsFlux'])
+
+
+# ---------------------------------------------------------------------------------------------------
+# K3 and the whole path
+# ---------------------------------------------------------------------------------------------------
+def _series_gpu(gpu, P, ny, nx, transects, u, v, th, arc, sverdrup=False, order='map', host=False):
+    import torch
+    _, p = _build(gpu, P, ny, nx)
+    p.computeWeights(transects)
+    if host:
+        return p, p.fluxSeries(u, v, th, arc[:, 1].copy(), arc[:, 2].copy(), sverdrup=sverdrup, order=order,
+                               chunk_steps=3)
+    d = 'cuda'
+    out = p.fluxSeries(torch.from_numpy(u).to(d), torch.from_numpy(v).to(d), torch.from_numpy(th).to(d),
+                       torch.from_numpy(arc[:, 1].copy()).to(d), torch.from_numpy(arc[:, 2].copy()).to(d),
+                       sverdrup=sverdrup, order=order)
+    return p, out.cpu().numpy()
+
+
+def _l1_scale(oracle, P, transects, u, v, th, arc, sverdrup):
+    """sum |w*f| per (t, transect): the scale against which flux errors are measured"""
+    og = oracle.Grid(P)
+    nt = u.shape[0]
+    out = numpy.zeros((nt, len(transects)))
+    plis = []
+    for xyz in transects:
+        op = oracle.PolylineIntegral(og)
+        op.computeWeights(xyz)
+        plis.append(op.merged_map())
+    for t in range(nt):
+        iV, _, _ = oracle.edgeflux_step_c(u[t], v[t], th, arc[:, 1].copy(), arc[:, 2].copy(), sverdrup)
+        f = iV.reshape(-1)
+        for m, (keys, ws) in enumerate(plis):
+            out[t, m] = numpy.abs(ws * f[keys]).sum()
+    return out
+
+
+def test_known_answers_readme(gpu, oracle):
+    # README.md:26-39: 360
+    g = oracle.DataGen()
+    P, arc = g.points(), oracle.arc_lengths(g.points())
+    u, v = g.uv('x')
+    _, s = _series_gpu(gpu, P, g.ny, g.nx, [tr(README_C1)], u, v, g.thickness(), arc)
+    assert abs(s[0, 0] - 360.) <= 1e-12 * 360.
+    # README.md:50-56: 0.5, node to node around a singular stream function
+    u, v = g.uv('arctan2(y, x+180)/(2*pi)')
+    _, s = _series_gpu(gpu, P, g.ny, g.nx, [tr(README_SINGULAR)], u, v, g.thickness(), arc)
+    assert abs(s[0, 0] - 0.5) <= 2e-15
+    # README.md:65-68: closed loop, zero to machine accuracy
+    g = oracle.DataGen(nx=360, ny=180)
+    P, arc = g.points(), oracle.arc_lengths(g.points())
+    u, v = g.uv('cos(2*pi*y/360) + sin(2*pi*x/360)')
+    _, s = _series_gpu(gpu, P, g.ny, g.nx, [tr(README_LOOP)], u, v, g.thickness(), arc)
+    assert abs(s[0, 0]) <= 1e-13
+
+
+@pytest.mark.parametrize('order', ['map', 'list'])
+@pytest.mark.parametrize('sverdrup', [False, True])
+def test_flux_series_vs_oracle(gpu, oracle, order, sverdrup):
+    g = oracle.DataGen(nx=72, ny=36, nz=5, nt=4, deltaDeg=(20., 30.))
+    P, arc = g.points(), oracle.arc_lengths(g.points())
+    u, v = g.uv(SF_C2)
+    rng = numpy.random.default_rng(99)
+    land = rng.random((g.nz, g.ny, g.nx)) < 0.15
+    u[:, land] = numpy.nan
+    v[:, land] = numpy.nan
+    transects = random_transects(rng, 12) + [tr(README_C2), tr(README_LOOP)]
+    th = g.thickness()
+    ref = oracle.flux_series(P, transects, u, v, th, sverdrup=sverdrup, order=order)
+    refc = oracle.flux_series(P, transects, u, v, th, sverdrup=sverdrup, order=order, use_c=True)
+    scale = _l1_scale(oracle, P, transects, u, v, th, arc, sverdrup)
+    p, s = _series_gpu(gpu, P, g.ny, g.nx, transects, u, v, th, arc, sverdrup=sverdrup, order=order)
+    assert s.shape == ref.shape == (4, 14)
+    assert (numpy.abs(s - ref) <= FLUX_RTOL * scale + 1e-300).all()
+    assert (numpy.abs(s - refc) <= FLUX_RTOL * scale + 1e-300).all()
+    # the host-buffer entry point (double-buffered staging) gives the same numbers as the device one
+    _, sh = _series_gpu(gpu, P, g.ny, g.nx, transects, u, v, th, arc, sverdrup=sverdrup, order=order, host=True)
+    assert numpy.array_equal(sh, s)
+    # mint-style getIntegral on the (ncell,4) array of one time step
+    iV, _, _ = oracle.edgeflux_step_c(u[1], v[1], th, arc[:, 1].copy(), arc[:, 2].copy(), sverdrup)
+    one = p.getIntegral(iV, order=order)
+    assert (numpy.abs(one - ref[1]) <= FLUX_RTOL * scale[1] + 1e-300).all()
+
+
+def test_c2_series_linear_in_time(gpu, oracle):
+    """BASELINE config 2 (README.md:89-91): flux(t) = flux(0)*(t+1)"""
+    g = oracle.DataGen(nx=360, ny=180, nz=10, nt=20, deltaDeg=(20., 30.))
+    P, arc = g.points(), oracle.arc_lengths(g.points())
+    u, v = g.uv(SF_C2)
+    p, s = _series_gpu(gpu, P, g.ny, g.nx, [tr(README_C2)], u, v, g.thickness(), arc)
+    assert p.getSubsegments()['cell'].size == 361
+    ref = oracle.flux_series(P, [tr(README_C2)], u, v, g.thickness())
+    assert numpy.abs(s - ref).max() <= 1e-12 * numpy.abs(ref).max()
+    assert numpy.allclose(s[:, 0] / s[0, 0], numpy.arange(1, 21), rtol=1e-12)
+    assert abs(s[0, 0] - 1.7386322852896516) <= 1e-11

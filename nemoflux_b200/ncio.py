@@ -1,0 +1,138 @@
+"""Minimal NetCDF access for the nemoflux file conventions (T.nc / U.nc / V.nc).
+
+The reference reads with xarray (field.py:22-35, horizgrid.py:12-15) and writes with netCDF4
+(datagen.py:168-208).  Neither is installed in this image, so this module uses netCDF4 when it is
+importable and falls back to ``scipy.io.netcdf_file`` (classic / 64-bit-offset NetCDF-3 only; a
+NetCDF-4/HDF5 file then raises a clear error).  Missing values (``_FillValue`` / ``missing_value``)
+are decoded to NaN like xarray's default ``mask_and_scale`` does, so ``fillna(0)`` semantics
+(field.py:157) carry over.
+"""
+import numpy
+
+
+class Variable(object):
+    def __init__(self, name, data, dims, attrs):
+        self.name, self._data, self.dimensions, self.attrs = name, data, tuple(dims), dict(attrs)
+        self.shape = tuple(data.shape)
+        self.dtype = data.dtype
+
+    def __getattr__(self, key):
+        try:
+            return self.__dict__['attrs'][key]
+        except KeyError:
+            raise AttributeError(key)
+
+    def __len__(self):
+        return self.shape[0] if self.shape else 0
+
+    def raw(self, idx=Ellipsis):
+        return numpy.asarray(self._data[idx])
+
+    def __getitem__(self, idx):
+        """values with missing data decoded to NaN (floating point variables only)"""
+        a = numpy.array(self._data[idx])
+        if a.dtype.kind == 'f':
+            for key in ('_FillValue', 'missing_value'):
+                if key in self.attrs:
+                    fv = numpy.asarray(self.attrs[key]).reshape(-1)[0]
+                    a[a == a.dtype.type(fv)] = numpy.nan
+        return a
+
+
+class Dataset(object):
+    """read-only view: ds['uo'] -> Variable; ds.attrs; ds.close()"""
+
+    def __init__(self, path):
+        self.path = path
+        self.variables = {}
+        self.attrs = {}
+        self._h = None
+        try:
+            import netCDF4
+        except ImportError:
+            netCDF4 = None
+        if netCDF4 is not None:
+            h = netCDF4.Dataset(path)
+            h.set_auto_maskandscale(False)
+            self._h = h
+            for name, var in h.variables.items():
+                attrs = {k: var.getncattr(k) for k in var.ncattrs()}
+                self.variables[name] = Variable(name, var, var.dimensions, attrs)
+            self.attrs = {k: h.getncattr(k) for k in h.ncattrs()}
+            return
+        with open(path, 'rb') as f:
+            magic = f.read(4)
+        if magic[:3] != b'CDF':
+            raise RuntimeError(f'{path}: not a classic NetCDF-3 file (magic {magic!r}); reading NetCDF-4/HDF5 files '
+                               'needs the netCDF4 package, which is not installed')
+        from scipy.io import netcdf_file
+        h = netcdf_file(path, 'r', mmap=True, maskandscale=False)
+        self._h = h
+        for name, var in h.variables.items():
+            attrs = {k: (v.decode() if isinstance(v, bytes) else v) for k, v in var._attributes.items()}
+            self.variables[name] = Variable(name, var.data, var.dimensions, attrs)
+        self.attrs = {k: (v.decode() if isinstance(v, bytes) else v) for k, v in h._attributes.items()}
+
+    def __getitem__(self, name):
+        return self.variables[name]
+
+    def __contains__(self, name):
+        return name in self.variables
+
+    def items(self):
+        return self.variables.items()
+
+    def close(self):
+        if self._h is not None:
+            self.variables = {}
+            try:
+                self._h.close()
+            except Exception:
+                pass
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+
+def open_dataset(path):
+    return Dataset(path)
+
+
+class Writer(object):
+    """createDimension / createVariable subset of netCDF4.Dataset(path, 'w') used by datagen.py:168-208"""
+
+    def __init__(self, path):
+        try:
+            import netCDF4
+            self._nc4 = netCDF4.Dataset(path, 'w')
+            self._h = None
+        except ImportError:
+            from scipy.io import netcdf_file
+            self._nc4 = None
+            self._h = netcdf_file(path, 'w', version=2)
+
+    def createDimension(self, name, size):
+        (self._nc4 or self._h).createDimension(name, size)
+
+    def createVariable(self, name, dtype, dims, fill_value=None, attrs=None, data=None):
+        if self._nc4 is not None:
+            v = self._nc4.createVariable(name, dtype, dims, fill_value=fill_value)
+        else:
+            v = self._h.createVariable(name, numpy.dtype(dtype), dims)
+            if fill_value is not None:
+                v._FillValue = numpy.array(fill_value, numpy.dtype(dtype))
+        for k, val in (attrs or {}).items():
+            setattr(v, k, val)
+        if data is not None:
+            v[:] = data
+        return v
+
+    def setAttr(self, name, value):
+        setattr(self._nc4 or self._h, name, value)
+
+    def close(self):
+        (self._nc4 or self._h).close()

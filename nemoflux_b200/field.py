@@ -1,0 +1,240 @@
+"""Field -- mirror of nemoflux/field.py with the compute step on the GPU.
+
+Same constructor, attributes and methods as the reference class (field.py:15-234):
+``Field(tFile, uFile, vFile, lonLatZPoints, sverdrup=False)``, ``timeIndex``, ``nt nz ny nx``, ``plis``,
+``thickness``, ``arcLengths``, ``edgeFluxesUArray / edgeFluxesVArray`` (absolute values, field.py:230-232),
+``integratedVelocity`` ((ncell,4), field.py:209-228), ``maxAbsFlux`` (running maximum, field.py:234),
+``update()``, ``getFluxText()``, ``getUV()``, ``readField()``.
+
+What differs: ONE locator is built per grid and shared by all transects (the reference builds one per
+transect, field.py:44-49); the vertical integration, edge-flux assembly and the transect integrals run in
+libnemoflux_gpu.so (K2, K3); ``fluxSeries()`` is new and evaluates every time step and transect in a few
+launches (the loop of fluxplot.py:51-59).  The VectorInterp arrow glyphs (field.py:71-95) are viz-only
+and not computed.
+"""
+import re
+
+import numpy
+
+from . import geo
+from . import ncio
+from . import timeobj
+from .horizgrid import HorizGrid
+from .latlonreader import LatLonReader  # noqa: F401  (re-exported like the reference module)
+from . import nemoflux_gpu
+
+EARTH_RADIUS = 6371000.0          # field.py:12
+
+
+class _TransectView(object):
+    """element of Field.plis: getIntegral(data, placement) of one transect of the shared batch (field.py:102)"""
+
+    def __init__(self, field, index):
+        self._field, self._index = field, index
+
+    def getIntegral(self, data, placement=nemoflux_gpu.CELL_BY_CELL_DATA):
+        return float(self._field.pli.getIntegral(data, placement)[self._index])
+
+    def getWeights(self):
+        return self._field.pli.getWeights(self._index)
+
+
+class Field(object):
+
+    def __init__(self, tFile, uFile, vFile, lonLatZPoints, sverdrup=False, verbose=True):
+        import torch
+        self.sverdrup = sverdrup
+        with ncio.open_dataset(tFile) as nc:
+            bounds_lat = nc['bounds_lat'][:]
+            bounds_lon = nc['bounds_lon'][:]
+            self.bounds_depth = nc['deptht_bounds'][:]
+        self.lonmin, self.lonmax = bounds_lon.min(), bounds_lon.max()
+        self.latmin, self.latmax = bounds_lat.min(), bounds_lat.max()
+        if verbose:
+            print(f'lon-lat box: {self.lonmin}, {self.latmin} -> {self.lonmax}, {self.latmax}')
+
+        self.timeIndex = 0
+        self.ncU = ncio.open_dataset(uFile)
+        self.ncV = ncio.open_dataset(vFile)
+        self.timeObj = timeobj.TimeObj(self.ncU)
+        self.nt, self.nz, self.ny, self.nx = self.getSizes()
+
+        # grid + ONE locator + all transects in one batch
+        self.device = torch.device('cuda', torch.cuda.current_device())
+        self.gr = HorizGrid(bounds_lon=bounds_lon, bounds_lat=bounds_lat)
+        self.pli = nemoflux_gpu.PolylineIntegral()
+        self.pli.build(self.gr.getMintGrid(), periodX=360.)
+        self.lonLatZPoints = [numpy.array(p, numpy.float64).reshape(-1, 3) for p in lonLatZPoints]
+        self.pli.computeWeights(self.lonLatZPoints, counterclock=False)
+        self.plis = [_TransectView(self, i) for i in range(len(self.lonLatZPoints))]
+
+        self.thickness = numpy.asarray(self.bounds_depth[:, 1] - self.bounds_depth[:, 0], numpy.float64)   # field.py:51
+
+        numCells = self.ny * self.nx
+        self.dx = min((self.lonmax - self.lonmin) / float(self.nx), (self.latmax - self.latmin) / float(self.ny))
+        self.arcLengths = numpy.zeros((numCells, 4), numpy.float64)
+        self.computeArcLengths()
+        self._d_thickness = torch.from_numpy(numpy.ascontiguousarray(self.thickness)).to(self.device)
+        self._d_arc1 = torch.from_numpy(numpy.ascontiguousarray(self.arcLengths[:, 1])).to(self.device)
+        self._d_arc2 = torch.from_numpy(numpy.ascontiguousarray(self.arcLengths[:, 2])).to(self.device)
+
+        self.edgeFluxesUArray = numpy.zeros((numCells,), numpy.float64)
+        self.edgeFluxesVArray = numpy.zeros((numCells,), numpy.float64)
+        self.integratedVelocity = numpy.zeros((numCells, 4), numpy.float64)
+        self.maxAbsFlux = 0.
+        self.fluxes = numpy.zeros(len(self.plis))
+
+        uVerticallyIntegrated, vVerticallyIntegrated = None, None
+        self.update()
+        if verbose:
+            print(f'max vertically integrated edge |flux|: {self.maxAbsFlux}')
+        self.buildEdgeUVGrids(bounds_lon, bounds_lat)
+
+    # ---- reference helpers -------------------------------------------------------------------------------
+    def getSizes(self):
+        nt, nz, ny, nx = 1, 1, 0, 0
+        shapeU = self.ncU['uo'].shape
+        if len(shapeU) == 4:
+            nt, nz, ny, nx = shapeU
+        elif len(shapeU) == 3:
+            nz, ny, nx = shapeU
+        elif len(shapeU) == 2:
+            ny, nx = shapeU
+        else:
+            raise RuntimeError("ERROR: uo's shape does not match (t, z, y, x), (z, y, x) or (y, x)")
+        return nt, nz, ny, nx
+
+    def buildEdgeUVGrids(self, bounds_lon, bounds_lat):
+        self.lonlat = numpy.zeros((self.ny, self.nx, 4, 3), numpy.float64)
+        self.lonlat[..., 0] = bounds_lon
+        self.lonlat[..., 1] = bounds_lat
+
+    def computeArcLengths(self):
+        self.arcLengths[:] = geo.cellArcLengths(self.gr.getPoints())
+
+    def _slab(self, nc, fieldName, t0, n):
+        """(n, nz, ny, nx) block of time steps with missing values as NaN (xarray semantics, field.py:149-157)"""
+        var = nc[fieldName]
+        try:
+            if len(var.shape) == 4:
+                a = var[t0:t0 + n]
+            elif len(var.shape) == 3:
+                a = var[...][None]
+            else:
+                a = var[...][None, None]
+        except Exception:
+            raise RuntimeError(f'ERROR: could not read {fieldName} field')
+        return numpy.ascontiguousarray(a)
+
+    def readField(self, nc, fieldName):
+        """vertically integrated field of the current time index, (ny, nx) host array (field.py:145-163);
+        computed by K2 with unit metric factors"""
+        import torch
+        a = torch.from_numpy(self._slab(nc, fieldName, self.timeIndex, 1)).to(self.device)
+        ones = torch.ones(self.ny * self.nx, dtype=torch.float64, device=self.device)
+        ef = nemoflux_gpu.edgeFluxAssemble(a, a, self._d_thickness, ones, ones)
+        return ef[0, :self.ny * self.nx].reshape(self.ny, self.nx).cpu().numpy()
+
+    def getUV(self):
+        return self.readField(self.ncU, 'uo'), self.readField(self.ncV, 'vo')
+
+    # ---- the compute step ----------------------------------------------------------------------------------
+    def update(self):
+        """edge fluxes and transect fluxes of self.timeIndex (field.py:112-120): K2 + K3 on the device"""
+        import torch
+        u = torch.from_numpy(self._slab(self.ncU, 'uo', self.timeIndex, 1)).to(self.device)
+        v = torch.from_numpy(self._slab(self.ncV, 'vo', self.timeIndex, 1)).to(self.device)
+        eflux = nemoflux_gpu.edgeFluxAssemble(u, v, self._d_thickness, self._d_arc1, self._d_arc2, sverdrup=self.sverdrup)
+        self.fluxes = self.pli.integrate(eflux).cpu().numpy()[0]
+        ncell = self.ny * self.nx
+        self.integratedVelocity[:] = nemoflux_gpu.edgeFluxToCellByCell(eflux, self.ny, self.nx)[0].cpu().numpy()
+        ef = eflux[0].abs().cpu().numpy()                     # from now on, edge fluxes are abs values (field.py:230)
+        self.edgeFluxesUArray[:] = ef[:ncell]
+        self.edgeFluxesVArray[:] = ef[ncell:]
+        self.maxAbsFlux = max(self.maxAbsFlux, nemoflux_gpu.edgeFluxAbsMax(eflux))
+
+    def computeIntegratedFlux(self, uVerticallyIntegrated, vVerticallyIntegrated):
+        """field.py:183-234 for callers that hold their own vertically integrated (ny, nx) fields"""
+        import torch
+        u = torch.from_numpy(numpy.ascontiguousarray(uVerticallyIntegrated, numpy.float64).reshape(1, 1, -1)).to(self.device)
+        v = torch.from_numpy(numpy.ascontiguousarray(vVerticallyIntegrated, numpy.float64).reshape(1, 1, -1)).to(self.device)
+        one = torch.ones(1, dtype=torch.float64, device=self.device)
+        eflux = nemoflux_gpu.edgeFluxAssemble(u, v, one, self._d_arc1, self._d_arc2, sverdrup=self.sverdrup)
+        ncell = self.ny * self.nx
+        self.integratedVelocity[:] = nemoflux_gpu.edgeFluxToCellByCell(eflux, self.ny, self.nx)[0].cpu().numpy()
+        ef = eflux[0].abs().cpu().numpy()
+        self.edgeFluxesUArray[:] = ef[:ncell]
+        self.edgeFluxesVArray[:] = ef[ncell:]
+        self.fluxes = self.pli.integrate(eflux).cpu().numpy()[0]
+        self.maxAbsFlux = max(self.maxAbsFlux, float(ef.max()))
+
+    def getFluxText(self):
+        """title text of the viewer (field.py:98-109): one %4.3g value per transect and the units"""
+        txt = ""
+        for totalFlux in self.fluxes:
+            txt += f"{totalFlux:4.3g}, "
+        txt += "(Sv) " if self.sverdrup else "(A m^2/s) "
+        return re.sub(r',\s*\(', ' (', txt)
+
+    def fluxSeries(self, chunk_steps=0):
+        """(nt, M) flux of every transect at every time step -- the loop of fluxplot.py:51-59 in a few launches.
+        Streams the time axis from the files through the host-buffer entry point of the C ABI."""
+        out = numpy.zeros((self.nt, len(self.plis)))
+        step_bytes = 8 * self.nz * self.ny * self.nx
+        n = chunk_steps if chunk_steps > 0 else max(1, min(self.nt, (1 << 30) // max(step_bytes, 1)))
+        for t0 in range(0, self.nt, n):
+            m = min(n, self.nt - t0)
+            u = self._slab(self.ncU, 'uo', t0, m)
+            v = self._slab(self.ncV, 'vo', t0, m)
+            out[t0:t0 + m] = self.pli.fluxSeries(u, v, self.thickness, self.arcLengths[:, 1].copy(),
+                                                 self.arcLengths[:, 2].copy(), sverdrup=self.sverdrup)
+        return out
+
+    def close(self):
+        self.ncU.close()
+        self.ncV.close()
+
+
+def parseLonLatPoints(text):
+    """'(lon0,lat0),(lon1,lat1),...'  ->  [polyline]        (the README.md:32 form, field.py:250)
+       '[(..),(..)],[(..),(..)]'      ->  [polyline, ...]   (the fluxviz.py:378 form)
+    each polyline an (n,3) array with z = 0"""
+    import ast
+    val = ast.literal_eval(text.strip())
+    if len(val) == 0:
+        raise RuntimeError('ERROR: empty list of target points')
+
+    def is_point(p):
+        return isinstance(p, (tuple, list)) and len(p) in (2, 3) and all(isinstance(c, (int, float)) for c in p)
+    lines = [val] if is_point(val[0]) else list(val)
+    out = []
+    for ln in lines:
+        out.append(numpy.array([(p[0], p[1], 0.0) for p in ln], numpy.float64))
+    return out
+
+
+def main(argv=None):
+    import argparse
+    ap = argparse.ArgumentParser(description='Compute fluxes')
+    ap.add_argument('-t', '--tFile', required=True, help='netcdf file holding the T-grid')
+    ap.add_argument('-u', '--uFile', required=True, help='netcdf file holding u data')
+    ap.add_argument('-v', '--vFile', required=True, help='netcdf file holding v data')
+    ap.add_argument('-l', '--lonLatPoints', default='', help='target points "(lon0, lat0), (lon1, lat1),..."')
+    ap.add_argument('-i', '--iFile', default='', help='alternatively read target points from text file')
+    ap.add_argument('-s', '--sverdrup', action='store_true')
+    a = ap.parse_args(argv)
+    if a.lonLatPoints:
+        pts = parseLonLatPoints(a.lonLatPoints)
+    elif a.iFile:
+        ll = LatLonReader(a.iFile).getLonLats()
+        pts = [numpy.array([(p[0], p[1], 0.) for p in ll])]
+    else:
+        raise RuntimeError('ERROR must provide either iFile or lonLatPoints!')
+    print(f'target points:\n {pts}')
+    f = Field(a.tFile, a.uFile, a.vFile, pts, a.sverdrup)
+    print(f'flux = {f.getFluxText()}')
+    return f
+
+
+if __name__ == '__main__':
+    main()

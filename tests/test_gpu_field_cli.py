@@ -1,0 +1,105 @@
+"""-m gpu: the reference-facing surface (Field / fluxviz / fluxplot on NetCDF files written by datagen)."""
+import os
+
+import numpy
+import pytest
+
+from conftest import GOLDEN
+from helpers import README_C1, README_C2, README_SINGULAR, SF_C2, tr
+
+pytestmark = pytest.mark.gpu
+
+
+def _files(tmp_path, *args):
+    from nemoflux_b200 import datagen
+    prefix = str(tmp_path) + '/'
+    datagen.cli(list(args) + [f'--prefix={prefix}'])
+    return prefix + 'T.nc', prefix + 'U.nc', prefix + 'V.nc'
+
+
+def test_field_simple_example_360(gpu, tmp_path, capsys):
+    """README.md:26-39 end to end: datagen --streamFunction="x", fluxviz ... -> 360"""
+    from nemoflux_b200 import fluxviz
+    T, U, V = _files(tmp_path, '--streamFunction=x')
+    fv = fluxviz.main(['-t', T, '-u', U, '-v', V, '--lonLatPoints=(-180,-70),(-160,-10),(-35,40),(20,-50),(60,50),(180,40)'])
+    f = fv.field
+    out = capsys.readouterr().out
+    assert 'flux =  360 (A m^2/s)' in out and 'lon-lat box: -180.0, -90.0 -> 180.0, 90.0' in out
+    assert f.getFluxText() == ' 360 (A m^2/s) '
+    assert (f.nt, f.nz, f.ny, f.nx) == (1, 1, 18, 36)
+    g = numpy.load(os.path.join(GOLDEN, 'c1_simple.npz'))       # the reference Field's own arrays
+    assert numpy.array_equal(f.arcLengths, g['arcLengths'])
+    assert numpy.abs(f.integratedVelocity - g['iV']).max() <= 1e-14 * numpy.abs(g['iV']).max()
+    assert numpy.allclose(f.edgeFluxesUArray, g['absEU'], rtol=1e-14) and numpy.allclose(f.edgeFluxesVArray, g['absEV'], rtol=1e-14)
+    assert abs(f.maxAbsFlux - 10.0) < 1e-12
+    assert abs(f.plis[0].getIntegral(f.integratedVelocity) - 360.) < 1e-10
+    U0, V0 = f.getUV()
+    assert numpy.allclose(U0, g['U'], rtol=1e-14) and numpy.allclose(V0, g['V'], rtol=1e-14)
+
+
+def test_field_singular_and_sverdrup(gpu, tmp_path):
+    from nemoflux_b200.field import Field
+    T, U, V = _files(tmp_path, '--streamFunction=arctan2(y, x+180)/(2*pi)')
+    f = Field(T, U, V, [tr(README_SINGULAR)], sverdrup=False, verbose=False)
+    assert f.getFluxText() == ' 0.5 (A m^2/s) '
+    fs = Field(T, U, V, [tr(README_SINGULAR), tr(README_C1)], sverdrup=True, verbose=False)
+    assert fs.getFluxText().endswith('(Sv) ')
+    assert abs(fs.fluxes[0] - 0.5 * 6.371) < 1e-14 and len(fs.plis) == 2
+    assert abs(fs.maxAbsFlux - 0.125 * 6.371) < 1e-14           # pictures/singular.png colour bar 0.125
+
+
+def test_fluxplot_series_and_time_stepping(gpu, oracle, tmp_path, capsys):
+    from nemoflux_b200 import fluxplot, fluxviz
+    T, U, V = _files(tmp_path, f'--streamFunction={SF_C2}', '--nx=72', '--ny=36', '--nz=5', '--nt=6', '--deltaDeg=20,30')
+    csv = str(tmp_path / 'series.csv')
+    pts = '[(-100,-70),(100,-70),(0,70)],[(-150,-20),(-20,35),(60,-40)]'
+    s = fluxplot.main(['-t', T, '-u', U, '-v', V, '-l', pts, '-o', csv])
+    assert s.shape == (6, 2)
+    d = oracle.DataGen(nx=72, ny=36, nz=5, nt=6, deltaDeg=(20., 30.))
+    u, v = d.uv(SF_C2)
+    ref = oracle.flux_series(d.points(), [tr([(-100, -70), (100, -70), (0, 70)]), tr([(-150, -20), (-20, 35), (60, -40)])],
+                             u, v, d.thickness())
+    assert numpy.abs(s - ref).max() <= 1e-12 * numpy.abs(ref).max()
+    rows = open(csv).read().strip().split('\n')
+    assert rows[0] == 'time,line0,line1' and len(rows) == 7
+    assert numpy.allclose([float(x) for x in rows[3].split(',')[1:]], s[2])
+    # the viewer's 't' key: one update per time index gives the same numbers as the batched series
+    fv = fluxviz.main(['-t', T, '-u', U, '-v', V, '-l', pts, '--allTimes'])
+    assert fv.field.timeIndex == 5 and numpy.allclose(fv.field.fluxes, s[5], rtol=1e-13)
+    fv.update('t')
+    assert fv.field.timeIndex == 0 and numpy.allclose(fv.field.fluxes, s[0], rtol=1e-13)
+    fv.update('T')
+    assert fv.field.timeIndex == 5
+    assert fv.field.maxAbsFlux >= numpy.abs(fv.field.edgeFluxesUArray).max()       # running maximum (field.py:234)
+    out = capsys.readouterr().out
+    assert out.count('flux = ') >= 6 and 'time index 5' in out
+
+
+def test_field_float32_and_land(gpu, oracle, tmp_path):
+    """real NEMO files: float32 uo/vo with _FillValue 1e20 over land -> zero flux there (README.md:118)"""
+    from nemoflux_b200 import ncio
+    from nemoflux_b200.field import Field
+    T, U, V = _files(tmp_path, f'--streamFunction={SF_C2}', '--nx=36', '--ny=18', '--nz=4', '--nt=2')
+    d = oracle.DataGen(nx=36, ny=18, nz=4, nt=2)
+    u, v = d.uv(SF_C2)
+    land = numpy.zeros((4, 18, 36), bool)
+    land[:, 5:9, 10:20] = True
+    land[3] = True
+    for fname, vname, a in ((U, 'uo', u), (V, 'vo', v)):
+        a32 = a.astype(numpy.float32)
+        a32[:, land] = numpy.float32(1.e20)
+        w = ncio.Writer(fname)
+        for name, n in (('t', 2), ('z', 4), ('y', 18), ('x', 36)):
+            w.createDimension(name, n)
+        w.createVariable(vname, 'float32', ('t', 'z', 'y', 'x'), fill_value=1.e20, data=a32)
+        w.close()
+    path = [tr([(-150, -50), (-20, 35), (60, -40), (170, 60)])]
+    f = Field(T, U, V, path, verbose=False)
+    s = f.fluxSeries(chunk_steps=1)
+    un = u.astype(numpy.float32).astype(numpy.float64)
+    vn = v.astype(numpy.float32).astype(numpy.float64)
+    un[:, land] = numpy.nan
+    vn[:, land] = numpy.nan
+    ref = oracle.flux_series(d.points(), path, un, vn, d.thickness())
+    assert numpy.abs(s - ref).max() <= 1e-12 * numpy.abs(ref).max()
+    assert numpy.isfinite(f.integratedVelocity).all() and (f.integratedVelocity.reshape(18, 36, 4)[6, 12] == 0).all()

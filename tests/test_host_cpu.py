@@ -1,0 +1,216 @@
+"""-m "not gpu": host-side logic of the package (no compute calls) -- C ABI exports, loud failure without a
+GPU, file formats, CLI flag parsing, time sharding with a 2-rank gloo group."""
+import json
+import os
+import re
+import subprocess
+import sys
+
+import numpy
+import pytest
+
+from conftest import GOLDEN, ROOT
+
+
+# ---- the C ABI -----------------------------------------------------------------------------------------
+def _declared_symbols():
+    text = open(os.path.join(ROOT, 'include', 'nemoflux_gpu.h')).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    return sorted(set(re.findall(r'\b(nfx_[a-z0-9_]+)\s*\(', text)))
+
+
+def test_library_exports_every_declared_symbol():
+    import ctypes
+    from nemoflux_b200 import _lib
+    names = _declared_symbols()
+    assert len(names) >= 30
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, f'declared in include/nemoflux_gpu.h but not exported: {missing}'
+    # the python binding covers the same set
+    bound = set(_lib.SIGNATURES) | {'nfx_last_error'}
+    assert set(names) == bound, set(names) ^ bound
+    assert _lib.load().nfx_version() >= 100
+
+
+def test_no_silent_cpu_fallback():
+    """without a CUDA device every entry point must fail loudly (there is no CPU path in the product)"""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('a GPU is present')
+    from nemoflux_b200 import nemoflux_gpu, _lib
+    with pytest.raises(_lib.NemofluxGpuError) as e:
+        nemoflux_gpu.Grid()
+    assert e.value.code == 3 and 'CUDA' in str(e.value)
+    with pytest.raises(_lib.NemofluxGpuError):
+        nemoflux_gpu.PolylineIntegral()
+    with pytest.raises(TypeError):
+        nemoflux_gpu.edgeFluxAssemble(torch.zeros(1, 1, 4, dtype=torch.float64), torch.zeros(1, 1, 4, dtype=torch.float64),
+                                      torch.ones(1, dtype=torch.float64), torch.ones(4, dtype=torch.float64),
+                                      torch.ones(4, dtype=torch.float64))
+
+
+def test_product_never_imports_the_oracle():
+    for d, _, files in os.walk(os.path.join(ROOT, 'nemoflux_b200')):
+        for fn in files:
+            if fn.endswith(('.py', '.cu', '.cuh', '.h')):
+                src = open(os.path.join(d, fn)).read()
+                assert 'import oracle' not in src and 'from oracle' not in src and 'libnfx_oracle' not in src, fn
+
+
+# ---- file formats ----------------------------------------------------------------------------------------
+WOCE_HEADER = ('EXPOCODE 09AR9404_1    S3 (P12)\n                                  CORR\n'
+               'STA. DIST(KM)   LAT      LONG     DEPTH\n-----------------------------------------\n')
+
+
+def test_latlonreader_matches_reference_outputs(tmp_path):
+    """golden = what the reference's LatLonReader returned for its 12 transect files; the files are rebuilt in
+    the same WOCE layout from the golden points (and the originals are parsed too where they are mounted)"""
+    from nemoflux_b200.latlonreader import LatLonReader
+    gold = json.load(open(os.path.join(GOLDEN, 'golden_summary.json')))['latlonreader']
+    assert len(gold) == 12 and len(gold['S3_sta_bdep.txt']) == 50 and len(gold['atlantic/S3.txt']) == 10
+    assert gold['sa/S3_sa.txt'] == [[16.0, -40.4], [28.0, -34.5], [31.0, -28.5], [36.0, -30.5]]
+    for name, pts in gold.items():
+        p = tmp_path / name.replace('/', '_')
+        with open(p, 'w') as f:
+            f.write(WOCE_HEADER)
+            for n, (lon, lat) in enumerate(pts):
+                f.write(f'  {55 + n}   {93.7 * n:8.1f}   {lat!r}   {lon!r}   802.4\n')
+            f.write('\n')
+        got = LatLonReader(str(p)).getLonLats()
+        assert got.shape == (len(pts), 2) and numpy.array_equal(got, numpy.array(pts))
+        ref = os.path.join('/root/reference/data', name)
+        if os.path.exists(ref):
+            assert numpy.array_equal(LatLonReader(ref).getLonLats(), numpy.array(pts))
+    # integer-looking coordinates and lines that must be skipped
+    p = tmp_path / 'odd.txt'
+    p.write_text(WOCE_HEADER + '  0      0.0   63     -10  0\n  x      0.0   1 2\n  0      5   63 -10\n  0  0.0 -46.0  164 0')
+    assert LatLonReader(str(p)).getLonLats().tolist() == [[-10.0, 63.0], [164.0, -46.0]]
+
+
+def test_datagen_cli_writes_nemo_conventions(tmp_path):
+    from nemoflux_b200 import datagen, ncio
+    prefix = str(tmp_path) + '/'
+    datagen.cli(['--streamFunction=x', f'--prefix={prefix}'])
+    g = numpy.load(os.path.join(GOLDEN, 'c1_simple.npz'))
+    with ncio.open_dataset(prefix + 'T.nc') as nc:
+        assert nc['bounds_lon'].dimensions == ('y', 'x', 'nvertex') and nc['bounds_lon'].shape == (18, 36, 4)
+        assert numpy.array_equal(nc['bounds_lon'][:], g['bounds_lon']) and numpy.array_equal(nc['bounds_lat'][:], g['bounds_lat'])
+        assert nc['deptht_bounds'].dimensions == ('z', 'axis_nbounds')
+        assert numpy.array_equal(nc['deptht_bounds'][:], numpy.stack([g['ztop'], g['zbot']], 1))
+    with ncio.open_dataset(prefix + 'U.nc') as nc:
+        uo = nc['uo']
+        assert uo.dimensions == ('t', 'z', 'y', 'x') and uo.standard_name == 'sea_water_x_velocity' and uo.units == 'm/s'
+        assert float(uo.attrs['_FillValue']) == 1.e20 and 'earth radius' in nc.attrs['earthRadius']
+        assert numpy.array_equal(uo[:], g['u'])            # the reference's own datagen output, bit for bit
+    with ncio.open_dataset(prefix + 'V.nc') as nc:
+        assert nc['vo'].standard_name == 'sea_water_y_velocity' and numpy.array_equal(nc['vo'][:], g['v'])
+    # README.md:89-91 flags
+    datagen.cli(['-s', '(1+10*z)*(t+1)*(cos(2*pi*y/360) + sin(2*pi*x/360))', '--nx=24', '--ny=12', '--nz=3', '--nt=2',
+                 '--deltaDeg=20,30', '-p', prefix + 'r'])
+    g = numpy.load(os.path.join(GOLDEN, 'rot24x12_t0_sv0.npz'))
+    with ncio.open_dataset(prefix + 'rU.nc') as nc:
+        m = ~g['mask']
+        assert nc['uo'].shape == (2, 3, 12, 24) and numpy.array_equal(nc['uo'][:][:, m], g['u'][:, m])
+    # missing values come back as NaN (xarray semantics the Field relies on, field.py:157)
+    w = ncio.Writer(prefix + 'm.nc')
+    w.createDimension('x', 3)
+    w.createVariable('a', 'float64', ('x',), fill_value=1.e20, data=numpy.array([1., 1.e20, 3.]))
+    w.close()
+    with ncio.open_dataset(prefix + 'm.nc') as nc:
+        a = nc['a'][:]
+        assert a[0] == 1. and numpy.isnan(a[1]) and a[2] == 3. and nc['a'].raw()[1] == 1.e20
+    with pytest.raises(ValueError):
+        datagen.parseDeltaDeg('1,2,3')
+    with pytest.raises(Exception):
+        datagen.eval_stream_function('__import__("os").system("true")', 0., 0., 0., 0, 1, 0., 1.)
+
+
+def test_transect_argument_forms(tmp_path):
+    from nemoflux_b200.field import parseLonLatPoints
+    from nemoflux_b200.fluxviz import parseTransects
+    flat = parseLonLatPoints('(-180,-70),(-160,-10),(-35,40)')                 # README.md:32
+    assert len(flat) == 1 and flat[0].shape == (3, 3) and flat[0][1].tolist() == [-160., -10., 0.]
+    many = parseLonLatPoints('[(0,0),(1,1)],[(2,2),(3,3),(4,4)]')               # fluxviz.py:378
+    assert [m.shape[0] for m in many] == [2, 3]
+    one = parseLonLatPoints('[(0,0),(1,1)]')
+    assert len(one) == 1 and one[0].shape == (2, 3)
+    with pytest.raises(RuntimeError):
+        parseTransects('', '')
+    a = tmp_path / 'S1.txt'
+    b = tmp_path / 'S2.txt'
+    a.write_text(WOCE_HEADER + '  0      0.0   -31.4   152.0   0\n  0      0.0   -34.5   172.0   0\n')
+    b.write_text(WOCE_HEADER + '  0      0.0   -46.0      164    0\n  0      0.0   -48.0      170    0\n  0 0.0 -40.0 179 0\n')
+    pts, names = parseTransects('', str(tmp_path / 'S*.txt'))
+    assert [p.shape[0] for p in pts] == [2, 3] and pts[0][0].tolist() == [152.0, -31.4, 0.0]
+    pts, names = parseTransects('', repr([str(a)]))
+    assert len(pts) == 1 and names == [str(a)]
+
+
+def test_fluxexact_cli(capsys):
+    from nemoflux_b200 import fluxexact
+    res = fluxexact.main(['--potentialFunction=x', '-l', '(-180,-70),(-160,-10),(180,40)', '--nz', '2'])
+    assert numpy.allclose(res, [360.0])
+    res = fluxexact.exactFlux('(1+10*z)*(t+1)*(cos(2*pi*y/360) + sin(2*pi*x/360))',
+                              numpy.array([(-100., -80.), (0., 80.)]), nz=10, nt=3)
+    assert numpy.allclose(res / res[0], [1, 2, 3])
+
+
+def test_timeobj():
+    from nemoflux_b200.timeobj import TimeObj
+    from nemoflux_b200.ncio import Variable
+    nc = {'uo': Variable('uo', numpy.zeros((2, 1)), ('t', 'x'), {}),
+          'time_counter': Variable('time_counter', numpy.array([0., 86400. * 31]), ('t',),
+                                   {'standard_name': 'time', 'units': 'seconds since 1950-01-01 00:00:00'})}
+    t = TimeObj(nc)
+    assert t.getSize() == 2 and t.getTimeAsString(1) == '1950-2-1'
+    t = TimeObj({'uo': nc['uo']})
+    assert t.getSize() == 0 and t.getTimeAsString(3) == 'time index 3'     # mock data has no time axis
+
+
+# ---- time sharding -------------------------------------------------------------------------------------------
+def test_shard_time_partitions():
+    from nemoflux_b200 import dist
+    assert dist.shard_counts(73, 8) == [10, 9, 9, 9, 9, 9, 9, 9]
+    assert dist.shard_counts(365, 2) == [183, 182] and dist.shard_counts(365, 4) == [92, 91, 91, 91]
+    for nt in (0, 1, 5, 73, 365):
+        for world in (1, 2, 3, 8):
+            assert dist.check_partition(nt, world)
+    with pytest.raises(ValueError):
+        dist.shard_time(10, 2, 2)
+
+
+WORKER = r'''
+import os, sys
+import numpy, torch
+import torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from nemoflux_b200 import dist as nd
+rank, world, nt, m = int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]), 5
+os.environ['MASTER_ADDR'] = '127.0.0.1'
+os.environ['MASTER_PORT'] = sys.argv[5]
+dist.init_process_group('gloo', rank=rank, world_size=world)
+full = torch.arange(nt * m, dtype=torch.float64).reshape(nt, m) * 0.5 + 1.0     # the 1-rank answer
+def compute_local(t0, n):      # stands for K2+K3 on this rank's time steps
+    return full[t0:t0 + n].clone()
+out = nd.sharded_flux_series(compute_local, nt)
+assert out.shape == (nt, m) and torch.equal(out, full), (rank, out)
+mx = nd.allreduce_max(float(rank + 1))
+assert mx == world
+dist.barrier()
+dist.destroy_process_group()
+print('ok', rank)
+'''
+
+
+@pytest.mark.parametrize('nt', [7, 8])
+def test_allgather_series_two_ranks_gloo(tmp_path, nt):
+    """world_size 2 on CPU: uneven (4+3) and even shards assemble to the single-rank series bit for bit"""
+    script = tmp_path / 'worker.py'
+    script.write_text(WORKER)
+    port = str(29500 + (os.getpid() + nt) % 2000)
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, str(r), '2', str(nt), port],
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT) for r in range(2)]
+    outs = [p.communicate(timeout=180)[0].decode() for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o

@@ -1,0 +1,223 @@
+"""-m "not gpu": the oracle against the golden vectors (outputs of the reference's own code), the known
+answers the reference records, and its own invariants.  No GPU, no /root/reference needed."""
+import json
+import os
+
+import numpy
+import pytest
+
+from conftest import GOLDEN
+from helpers import README_C1, README_C2, README_LOOP, README_SINGULAR, SF_C2, random_transects, tr
+
+
+def _golden(name):
+    return numpy.load(os.path.join(GOLDEN, name))
+
+
+# ---- K2 pinned on the reference's own outputs ------------------------------------------------------------
+@pytest.mark.parametrize('name,ti,sv', [('c1_simple.npz', 0, False), ('singular.npz', 0, False),
+                                        ('rot24x12_t0_sv0.npz', 0, False), ('rot24x12_t0_sv1.npz', 0, True),
+                                        ('rot24x12_t1_sv0.npz', 1, False), ('rot24x12_t1_sv1.npz', 1, True)])
+def test_field_restatement_matches_reference_outputs(oracle, name, ti, sv):
+    g = _golden(name)
+    u, v = g['u'], g['v']
+    th = g['zbot'] - g['ztop']
+    assert numpy.array_equal(th, g['thickness'])
+    ny, nx = u.shape[2:]
+    pts = numpy.zeros((ny, nx, 4, 3))
+    pts[..., 0], pts[..., 1] = g['bounds_lon'], g['bounds_lat']
+    arc = oracle.arc_lengths(pts.reshape(-1, 4, 3))
+    assert numpy.allclose(arc, g['arcLengths'], rtol=1e-13, atol=1e-16)
+    U = oracle.read_field(u[ti], th)
+    V = oracle.read_field(v[ti], th)
+    assert numpy.allclose(U, g['U'], rtol=1e-14, atol=1e-300)
+    assert numpy.allclose(V, g['V'], rtol=1e-14, atol=1e-300)
+    iV, eU, eV = oracle.integrated_flux(U, V, g['arcLengths'], sv)
+    scale = numpy.abs(g['iV']).max()
+    assert numpy.abs(iV - g['iV']).max() <= 1e-14 * scale
+    assert numpy.allclose(numpy.abs(eU), g['absEU'], rtol=1e-14, atol=0)
+    assert numpy.allclose(numpy.abs(eV), g['absEV'], rtol=1e-14, atol=0)
+    assert abs(max(numpy.abs(eU).max(), numpy.abs(eV).max()) - float(g['maxAbsFlux'])) <= 1e-14 * scale
+    # the sequential C restatement (the bit-exact reference of the CUDA kernel) agrees to rounding
+    iVc, _, _ = oracle.edgeflux_step_c(u[ti], v[ti], th, g['arcLengths'][:, 1].copy(), g['arcLengths'][:, 2].copy(), sv)
+    assert numpy.abs(iVc - g['iV']).max() <= 1e-13 * scale
+
+
+def test_datagen_restatement_matches_reference_outputs(oracle):
+    g = _golden('c1_simple.npz')
+    d = oracle.DataGen()
+    u, v = d.uv('x')
+    assert numpy.array_equal(d.bounds_lon, g['bounds_lon']) and numpy.array_equal(d.bounds_lat, g['bounds_lat'])
+    assert numpy.allclose(u, g['u'], rtol=1e-13, atol=1e-13) and numpy.allclose(v, g['v'], rtol=1e-13, atol=1e-13)
+    assert numpy.array_equal(d.ztop, g['ztop']) and numpy.array_equal(d.zbot, g['zbot'])
+    g = _golden('singular.npz')
+    u, v = d.uv('arctan2(y, x+180)/(2*pi)')
+    assert numpy.allclose(u, g['u'], rtol=1e-13, atol=1e-14) and numpy.allclose(v, g['v'], rtol=1e-13, atol=1e-14)
+    # pole displaced grid: vectorised rotation vs the reference's per-vertex loop (ulp differences only; the
+    # longitude of a vertex sitting on the pole is arbitrary in both)
+    g = _golden('rot24x12_t0_sv0.npz')
+    d = oracle.DataGen(nx=24, ny=12, nz=3, nt=2, deltaDeg=(20., 30.))
+    assert numpy.abs(d.bounds_lat - g['bounds_lat']).max() < 1e-12
+    notpole = numpy.abs(numpy.abs(g['bounds_lat']) - 90.) > 1e-6
+    dl = numpy.abs(d.bounds_lon - g['bounds_lon'])[notpole]
+    assert numpy.minimum(dl, numpy.abs(dl - 360.)).max() < 1e-11
+    u, v = d.uv(SF_C2)
+    m = ~g['mask']
+    assert numpy.allclose(u[:, m], g['u'][:, m], rtol=1e-13, atol=1e-13)
+    # C2 samples (360x180, nz=10, nt=20)
+    g = _golden('c2_sample.npz')
+    d = oracle.DataGen(nx=360, ny=180, nz=10, nt=20, deltaDeg=(20., 30.))
+    assert numpy.abs(d.bounds_lat[::17, ::13] - g['bounds_lat_rows']).max() < 1e-12
+    u, v = d.uv(SF_C2)
+    for ti in (0, 19):
+        U = oracle.read_field(u[ti], d.thickness())
+        assert numpy.allclose(U, g[f'U_t{ti}'], rtol=1e-12, atol=1e-13)
+    with open(os.path.join(GOLDEN, 'golden_summary.json')) as f:
+        summ = json.load(f)
+    arc = oracle.arc_lengths(d.points())
+    iV, eU, eV = oracle.integrated_flux(oracle.read_field(u[19], d.thickness()), oracle.read_field(v[19], d.thickness()), arc)
+    assert abs(max(numpy.abs(eU).max(), numpy.abs(eV).max()) - summ['c2_digests']['maxAbsFlux_t19']) < 1e-10
+
+
+# ---- the mint restatement: known answers the reference records --------------------------------------------
+def test_known_answer_360(oracle):
+    """README.md:26-39, pictures/simple.png"""
+    d = oracle.DataGen()
+    u, v = d.uv('x')
+    s = oracle.flux_series(d.points(), [tr(README_C1)], u, v, d.thickness())
+    assert abs(s[0, 0] - 360.) < 1e-12 * 360
+    assert abs(numpy.abs(oracle.integrated_flux(oracle.read_field(u[0], d.thickness()), oracle.read_field(v[0], d.thickness()),
+                                                oracle.arc_lengths(d.points()))[0]).max() - 10.0) < 1e-12   # colour bar max
+    p = oracle.PolylineIntegral(oracle.Grid(d.points()))
+    p.computeWeights(tr(README_C1))
+    assert len(p.subsegs) == 59
+    assert list(numpy.bincount(p.subsegs['seg'])) == [6, 15, 14, 12, 12]
+    assert list(p.subsegs['cell'][:6]) == [72, 108, 144, 181, 217, 253]
+    assert numpy.allclose(p.subsegs['w'][0], [1 / 6, 1 / 6, 1 / 6, 5 / 6], atol=1e-14)
+    assert numpy.allclose(p.subsegs['w'].sum(0), [18., 5.245454545454547, 18., 5.754545454545455], atol=1e-12)
+    assert numpy.allclose(p.segment_totals(5), 1.0, atol=1e-14)
+
+
+def test_known_answer_singular_half(oracle):
+    """README.md:50-58: node-to-node path around a singular stream function gives exactly psi(B)-psi(A) = 0.5"""
+    d = oracle.DataGen()
+    u, v = d.uv('arctan2(y, x+180)/(2*pi)')
+    for order in ('map', 'list'):
+        s = oracle.flux_series(d.points(), [tr(README_SINGULAR)], u, v, d.thickness(), order=order)
+        assert abs(s[0, 0] - 0.5) <= 2e-16 * 4
+
+
+def test_known_answer_closed_loops(oracle):
+    """README.md:65-68 (4.2e-15 in pictures/closed2.png) and README.md:77-79 (2.34e-11 with the displaced pole)"""
+    sf = 'cos(2*pi*y/360) + sin(2*pi*x/360)'
+    d = oracle.DataGen(nx=360, ny=180)
+    u, v = d.uv(sf)
+    s = oracle.flux_series(d.points(), [tr(README_LOOP)], u, v, d.thickness())
+    assert abs(s[0, 0]) < 1e-13
+    d = oracle.DataGen(nx=360, ny=180, deltaDeg=(20., 30.))
+    u, v = d.uv(sf)
+    s = oracle.flux_series(d.points(), [tr(README_LOOP)], u, v, d.thickness())
+    assert abs(s[0, 0]) < 1e-10          # arccos arc lengths vs datagen's un-rotated ds: expected level ~2e-11
+
+
+def test_c2_series(oracle):
+    """BASELINE config 2: 361 sub-segments, flux(t) = 1.7386322852...*(t+1)"""
+    d = oracle.DataGen(nx=360, ny=180, nz=10, nt=20, deltaDeg=(20., 30.))
+    u, v = d.uv(SF_C2)
+    s = oracle.flux_series(d.points(), [tr(README_C2)], u, v, d.thickness())[:, 0]
+    assert abs(s[0] - 1.7386322852896516) < 1e-11
+    assert numpy.allclose(s / s[0], numpy.arange(1, 21), rtol=1e-12)
+    p = oracle.PolylineIntegral(oracle.Grid(d.points()))
+    p.computeWeights(tr(README_C2))
+    assert len(p.subsegs) == 361
+    assert numpy.allclose(p.segment_totals(2), 1.0, atol=1e-13)
+
+
+def test_node_to_node_exact_and_linear(oracle):
+    """fluxexact.py:36-46: F = sum_k dz_k (psi_k(B) - psi_k(A)); linear in u,v and in the thickness"""
+    d = oracle.DataGen(nx=36, ny=18, nz=4, nt=3)
+    u, v = d.uv(SF_C2)
+    path = [(-120, -40), (-33.3, 12.5), (70, -60), (100, 50)]          # ends on nodes, interior points are not
+    s = oracle.flux_series(d.points(), [tr(path)], u, v, d.thickness())[:, 0]
+    for t in range(3):
+        ex = 0.0
+        for k in range(4):
+            ex += (d.potential_nodes(SF_C2, t, k)[14, 28] - d.potential_nodes(SF_C2, t, k)[5, 6]) * d.thickness()[k]
+        assert abs(s[t] - ex) <= 1e-12 * abs(ex)
+    s2 = oracle.flux_series(d.points(), [tr(path)], 3 * u, 3 * v, d.thickness())[:, 0]
+    s3 = oracle.flux_series(d.points(), [tr(path)], u, v, 2 * d.thickness())[:, 0]
+    assert numpy.allclose(s2, 3 * s, rtol=1e-13) and numpy.allclose(s3, 2 * s, rtol=1e-13)
+
+
+@pytest.mark.parametrize('delta', [(0., 0.), (20., 30.)])
+def test_c_oracle_vs_independent_numpy_brute_force(oracle, delta):
+    from oracle import brute_numpy
+    d = oracle.DataGen(nx=40, ny=20, deltaDeg=delta)
+    P = d.points()
+    rng = numpy.random.default_rng(3)
+    nodes = numpy.stack([d.xx, d.yy], -1) if delta == (0., 0.) else None
+    transects = random_transects(rng, 8, nodes=nodes) + [tr(README_C1), tr(README_LOOP), tr([(-180, -40), (180, -40)])]
+    g = oracle.Grid(P)
+    checked = 0
+    for xyz in transects:
+        p = oracle.PolylineIntegral(g, filter_mode=1)
+        p.computeWeights(xyz)
+        pb = oracle.PolylineIntegral(g, filter_mode=0)
+        pb.computeWeights(xyz)
+        assert numpy.array_equal(p.subsegs, pb.subsegs)              # the bbox filter is a pure superset filter
+        b = brute_numpy.compute_weights(P, xyz)
+        assert numpy.array_equal(b['cell'], p.subsegs['cell'])
+        assert numpy.array_equal(b['seg'], p.subsegs['seg']) and numpy.array_equal(b['img'], p.subsegs['img'])
+        assert numpy.allclose(b['ta'], p.subsegs['ta'], atol=1e-13) and numpy.allclose(b['coeff'], p.subsegs['coeff'], atol=1e-12)
+        # cells next to the displaced pole are folded quads in the lon-lat plane: the bilinear map has two
+        # inverses there and the two solvers may pick different ones -- compare away from the poles
+        ok = numpy.abs(P[p.subsegs['cell'], :, 1]).max(axis=1) < (78. if delta != (0., 0.) else 91.)
+        checked += int(ok.sum())
+        assert numpy.abs(b['w'] - p.subsegs['w'])[ok].max(initial=0.) <= 1e-11
+    assert checked > 500
+
+
+def test_map_and_list_orders(oracle):
+    d = oracle.DataGen(nx=36, ny=18)
+    p = oracle.PolylineIntegral(oracle.Grid(d.points()))
+    p.computeWeights(tr(README_SINGULAR))          # runs along grid lines: duplicate sub-segments, coeff 0/1
+    assert set(numpy.round(p.subsegs['coeff'], 12)) <= {0.0, 1.0}
+    assert (p.subsegs['coeff'] == 0.0).any()
+    keys, ws = p.merged_map()
+    assert (numpy.diff(keys) > 0).all()
+    cells, edges, w = p.emission_list()
+    acc = {}
+    for c, e, x in zip(cells, edges, w):
+        acc[c * 4 + e] = acc.get(c * 4 + e, 0.0) + x
+    assert numpy.array_equal(keys, numpy.array(sorted(acc)))
+    assert numpy.array_equal(ws, numpy.array([acc[k] for k in sorted(acc)]))
+    data = numpy.random.default_rng(0).standard_normal((36 * 18, 4))
+    a, b = p.getIntegral(data, 'map'), p.getIntegral(data, 'list')
+    assert abs(a - b) <= 1e-13 * numpy.abs(data).max() * numpy.abs(w).sum()
+
+
+def test_edge_cases(oracle):
+    d = oracle.DataGen()
+    g = oracle.Grid(d.points())
+    p = oracle.PolylineIntegral(g)
+    for xyz in (numpy.zeros((0, 3)), tr([(1, 1)]), tr([(1, 1), (1, 1)]), tr([(0, 100), (10, 120)])):
+        p.computeWeights(xyz)
+        assert len(p.subsegs) == 0
+        assert p.getIntegral(numpy.ones((648, 4))) == 0.0
+    # the x-period: a transect given 360 degrees to the east gives the same weights
+    a = oracle.PolylineIntegral(g)
+    a.computeWeights(tr([(-100, -20), (-60, 30)]))
+    b = oracle.PolylineIntegral(g)
+    b.computeWeights(tr([(260, -20), (300, 30)]))
+    assert numpy.array_equal(a.subsegs['cell'], b.subsegs['cell'])
+    assert numpy.allclose(a.subsegs['w'], b.subsegs['w'], atol=1e-13)
+    # without the period nothing is found out there
+    c = oracle.PolylineIntegral(g, periodX=0.)
+    c.computeWeights(tr([(260, -20), (300, 30)]))
+    assert len(c.subsegs) == 0
+    # row 0 south edges stay zero (field.py:219) and the west edge of column 0 is periodic (field.py:223)
+    U = numpy.arange(18 * 36, dtype=float).reshape(18, 36) + 1
+    iV, eU, eV = oracle.integrated_flux(U, 2 * U, numpy.ones((648, 4)))
+    iV = iV.reshape(18, 36, 4)
+    assert (iV[0, :, 0] == 0).all() and numpy.array_equal(iV[:, 0, 3], eU.reshape(18, 36)[:, -1])
+    assert oracle.lib().orc_flux_index(0, 0, 18, 36) == -1 and oracle.lib().orc_flux_index(36, 3, 18, 36) == 71

@@ -39,6 +39,7 @@ static void require_gpu(int* dev) {
 template <typename F>
 static int guarded(F&& f) {
     try {
+        cudaGetLastError();  // a stale non-sticky error of an earlier call must not be blamed on this one
         f();
         return NFX_OK;
     } catch (const Error& e) {
@@ -182,6 +183,7 @@ int nfx_pli_new(nfx_pli** self) {
         int dev;
         require_gpu(&dev);
         *self = new nfx_pli();
+        (*self)->d.device = dev;
     });
 }
 
@@ -189,14 +191,9 @@ int nfx_pli_del(nfx_pli** self) {
     return guarded([&] {
         NFX_REQUIRE(self, "NULL handle");
         if (*self) {
-            if ((*self)->d.grid) {
-                DeviceGuard g((*self)->d.grid->device);
-                free_host_path((*self)->d);
-                delete *self;
-            } else {
-                free_host_path((*self)->d);
-                delete *self;
-            }
+            DeviceGuard g((*self)->d.device);
+            free_host_path((*self)->d);
+            delete *self;
         }
         *self = nullptr;
     });
@@ -206,6 +203,7 @@ int nfx_pli_set_grid(nfx_pli** self, nfx_grid* grid) {
     return guarded([&] {
         NFX_REQUIRE(self && *self && grid, "NULL handle");
         (*self)->d.grid = &grid->d;
+        (*self)->d.device = grid->d.device;
     });
 }
 

@@ -83,7 +83,8 @@ struct Csr {
 };
 
 struct PliDev {
-    GridDev* grid = nullptr;
+    GridDev* grid = nullptr;   // borrowed; never dereferenced by nfx_pli_del (the grid may already be gone)
+    int device = 0;
     double period_x = 360.0;
     bool locator_requested = false;
     int ntransects = 0;

@@ -29,14 +29,14 @@ EARTH_RADIUS = 6371000.0          # field.py:12
 class _TransectView(object):
     """element of Field.plis: getIntegral(data, placement) of one transect of the shared batch (field.py:102)"""
 
-    def __init__(self, field, index):
-        self._field, self._index = field, index
+    def __init__(self, pli, index):
+        self._pli, self._index = pli, index          # no reference back to the Field: no reference cycle
 
     def getIntegral(self, data, placement=nemoflux_gpu.CELL_BY_CELL_DATA):
-        return float(self._field.pli.getIntegral(data, placement)[self._index])
+        return float(self._pli.getIntegral(data, placement)[self._index])
 
     def getWeights(self):
-        return self._field.pli.getWeights(self._index)
+        return self._pli.getWeights(self._index)
 
 
 class Field(object):
@@ -66,7 +66,7 @@ class Field(object):
         self.pli.build(self.gr.getMintGrid(), periodX=360.)
         self.lonLatZPoints = [numpy.array(p, numpy.float64).reshape(-1, 3) for p in lonLatZPoints]
         self.pli.computeWeights(self.lonLatZPoints, counterclock=False)
-        self.plis = [_TransectView(self, i) for i in range(len(self.lonLatZPoints))]
+        self.plis = [_TransectView(self.pli, i) for i in range(len(self.lonLatZPoints))]
 
         self.thickness = numpy.asarray(self.bounds_depth[:, 1] - self.bounds_depth[:, 0], numpy.float64)   # field.py:51
 

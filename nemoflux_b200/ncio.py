@@ -25,12 +25,19 @@ class Variable(object):
     def __len__(self):
         return self.shape[0] if self.shape else 0
 
+    @staticmethod
+    def _native(a):
+        """NetCDF-3 data are big-endian on disk: hand out native byte order (torch.from_numpy needs it)"""
+        if a.dtype.byteorder not in ('=', '|') and not a.dtype.isnative:
+            a = a.astype(a.dtype.newbyteorder('='))
+        return a
+
     def raw(self, idx=Ellipsis):
-        return numpy.asarray(self._data[idx])
+        return self._native(numpy.array(self._data[idx]))
 
     def __getitem__(self, idx):
         """values with missing data decoded to NaN (floating point variables only)"""
-        a = numpy.array(self._data[idx])
+        a = self._native(numpy.array(self._data[idx]))
         if a.dtype.kind == 'f':
             for key in ('_FillValue', 'missing_value'):
                 if key in self.attrs:
@@ -84,11 +91,16 @@ class Dataset(object):
 
     def close(self):
         if self._h is not None:
+            for v in self.variables.values():
+                v._data = None
             self.variables = {}
-            try:
-                self._h.close()
-            except Exception:
-                pass
+            import warnings
+            with warnings.catch_warnings():
+                warnings.simplefilter('ignore')
+                try:
+                    self._h.close()
+                except Exception:
+                    pass
             self._h = None
 
     def __enter__(self):

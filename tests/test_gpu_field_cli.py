@@ -103,3 +103,30 @@ def test_field_float32_and_land(gpu, oracle, tmp_path):
     ref = oracle.flux_series(d.points(), path, un, vn, d.thickness())
     assert numpy.abs(s - ref).max() <= 1e-12 * numpy.abs(ref).max()
     assert numpy.isfinite(f.integratedVelocity).all() and (f.integratedVelocity.reshape(18, 36, 4)[6, 12] == 0).all()
+
+
+def test_integration_md_binding_runs(gpu, oracle, tmp_path):
+    """the ctypes stub INTEGRATION.md shows to nemoflux maintainers works as written: mint-style calls only"""
+    import re
+    import types
+    from conftest import ROOT
+    from nemoflux_b200 import _lib
+    text = open(os.path.join(ROOT, 'INTEGRATION.md')).read()
+    code = re.search(r'```python\n(# nemoflux/mint_gpu.py.*?)```', text, re.S).group(1)
+    code = code.replace("'libnemoflux_gpu.so'", repr(_lib.LIB_PATH))
+    mint = types.ModuleType('mint_gpu')
+    exec(compile(code, 'mint_gpu.py', 'exec'), mint.__dict__)
+    d = oracle.DataGen()
+    u, v = d.uv('x')
+    arc = oracle.arc_lengths(d.points())
+    iV, _, _ = oracle.integrated_flux(oracle.read_field(u[0], d.thickness()), oracle.read_field(v[0], d.thickness()), arc)
+    g = mint.Grid()
+    g.setPoints(d.points())
+    assert g.getNumberOfCells() == 648
+    pli = mint.PolylineIntegral()
+    pli.setGrid(g)
+    pli.buildLocator(numCellsPerBucket=128, periodX=360., enableFolding=False)
+    pli.computeWeights(tr(README_C1), counterclock=False)
+    assert abs(pli.getIntegral(iV, mint.CELL_BY_CELL_DATA) - 360.) < 1e-10
+    with pytest.raises(RuntimeError):
+        pli.buildLocator(enableFolding=True)

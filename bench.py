@@ -45,6 +45,8 @@ def parse_args():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--workload', default='C3')
     ap.add_argument('--nt-local', type=int, default=0, help='time steps resident per rank (0 = the workload\'s nt)')
+    ap.add_argument('--nt-total', type=int, default=0, help='strong scaling: shard this many time steps over the ranks')
+    ap.add_argument('--force-host-samples', action='store_true', help='run e2e / cpu samples even for >12 GB time steps')
     ap.add_argument('--dtype', default='f64', choices=['f64', 'f32'], help='storage type of uo/vo (compute is f64)')
     ap.add_argument('--e2e-steps', type=int, default=24, help='time steps of the host-buffer (e2e) sample')
     ap.add_argument('--cpu-steps', type=int, default=24, help='time steps of the cpu_baseline sample')
@@ -213,9 +215,21 @@ def run_b200(args):
         _lib.set_option(_lib.NFX_OPT_K2_BLOCK, args.k2_block)
 
     syn = synth.make(args.workload)
-    nt_local = args.nt_local or syn.nt                 # weak scaling: every rank holds nt_local steps
-    nt_total = nt_local * world
-    t0_rank = rank * nt_local
+    from nemoflux_b200 import dist as nfx_dist
+    if args.nt_total > 0:                              # strong scaling: a fixed series sharded by time
+        nt_total = args.nt_total
+        counts = nfx_dist.shard_counts(nt_total, world)
+        t0_rank, nt_local = nfx_dist.shard_time(nt_total, world, rank)
+        scaling = 'strong'
+    else:                                              # weak scaling: every rank holds nt_local steps
+        nt_local = args.nt_local or syn.nt
+        nt_total = nt_local * world
+        counts = [nt_local] * world
+        t0_rank = rank * nt_local
+        scaling = 'weak'
+    cmax = max(counts)
+    step_bytes_uv = 2 * (8 if args.dtype == 'f64' else 4) * syn.units_per_step()
+    big_steps = step_bytes_uv > 12e9 and not args.force_host_samples
     tdtype = torch.float64 if args.dtype == 'f64' else torch.float32
     esize = 8 if args.dtype == 'f64' else 4
     M = syn.ntransects
@@ -240,8 +254,9 @@ def run_b200(args):
     arc2 = torch.from_numpy(syn.arc2).to(dev)
     u, v = syn.fill_device(t0_rank, nt_local, dev, tdtype)
     eflux = torch.empty((nt_local, 2 * syn.ncell), dtype=torch.float64, device=dev)
-    series = torch.empty((nt_local, M), dtype=torch.float64, device=dev)
-    gathered = torch.empty((world * nt_local, M), dtype=torch.float64, device=dev) if world > 1 else None
+    series_pad = torch.zeros((cmax, M), dtype=torch.float64, device=dev)       # padded to the largest shard
+    series = series_pad[:nt_local]
+    gathered = torch.empty((world * cmax, M), dtype=torch.float64, device=dev) if world > 1 else None
 
     def step(ev=None):
         if ev is not None:
@@ -253,7 +268,7 @@ def run_b200(args):
         if ev is not None:
             ev[2].record()
         if world > 1:
-            dist.all_gather_into_tensor(gathered, series)
+            dist.all_gather_into_tensor(gathered, series_pad)
         return gathered if world > 1 else series
 
     def barrier():
@@ -286,9 +301,11 @@ def run_b200(args):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     total_ms, k2_ms_max, k3_ms_max = [float(x) for x in tt.cpu()]
     ms_per_step = total_ms / args.steps
-    units_step_all = syn.units_per_step() * nt_local * world
+    units_step_all = syn.units_per_step() * nt_total
     value = units_step_all / (ms_per_step * 1e-3)
     final_series = out.cpu().numpy().copy()
+    if world > 1:                                      # drop the padding of the shorter shards
+        final_series = numpy.concatenate([final_series[r * cmax:r * cmax + counts[r]] for r in range(world)], 0)
 
     # ---- roofline of K2 -------------------------------------------------------------------------------
     peaks = {}
@@ -318,8 +335,8 @@ def run_b200(args):
     # ---- e2e: host buffers through the public API, every rank streams its own shard ----------------------
     e2e = None
     s_e2e = None
-    ne = min(args.e2e_steps, nt_local)
-    if not args.no_e2e:
+    ne = max(1, min(args.e2e_steps, nt_local, int(8e9 // step_bytes_uv)))
+    if not args.no_e2e and not big_steps:
         hu = torch.empty((ne, syn.nz, syn.ny, syn.nx), dtype=tdtype).pin_memory()
         hv = torch.empty_like(hu).pin_memory()
         hu.copy_(u[:ne])
@@ -377,7 +394,7 @@ def run_b200(args):
 
     # ---- cpu baseline + parity against the oracle on a bounded sample -----------------------------------
     cpu = None
-    if not args.no_cpu:
+    if not args.no_cpu and not big_steps:
         from oracle import oracle as O
         O.lib()
         tk = time.perf_counter()
@@ -396,6 +413,7 @@ def run_b200(args):
         parity['edge_lists_bit_exact'] = bool(ok)
         parity['subsegments'] = int(nsub)
         nc = min(args.cpu_steps, nt_local) if world == 1 else min(4, nt_local)
+        nc = max(1, min(nc, int(8e9 // step_bytes_uv)))
         steps = list(range(nc))
         fields = [syn.uv_host(t) for t in steps]
         cpu_reference_pass(O, syn, oplis, fields[:1], args.order)          # warm-up
@@ -424,12 +442,12 @@ def run_b200(args):
 
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
-        'warmup': max(args.warmup, 3), 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
+        'warmup': max(args.warmup, 3), 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': scaling,
         'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
         'config': {'workload': f'{args.workload}: {syn.label}, {nt_local} time steps per GPU ({nt_total} total), '
                                f'{M} transects, u/v stored {args.dtype} resident in HBM',
                    'nx': syn.nx, 'ny': syn.ny, 'nz': syn.nz, 'nt_per_gpu': nt_local, 'nt_total': nt_total,
-                   'transects': M, 'storage_dtype': args.dtype, 'sharding': f'time x{world}',
+                   'transects': M, 'storage_dtype': args.dtype, 'sharding': f'time x{world} {counts}',
                    'l2_policy': f'inputs per step {2 * esize * syn.units_per_step() * nt_local / 1e9:.1f} GB >> 126 MB L2',
                    'summation_order': args.order},
         'hbm_gbs_aggregate': 2.0 * esize * units_step_all / (ms_per_step * 1e-3) / 1e9,

@@ -17,6 +17,8 @@
 // Algorithmic bytes: 2 * sizeof(T) * nz per cell and time step (u and v read once).  Roofline: HBM.
 #include <cuda.h>
 
+#include <algorithm>
+
 #include "nfx_common.cuh"
 
 namespace nfx {
@@ -82,6 +84,13 @@ __device__ __forceinline__ void pin(float8x& r) {
     asm volatile(""
                  : "+f"(r.a[0]), "+f"(r.a[1]), "+f"(r.a[2]), "+f"(r.a[3]), "+f"(r.a[4]), "+f"(r.a[5]), "+f"(r.a[6]),
                    "+f"(r.a[7]));
+}
+
+// eflux is written once and read later by K3: streaming (evict-first) stores.  Measured with
+// tools/readbw.cu: default write-back stores cost 10 % of the read stream (DRAM read/write turnarounds for
+// 1.3 % of the traffic), evict-first stores 5 %.
+__device__ __forceinline__ void st_stream2(double* p, double a, double b) {
+    __stcs(reinterpret_cast<double2*>(p), make_double2(a, b));
 }
 
 template <typename T, int VEC>
@@ -214,14 +223,14 @@ k2_edgeflux_ldg(const T* __restrict__ u, const T* __restrict__ v, const double* 
     if constexpr (VEC % 2 == 0) {  // ncell even on this path -> 16-byte aligned stores
 #pragma unroll
         for (int e = 0; e < VEC; e += 2) {
-            *reinterpret_cast<double2*>(ou + e) = make_double2(fu[e], fu[e + 1 < VEC ? e + 1 : e]);
-            *reinterpret_cast<double2*>(ov + e) = make_double2(fv[e], fv[e + 1 < VEC ? e + 1 : e]);
+            st_stream2(ou + e, fu[e], fu[e + 1 < VEC ? e + 1 : e]);
+            st_stream2(ov + e, fv[e], fv[e + 1 < VEC ? e + 1 : e]);
         }
     } else {
 #pragma unroll
         for (int e = 0; e < VEC; ++e) {
-            ou[e] = fu[e];
-            ov[e] = fv[e];
+            __stcs(ou + e, fu[e]);
+            __stcs(ov + e, fv[e]);
         }
     }
 }
@@ -258,6 +267,201 @@ void dispatch_ldg(const T* u, const T* v, const double* dz, const double* arc1, 
     NFX_K2_CASE(3, 512)
 #undef NFX_K2_CASE
     throw Error(NFX_E_INVALID, "edgeflux: unsupported (unroll, block) option pair");
+}
+
+
+// ---------------------------------------------------------------------------------------------------------
+// TMA-staged variant: a persistent CTA per SM; one producer thread streams level tiles from HBM into a ring
+// of shared-memory stages with 1-D bulk copies (cp.async.bulk ... mbarrier::complete_tx, SASS UBLKCP) and
+// consumer warps run the z-sum out of shared memory.  Bytes in flight per SM = STAGES * KL * 2 * TC * sizeof(T)
+// (up to ~200 KB), independent of registers and of the compiler's load scheduling -- the direct-load kernel
+// above keeps only ~64 KB in flight per SM and stalls on the long scoreboard.
+// Needs 16-byte aligned rows: ncell * sizeof(T) % 16 == 0.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+        "l"(src), "r"(bytes), "r"(bar), "l"(policy)
+        : "memory");
+}
+
+template <typename T, int N>
+struct alignas(sizeof(T) * N) Cols {
+    T v[N];
+};
+
+// TC columns per tile, KL levels per stage, CT consumer threads (+32 producer), CPT = TC/CT columns per thread
+template <typename T, int TC, int KL, int STAGES, int CT>
+__global__ void __launch_bounds__(CT + 32, 1)
+k2_edgeflux_tma(const T* __restrict__ u, const T* __restrict__ v, const double* __restrict__ dz,
+                const double* __restrict__ arc1, const double* __restrict__ arc2, double* __restrict__ eflux, int nt, int nz,
+                int64_t ncell, int ntiles, double scale, int use_scale, T fill, int has_fill) {
+    constexpr int CPT = TC / CT;
+    static_assert(TC % CT == 0 && (CPT * sizeof(T)) % 8 == 0, "bad tile shape");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    T* s_u = reinterpret_cast<T*>(smem_raw);                                      // [STAGES][KL][TC]
+    T* s_v = s_u + (size_t)STAGES * KL * TC;                                      // [STAGES][KL][TC]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_v + (size_t)STAGES * KL * TC);  // full[STAGES], empty[STAGES]
+    double* s_dz = reinterpret_cast<double*>(bars + 2 * STAGES);                  // [nz]
+    const int tid = threadIdx.x;
+    for (int k = tid; k < nz; k += CT + 32) s_dz[k] = dz[k];
+    if (tid == 0) {
+        for (int i = 0; i < STAGES; ++i) {
+            mbar_init(smem_u32(bars + i), 1);                 // full: the producer's expect_tx arrive
+            mbar_init(smem_u32(bars + STAGES + i), CT / 32);  // empty: one arrive per consumer warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int64_t nitems = (int64_t)nt * ntiles;
+    const int nk = (nz + KL - 1) / KL;
+    if (tid >= CT) {
+        // ---- producer warp: one elected lane issues the bulk copies ----
+        if (tid == CT) {
+            uint64_t policy;
+            asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+            uint32_t it = 0;
+            for (int64_t w = blockIdx.x; w < nitems; w += gridDim.x) {
+                const int64_t t = w / ntiles;
+                const int64_t c0 = (w - t * ntiles) * TC;
+                const int ncols = (int)min((int64_t)TC, ncell - c0);
+                const uint32_t row_bytes = (uint32_t)(ncols * sizeof(T));
+                const T* gu = u + t * nz * ncell + c0;
+                const T* gv = v + t * nz * ncell + c0;
+                for (int kb = 0; kb < nk; ++kb, ++it) {
+                    const int stage = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    const int k0 = kb * KL;
+                    const int kl = min(KL, nz - k0);
+                    const uint32_t full = smem_u32(bars + stage), empty = smem_u32(bars + STAGES + stage);
+                    mbar_wait(empty, ph ^ 1);
+                    mbar_expect_tx(full, 2u * kl * row_bytes);
+                    T* du = s_u + ((size_t)stage * KL) * TC;
+                    T* dv = s_v + ((size_t)stage * KL) * TC;
+                    for (int q = 0; q < kl; ++q) {
+                        bulk_g2s(smem_u32(du + (size_t)q * TC), gu + (int64_t)(k0 + q) * ncell, row_bytes, full, policy);
+                        bulk_g2s(smem_u32(dv + (size_t)q * TC), gv + (int64_t)(k0 + q) * ncell, row_bytes, full, policy);
+                    }
+                }
+            }
+        }
+        return;
+    }
+    // ---- consumers ----
+    using CV = Cols<T, CPT>;
+    const int lane = tid & 31;
+    uint32_t it = 0;
+    for (int64_t w = blockIdx.x; w < nitems; w += gridDim.x) {
+        const int64_t t = w / ntiles;
+        const int64_t c0 = (w - t * ntiles) * TC;
+        const int64_t c = c0 + (int64_t)tid * CPT;
+        double su[CPT], sv[CPT];
+#pragma unroll
+        for (int e = 0; e < CPT; ++e) {
+            su[e] = 0.0;
+            sv[e] = 0.0;
+        }
+        for (int kb = 0; kb < nk; ++kb, ++it) {
+            const int stage = it % STAGES;
+            const uint32_t ph = (it / STAGES) & 1;
+            const int k0 = kb * KL;
+            const int kl = min(KL, nz - k0);
+            mbar_wait(smem_u32(bars + stage), ph);
+            const T* pu = s_u + ((size_t)stage * KL) * TC + tid * CPT;
+            const T* pv = s_v + ((size_t)stage * KL) * TC + tid * CPT;
+            if (kl == KL) {
+#pragma unroll
+                for (int q = 0; q < KL; ++q) {
+                    const CV a = *reinterpret_cast<const CV*>(pu + (size_t)q * TC);
+                    const CV b = *reinterpret_cast<const CV*>(pv + (size_t)q * TC);
+                    const double d = s_dz[k0 + q];
+#pragma unroll
+                    for (int e = 0; e < CPT; ++e) {
+                        su[e] = __dadd_rn(su[e], __dmul_rn(d, clean<T>(a.v[e], fill, has_fill)));
+                        sv[e] = __dadd_rn(sv[e], __dmul_rn(d, clean<T>(b.v[e], fill, has_fill)));
+                    }
+                }
+            } else {
+                for (int q = 0; q < kl; ++q) {
+                    const CV a = *reinterpret_cast<const CV*>(pu + (size_t)q * TC);
+                    const CV b = *reinterpret_cast<const CV*>(pv + (size_t)q * TC);
+                    const double d = s_dz[k0 + q];
+#pragma unroll
+                    for (int e = 0; e < CPT; ++e) {
+                        su[e] = __dadd_rn(su[e], __dmul_rn(d, clean<T>(a.v[e], fill, has_fill)));
+                        sv[e] = __dadd_rn(sv[e], __dmul_rn(d, clean<T>(b.v[e], fill, has_fill)));
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(bars + STAGES + stage));   // this warp is done with the stage
+        }
+        if (c < ncell) {
+            double* ou = eflux + t * 2 * ncell + c;
+            double* ov = ou + ncell;
+            const int nvalid = (int)min((int64_t)CPT, ncell - c);   // even: ncell and c are even on this path
+#pragma unroll
+            for (int e = 0; e < CPT; e += 2) {
+                if (e < nvalid) {
+                    double fu0 = __dmul_rn(su[e], arc1[c + e]), fu1 = __dmul_rn(su[e + 1], arc1[c + e + 1]);
+                    double fv0 = __dmul_rn(-sv[e], arc2[c + e]), fv1 = __dmul_rn(-sv[e + 1], arc2[c + e + 1]);
+                    if (use_scale) {
+                        fu0 = __dmul_rn(fu0, scale);
+                        fu1 = __dmul_rn(fu1, scale);
+                        fv0 = __dmul_rn(fv0, scale);
+                        fv1 = __dmul_rn(fv1, scale);
+                    }
+                    st_stream2(ou + e, fu0, fu1);
+                    st_stream2(ov + e, fv0, fv1);
+                }
+            }
+        }
+    }
+}
+
+template <typename T, int TC, int KL, int STAGES, int CT>
+void launch_tma(const T* u, const T* v, const double* dz, const double* arc1, const double* arc2, double* eflux, int nt,
+                int nz, int64_t ncell, double scale, int use_scale, T fill, int has_fill, cudaStream_t s) {
+    static int num_sms = 0;
+    if (num_sms == 0) {
+        int dev = 0;
+        NFX_CUDA(cudaGetDevice(&dev));
+        NFX_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    const size_t smem = 2 * sizeof(T) * (size_t)STAGES * KL * TC + sizeof(uint64_t) * 2 * STAGES + sizeof(double) * nz;
+    auto kern = k2_edgeflux_tma<T, TC, KL, STAGES, CT>;
+    static bool configured = false;
+    if (!configured) {
+        NFX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        configured = true;
+    }
+    NFX_REQUIRE(smem <= 227 * 1024, "edgeflux (TMA): too many levels for the shared-memory ring");
+    const int ntiles = (int)((ncell + TC - 1) / TC);
+    const int64_t nitems = (int64_t)nt * ntiles;
+    const int grid = (int)std::min<int64_t>(nitems, num_sms);
+    kern<<<grid, CT + 32, smem, s>>>(u, v, dz, arc1, arc2, eflux, nt, nz, ncell, ntiles, scale, use_scale, fill, has_fill);
 }
 
 // ---- (ncell,4) layout of field.py:209-223 -------------------------------------------------------------
@@ -303,6 +507,31 @@ void edgeflux_assemble(const void* u, const void* v, int dtype, const double* th
     const uintptr_t addr_bits = ((uintptr_t)u) | ((uintptr_t)v) | ((uintptr_t)eflux);
     const bool aligned16 = (addr_bits & 15) == 0;
     const bool aligned32 = (addr_bits & 31) == 0 && opt.variant != NFX_K2_LDG128;
+    const bool want_tma = (opt.variant == NFX_K2_TMA);
+    if (want_tma && aligned16 && dtype == NFX_F64 && ncell % 2 == 0) {
+        const int cfg = opt.unroll;   // tile configuration selector for the sweep (0 = default)
+        const double* pu = (const double*)u;
+        const double* pv = (const double*)v;
+#define NFX_TMA_CASE(ID, TC, KL, ST, CT)                                                                             \
+    if (cfg == ID) {                                                                                                 \
+        launch_tma<double, TC, KL, ST, CT>(pu, pv, thickness, arc1, arc2, eflux, nt, nz, ncell, scale, sverdrup, fill, \
+                                           has_fill, s);                                                             \
+        count_launch();                                                                                              \
+        NFX_CUDA(cudaGetLastError());                                                                                \
+        return;                                                                                                      \
+    }
+        NFX_TMA_CASE(0, 512, 5, 5, 256)
+        NFX_TMA_CASE(1, 512, 5, 4, 256)
+        NFX_TMA_CASE(2, 512, 3, 8, 256)
+        NFX_TMA_CASE(3, 1024, 5, 2, 512)
+        NFX_TMA_CASE(4, 1024, 3, 4, 512)
+        NFX_TMA_CASE(5, 512, 5, 5, 128)
+        NFX_TMA_CASE(6, 256, 5, 10, 128)
+        NFX_TMA_CASE(7, 512, 15, 1, 256)
+        NFX_TMA_CASE(8, 512, 5, 2, 256)
+#undef NFX_TMA_CASE
+        throw Error(NFX_E_INVALID, "edgeflux (TMA): unknown tile configuration");
+    }
     if (dtype == NFX_F64) {
         const double* pu = (const double*)u;
         const double* pv = (const double*)v;

@@ -125,20 +125,25 @@ class OrcaSynth(object):
             u, v = out
         U1, V1, U2, V2 = (torch.from_numpy(a).to(device) for a in (self.U1, self.V1, self.U2, self.V2))
         mask = torch.from_numpy(self.mask).to(device) if self.mask is not None else None
-        tmp = torch.empty((self.nz, self.ny, self.nx), dtype=torch.float64, device=device)
+        # work on slabs of levels so that the temporaries stay small next to an ORCA12 time step (7.9 GB)
+        kc = max(1, min(self.nz, int(2.5e8 // max(self.ncell, 1))))
+        tmp = torch.empty((kc, self.ny, self.nx), dtype=torch.float64, device=device)
         acc = torch.empty_like(tmp)
         nan = float('nan')
         for i in range(nt_local):
             a1, a2 = self.coeffs(t0 + i)
             a1 = torch.from_numpy(a1).to(device)[:, None, None]
             a2 = torch.from_numpy(a2).to(device)[:, None, None]
-            for dst, A, B in ((u, U1, U2), (v, V1, V2)):
-                torch.mul(a1, A[None], out=acc)
-                torch.mul(a2, B[None], out=tmp)
-                acc.add_(tmp)
-                if mask is not None:
-                    acc.masked_fill_(mask, nan)
-                dst[i].copy_(acc)
+            for k0 in range(0, self.nz, kc):
+                k1 = min(self.nz, k0 + kc)
+                n = k1 - k0
+                for dst, A, B in ((u, U1, U2), (v, V1, V2)):
+                    torch.mul(a1[k0:k1], A[None], out=acc[:n])          # same operations, same order as uv_host
+                    torch.mul(a2[k0:k1], B[None], out=tmp[:n])
+                    acc[:n].add_(tmp[:n])
+                    if mask is not None:
+                        acc[:n].masked_fill_(mask[k0:k1], nan)
+                    dst[i, k0:k1].copy_(acc[:n])
         return u, v
 
     # ---- transects -----------------------------------------------------------------------------------

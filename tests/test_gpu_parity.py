@@ -314,3 +314,34 @@ def test_c2_series_linear_in_time(gpu, oracle):
     assert numpy.abs(s - ref).max() <= 1e-12 * numpy.abs(ref).max()
     assert numpy.allclose(s[:, 0] / s[0, 0], numpy.arange(1, 21), rtol=1e-12)
     assert abs(s[0, 0] - 1.7386322852896516) <= 1e-11
+
+
+@pytest.mark.parametrize('cfg', [0, 2, 3, 6, 7])
+def test_k2_tma_variant_bit_exact(gpu, oracle, cfg):
+    """the TMA (cp.async.bulk) staged variant gives the same bits as the direct-load kernel and the oracle,
+    including ragged tiles (ncell not a multiple of the tile) and a level count that is no multiple of KL"""
+    import torch
+    from nemoflux_b200 import _lib
+    rng = numpy.random.default_rng(17 + cfg)
+    d = 'cuda'
+    try:
+        for (nt, nz, ny, nx) in [(3, 75, 26, 42), (2, 7, 9, 14), (5, 16, 40, 64), (1, 1, 2, 3)]:
+            u, v = _rand_uv(rng, nt, nz, ny, nx, numpy.float64)
+            th = rng.uniform(0.5, 20., nz)
+            a1 = rng.uniform(1e-3, 2e-2, ny * nx)
+            a2 = rng.uniform(1e-3, 2e-2, ny * nx)
+            args = [torch.from_numpy(x).to(d) for x in (u, v, th, a1, a2)]
+            _lib.set_option(_lib.NFX_OPT_K2_VARIANT, _lib.NFX_K2_TMA)
+            _lib.set_option(_lib.NFX_OPT_K2_UNROLL, cfg)
+            ef = gpu.edgeFluxAssemble(*args, sverdrup=True).cpu().numpy()
+            _lib.set_option(_lib.NFX_OPT_K2_VARIANT, _lib.NFX_K2_LDG)
+            _lib.set_option(_lib.NFX_OPT_K2_UNROLL, 0)
+            ef2 = gpu.edgeFluxAssemble(*args, sverdrup=True).cpu().numpy()
+            assert_bitwise(ef, ef2, 'TMA vs LDG')
+            for t in range(nt):
+                _, eU, eV = oracle.edgeflux_step_c(u[t], v[t], th, a1, a2, True)
+                assert_bitwise(ef[t, :ny * nx], eU, 'eU')
+                assert_bitwise(ef[t, ny * nx:], eV, 'eV')
+    finally:
+        _lib.set_option(_lib.NFX_OPT_K2_VARIANT, _lib.NFX_K2_AUTO)
+        _lib.set_option(_lib.NFX_OPT_K2_UNROLL, 0)

@@ -31,7 +31,7 @@ def main():
         ncell = nx * ny
         for dt in a.dtypes.split(','):
             tdt, es = (torch.float64, 8) if dt == 'f64' else (torch.float32, 4)
-            nt = max(1, int(a.gb * 1e9 / (2 * es * nz * ncell)))
+            nt = max(2, int(a.gb * 1e9 / (2 * es * nz * ncell)))
             u = torch.randn((nt, nz, ncell), dtype=tdt, device=dev)
             v = torch.randn((nt, nz, ncell), dtype=tdt, device=dev)
             th = torch.rand(nz, dtype=torch.float64, device=dev)
@@ -42,7 +42,7 @@ def main():
             ref = None
             for variant, unroll, block in [(1, 5, 256), (1, 3, 256), (1, 8, 256), (1, 15, 256), (1, 5, 128), (1, 8, 128),
                                            (1, 15, 128), (1, 5, 512), (1, 3, 512), (3, 5, 256), (3, 8, 256), (3, 15, 256),
-                                           (3, 15, 128), (3, 5, 512), (2, 0, 0)]:
+                                           (3, 15, 128), (3, 5, 512)] + [(2, c, 0) for c in range(9)]:
                 try:
                     _lib.set_option(_lib.NFX_OPT_K2_VARIANT, variant)
                     _lib.set_option(_lib.NFX_OPT_K2_UNROLL, unroll)

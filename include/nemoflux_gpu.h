@@ -50,6 +50,8 @@ extern "C" {
 #define NFX_OPT_K2_VARIANT 1
 #define NFX_OPT_K2_UNROLL 2   /* levels in flight per thread (0 = default) */
 #define NFX_OPT_K2_BLOCK 3    /* threads per CTA (0 = default)             */
+#define NFX_OPT_FAST_SERIES 4 /* 1 (default): nfx_flux_series with eflux == NULL keeps the edge fluxes in L2 */
+#define NFX_OPT_RING_SLOT_MB 5 /* size of one eflux ring slot of that path in MB (default 8)                */
 
 typedef struct nfx_grid nfx_grid;
 typedef struct nfx_pli nfx_pli;
@@ -121,6 +123,9 @@ int nfx_edgeflux_absmax(const double* eflux, int nt, int64_t ncell, double* resu
 /* series device (nt, ntransects): sum_n w_n * eflux[t, index(cell_n, edge_n)]; needs
  * nfx_grid_set_cgrid_shape before nfx_pli_compute_weights* */
 int nfx_pli_integrate(nfx_pli** self, const double* eflux, int nt, int order, double* series, void* stream);
+/* nfx_flux_series: eflux may be NULL -- then the edge fluxes are not materialised in HBM at all: K2 writes
+ * them into a small ring that stays in L2 and K3 consumes them from there (the fast path).  With eflux != NULL
+ * the (nt, 2*ncell) array is produced as by nfx_edgeflux_assemble. */
 int nfx_flux_series(nfx_pli** self, const void* u, const void* v, int dtype, const double* thickness,
                     const double* arc1, const double* arc2, int nt, int nz, int sverdrup, double fill, int order,
                     double* eflux, double* series, void* stream);

@@ -1,5 +1,6 @@
 // extern "C" entry points of libnemoflux_gpu.so -- see include/nemoflux_gpu.h.
 #include <atomic>
+#include <cstdlib>
 #include <cstring>
 
 #include "nfx_common.cuh"
@@ -9,6 +10,8 @@ namespace nfx {
 static thread_local std::string g_last_error;
 static std::atomic<int64_t> g_launches{0};
 static K2Options g_k2opt;
+static int g_fast_series = 1;             // NFX_OPT_FAST_SERIES
+static int64_t g_slot_bytes = 8 << 20;    // NFX_OPT_RING_SLOT_MB
 
 void set_last_error(const std::string& m) { g_last_error = m; }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
@@ -68,6 +71,33 @@ static void free_host_path(PliDev& p) {
     p.copy_stream = p.compute_stream = nullptr;
 }
 
+// K2+K3 with the edge fluxes kept in L2 (nfx_k23_fused.cu): one persistent launch; large grids are cut into
+// panels of cells whose (2, panel) slab of edge fluxes fits a ring slot, their partial sums are added at the end.
+static void flux_series_fast(PliDev& p, const void* u, const void* v, int dtype, const double* thickness,
+                             const double* arc1, const double* arc2, int nt, int nz, int sverdrup, double fill,
+                             int order, double* series, cudaStream_t stream) {
+    NFX_REQUIRE(order == NFX_ORDER_LIST || order == NFX_ORDER_MAP, "order must be NFX_ORDER_LIST or NFX_ORDER_MAP");
+    NFX_REQUIRE(p.csr[order][0].rowptr.p != nullptr, "computeWeights was not called");
+    NFX_REQUIRE(p.has_compact, "nfx_grid_set_cgrid_shape must be called before computeWeights for the flux path");
+    const int64_t ncell = p.grid->ncell;
+    const int M = p.ntransects;
+    if (nt <= 0 || M <= 0) return;
+    int64_t panel = ncell;
+    if (ncell * 16 > g_slot_bytes) {
+        const int64_t np0 = (ncell * 16 + g_slot_bytes - 1) / g_slot_bytes;
+        panel = ((ncell + np0 - 1) / np0 + 1023) / 1024 * 1024;
+    }
+    PanelPlan& pl = p.plan[order];
+    if (!pl.built || pl.panel_cells != panel) build_panel_plan(p, order, panel, stream);
+    double* out = series;
+    if (pl.npanels > 1) {
+        p.partial.ensure((size_t)nt * pl.npanels * M);
+        out = p.partial.p;
+    }
+    flux_series_fused(p, pl, u, v, dtype, thickness, arc1, arc2, nt, nz, sverdrup, fill, out, stream);
+    if (pl.npanels > 1) reduce_panels(p.partial.p, nt, pl.npanels, M, series, stream);
+}
+
 static const Csr& pick_csr(PliDev& p, int order, int layout) {
     NFX_REQUIRE(order == NFX_ORDER_LIST || order == NFX_ORDER_MAP, "order must be NFX_ORDER_LIST or NFX_ORDER_MAP");
     NFX_REQUIRE(p.csr[order][0].rowptr.p != nullptr, "computeWeights was not called");
@@ -106,6 +136,11 @@ int nfx_set_option(int option, int value) {
                 break;
             case NFX_OPT_K2_UNROLL: g_k2opt.unroll = value; break;
             case NFX_OPT_K2_BLOCK: g_k2opt.block = value; break;
+            case NFX_OPT_FAST_SERIES: g_fast_series = value ? 1 : 0; break;
+            case NFX_OPT_RING_SLOT_MB:
+                NFX_REQUIRE(value >= 1 && value <= 64, "ring slot must be 1..64 MB");
+                g_slot_bytes = (int64_t)value << 20;
+                break;
             default: throw Error(NFX_E_INVALID, "unknown option");
         }
     });
@@ -118,6 +153,8 @@ int nfx_get_option(int option, int* value) {
             case NFX_OPT_K2_VARIANT: *value = g_k2opt.variant; break;
             case NFX_OPT_K2_UNROLL: *value = g_k2opt.unroll; break;
             case NFX_OPT_K2_BLOCK: *value = g_k2opt.block; break;
+            case NFX_OPT_FAST_SERIES: *value = g_fast_series; break;
+            case NFX_OPT_RING_SLOT_MB: *value = (int)(g_slot_bytes >> 20); break;
             default: throw Error(NFX_E_INVALID, "unknown option");
         }
     });
@@ -387,7 +424,17 @@ int nfx_flux_series(nfx_pli** self, const void* u, const void* v, int dtype, con
         PliDev& p = (*self)->d;
         NFX_REQUIRE(p.grid, "setGrid was not called");
         DeviceGuard g(p.grid->device);
+        NFX_REQUIRE(u && v && thickness && arc1 && arc2 && series, "NULL pointer");
+        if (eflux == nullptr && g_fast_series) {
+            flux_series_fast(p, u, v, dtype, thickness, arc1, arc2, nt, nz, sverdrup, fill, order, series,
+                             (cudaStream_t)stream);
+            return;
+        }
         const Csr& c = pick_csr(p, order, 1);
+        if (eflux == nullptr) {   // fused pass switched off: the two-launch path with an internal eflux array
+            p.stage_eflux[0].ensure((size_t)nt * 2 * p.grid->ncell);
+            eflux = p.stage_eflux[0].p;
+        }
         edgeflux_assemble(u, v, dtype, thickness, arc1, arc2, nt, nz, p.grid->ncell, sverdrup, fill, eflux, g_k2opt,
                           (cudaStream_t)stream);
         csr_integrate(c, p.ntransects, eflux, p.grid->ncell * 2, nt, series, (cudaStream_t)stream);
@@ -428,7 +475,7 @@ int nfx_flux_series_host(nfx_pli** self, const void* u, const void* v, int dtype
         for (int i = 0; i < 2; ++i) {
             p.stage_u[i].ensure(step_bytes * chunk_steps);
             p.stage_v[i].ensure(step_bytes * chunk_steps);
-            p.stage_eflux[i].ensure((size_t)chunk_steps * 2 * ncell);
+            if (!g_fast_series) p.stage_eflux[i].ensure((size_t)chunk_steps * 2 * ncell);
         }
         p.stage_series.ensure((size_t)nt * M);
         p.stage_thick.ensure(nz);
@@ -449,15 +496,22 @@ int nfx_flux_series_host(nfx_pli** self, const void* u, const void* v, int dtype
             NFX_CUDA(cudaMemcpyAsync(p.stage_v[slot].p, hv, step_bytes * n, cudaMemcpyHostToDevice, cs));
             NFX_CUDA(cudaEventRecord(p.ev_ready[slot], cs));
             NFX_CUDA(cudaStreamWaitEvent(ks, p.ev_ready[slot], 0));
-            edgeflux_assemble(p.stage_u[slot].p, p.stage_v[slot].p, dtype, p.stage_thick.p, p.stage_arc1.p,
-                              p.stage_arc2.p, n, nz, ncell, sverdrup, fill, p.stage_eflux[slot].p, g_k2opt, ks);
-            csr_integrate(c, M, p.stage_eflux[slot].p, ncell * 2, n, p.stage_series.p + (size_t)t0 * M, ks);
+            if (g_fast_series) {
+                flux_series_fast(p, p.stage_u[slot].p, p.stage_v[slot].p, dtype, p.stage_thick.p, p.stage_arc1.p,
+                                 p.stage_arc2.p, n, nz, sverdrup, fill, order, p.stage_series.p + (size_t)t0 * M, ks);
+            } else {
+                edgeflux_assemble(p.stage_u[slot].p, p.stage_v[slot].p, dtype, p.stage_thick.p, p.stage_arc1.p,
+                                  p.stage_arc2.p, n, nz, ncell, sverdrup, fill, p.stage_eflux[slot].p, g_k2opt, ks);
+                csr_integrate(c, M, p.stage_eflux[slot].p, ncell * 2, n, p.stage_series.p + (size_t)t0 * M, ks);
+            }
             NFX_CUDA(cudaEventRecord(p.ev_done[slot], ks));
             used[slot] = true;
         }
         NFX_CUDA(cudaMemcpyAsync(series, p.stage_series.p, sizeof(double) * (size_t)nt * M, cudaMemcpyDeviceToHost, ks));
         NFX_CUDA(cudaStreamSynchronize(ks));
         NFX_CUDA(cudaStreamSynchronize(cs));
+        if (g_fast_series && fused_error_flag(p, ks) != 0)
+            throw Error(NFX_E_INTERNAL, "fused K2+K3 pass aborted (a bounded wait overflowed)");
     });
 }
 

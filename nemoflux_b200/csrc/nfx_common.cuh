@@ -82,6 +82,18 @@ struct Csr {
     const double* w = nullptr;  // borrowed: PliDev::w (list order) or PliDev::map_w (map order)
 };
 
+// CSR grouped by (panel of cells, transect) for the L2-resident fast path of nfx_flux_series: row = panel*M + m,
+// idx = panel-local index into a (2, panel_cols) slab [eU | eV]; entries that always read 0 are dropped
+struct PanelPlan {
+    bool built = false;
+    int64_t panel_cells = 0;
+    int npanels = 0;
+    int64_t nnz = 0;
+    DevBuf<int64_t> rowptr;   // (npanels*M + 1)
+    DevBuf<int32_t> idx;
+    DevBuf<double> w;
+};
+
 struct PliDev {
     GridDev* grid = nullptr;   // borrowed; never dereferenced by nfx_pli_del (the grid may already be gone)
     int device = 0;
@@ -101,6 +113,9 @@ struct PliDev {
     // CSRs: [order][layout]; layout 0 = (ncell,4) cell-by-cell data, 1 = compact [eU|eV]
     Csr csr[2][2];
     bool has_compact = false;
+    PanelPlan plan[2];            // per summation order
+    DevBuf<double> ring, partial;  // L2-resident eflux ring and per-panel partial sums of the fused pass
+    DevBuf<int> fused_sync;        // work counter, error flag, per-batch completion counters
     std::vector<int64_t> h_sub_offsets, h_map_offsets;
     // scratch reused by the host-buffer entry points
     DevBuf<double> scratch_data, scratch_res;
@@ -126,11 +141,24 @@ struct K2Options {
 void edgeflux_assemble(const void* u, const void* v, int dtype, const double* thickness, const double* arc1,
                        const double* arc2, int nt, int nz, int64_t ncell, int sverdrup, double fill, double* eflux,
                        const K2Options& opt, cudaStream_t s);
+void edgeflux_assemble_panel(const void* u, const void* v, int dtype, const double* thickness, const double* arc1,
+                             const double* arc2, int nt, int nz, int64_t ncols, int64_t ld, int sverdrup, double fill,
+                             double* eflux, int keep_l2, const K2Options& opt, cudaStream_t s);
 void edgeflux_to_cell_by_cell(const double* eflux, int nt, int ny, int nx, double* iv, cudaStream_t s);
 void edgeflux_absmax(const double* eflux, int nt, int64_t ncell, double* result_host, cudaStream_t s);
 
 // K3 (nfx_k3_reduce.cu)
 void csr_integrate(const Csr& c, int ntransects, const double* data, int64_t stride_t, int nt, double* series,
                    cudaStream_t s);
+void rows_integrate(const int64_t* rowptr, const int32_t* idx, const double* w, int nrows, const double* data,
+                    int64_t stride_t, int nt, double* out, int64_t out_stride_t, cudaStream_t s);
+void reduce_panels(const double* partial, int nt, int npanels, int ntransects, double* series, cudaStream_t s);
+void build_panel_plan(PliDev& p, int order, int64_t panel_cells, cudaStream_t s);
+
+// K2+K3 fused persistent pass (nfx_k23_fused.cu)
+void flux_series_fused(PliDev& p, const PanelPlan& pl, const void* u, const void* v, int dtype, const double* thickness,
+                       const double* arc1, const double* arc2, int nt, int nz, int sverdrup, double fill, double* out,
+                       cudaStream_t s);
+int fused_error_flag(PliDev& p, cudaStream_t s);
 
 }  // namespace nfx

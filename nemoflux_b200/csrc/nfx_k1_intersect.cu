@@ -578,7 +578,77 @@ __global__ void k_scale_offsets(const int64_t* __restrict__ in, int n, int64_t m
 
 inline unsigned nblk(int64_t n, int b) { return (unsigned)std::max<int64_t>(1, (n + b - 1) / b); }
 
+// ---- panel plan: CSR rows (panel, transect) -------------------------------------------------------------
+constexpr int kMaxPanels = 64;
+
+// one thread per transect, sequential over its entries (keeps the entry order inside every row -> deterministic)
+template <bool FILL>
+__global__ void k_panel_rows(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ idx,
+                             const double* __restrict__ w, int ntransects, int64_t ncell, int64_t panel_cells,
+                             int npanels, int64_t* __restrict__ counts, const int64_t* __restrict__ prow,
+                             int32_t* __restrict__ pidx, double* __restrict__ pw) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= ntransects) return;
+    int64_t pos[kMaxPanels];
+    for (int q = 0; q < npanels; ++q) pos[q] = FILL ? prow[(int64_t)q * ntransects + m] : 0;
+    for (int64_t n = rowptr[m]; n < rowptr[m + 1]; ++n) {
+        const int32_t f = idx[n];
+        if (f < 0) continue;   // south edge of row 0: always 0 (field.py:61,219)
+        const int is_v = f >= ncell;
+        const int64_t c = is_v ? f - ncell : f;
+        const int q = (int)(c / panel_cells);
+        if (FILL) {
+            const int64_t c0 = (int64_t)q * panel_cells;
+            const int64_t pc = min(panel_cells, ncell - c0);
+            pidx[pos[q]] = (int32_t)((c - c0) + (is_v ? pc : 0));
+            pw[pos[q]] = w[n];
+        }
+        ++pos[q];
+    }
+    if (!FILL)
+        for (int q = 0; q < npanels; ++q) counts[(int64_t)q * ntransects + m] = pos[q];
+}
+
 }  // namespace
+
+void build_panel_plan(PliDev& p, int order, int64_t panel_cells, cudaStream_t s) {
+    NFX_REQUIRE(p.has_compact, "the flux path needs nfx_grid_set_cgrid_shape before computeWeights");
+    PanelPlan& pl = p.plan[order];
+    const Csr& c = p.csr[order][1];
+    const int64_t ncell = p.grid->ncell;
+    const int M = p.ntransects;
+    const int npanels = (int)((ncell + panel_cells - 1) / panel_cells);
+    NFX_REQUIRE(npanels >= 1 && npanels <= kMaxPanels, "panel plan: too many panels");
+    pl.panel_cells = panel_cells;
+    pl.npanels = npanels;
+    const int64_t nrows = (int64_t)npanels * M;
+    pl.rowptr.ensure((size_t)nrows + 1);
+    if (M == 0 || c.nnz == 0) {
+        NFX_CUDA(cudaMemsetAsync(pl.rowptr.p, 0, sizeof(int64_t) * (nrows + 1), s));
+        pl.nnz = 0;
+        pl.built = true;
+        return;
+    }
+    DevBuf<int64_t> counts, tmp;
+    counts.alloc((size_t)nrows);
+    k_panel_rows<false><<<nblk(M, 64), 64, 0, s>>>(c.rowptr.p, c.idx.p, c.w, M, ncell, panel_cells, npanels, counts.p,
+                                                  nullptr, nullptr, nullptr);
+    count_launch();
+    NFX_CUDA(cudaGetLastError());
+    exclusive_scan(counts.p, pl.rowptr.p, nrows, tmp, s);
+    int64_t nnz = 0;
+    NFX_CUDA(cudaMemcpyAsync(&nnz, pl.rowptr.p + nrows, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    NFX_CUDA(cudaStreamSynchronize(s));
+    pl.nnz = nnz;
+    pl.idx.ensure((size_t)std::max<int64_t>(nnz, 1));
+    pl.w.ensure((size_t)std::max<int64_t>(nnz, 1));
+    k_panel_rows<true><<<nblk(M, 64), 64, 0, s>>>(c.rowptr.p, c.idx.p, c.w, M, ncell, panel_cells, npanels, nullptr,
+                                                 pl.rowptr.p, pl.idx.p, pl.w.p);
+    count_launch();
+    NFX_CUDA(cudaGetLastError());
+    NFX_CUDA(cudaStreamSynchronize(s));
+    pl.built = true;
+}
 
 // ---- host side --------------------------------------------------------------------------------------
 void grid_upload_points(GridDev& g, int64_t ncells, const double* points_host) {
@@ -643,6 +713,7 @@ void pli_compute_weights(PliDev& p, int ntransects, const int* offsets, const do
     p.h_sub_offsets.assign(ntransects + 1, 0);
     p.h_map_offsets.assign(ntransects + 1, 0);
     p.has_compact = (g.ny > 0 && g.nx > 0);
+    p.plan[0].built = p.plan[1].built = false;
     for (int o = 0; o < 2; ++o)
         for (int l = 0; l < 2; ++l) p.csr[o][l].nnz = 0;
     p.sub_offsets.ensure(ntransects + 1);

@@ -1,0 +1,333 @@
+// K2+K3 fused, persistent: the whole flux time series in ONE launch, edge fluxes never reach HBM.
+//
+// Why: measured with tools/readbw.cu on a B200 the u/v stream alone runs at 7.47 TB/s, but writing the
+// edge fluxes (1.3 % of the traffic) costs 10 % (DRAM read/write turnarounds), 5 % with evict-first stores,
+// and 0.4 % when they go, with L2::evict_last, to a small ring that is overwritten while still in L2.  K3
+// then gathers from L2 instead of HBM.  Cutting the work into batches launched one after the other loses
+// more to launch tails than it wins (profiles/r1_fused_notes.md), hence one persistent kernel.
+//
+// Work is cut into batches b = (time step t, panel q of cells) whose (2, panel) slab of edge fluxes fits a
+// ring slot; the ring has R slots.  Work items are handed out in a fixed global order by an atomic counter:
+//     ... | K2 tiles of batch b (ntiles items) | K3 items of batch b-1 (nk3 items) | K2 tiles of b+1 | ...
+// K2 item: z-sum + metric factors for 256*VEC columns (field.py:145-163, 195-196, 225-228), written to ring
+//          slot b % R; waits (b >= R) until K3 of batch b-R has finished reading that slot.
+// K3 item: 8 transects x batch b: one warp per transect gathers from the slot (L2) and writes
+//          partial[(t, q), m]; waits until all K2 tiles of batch b are done.
+// Every wait is on items with a SMALLER id, i.e. items already taken by a running CTA -> no deadlock, whatever
+// the number of resident CTAs.  Spins are bounded; on overflow an error flag is raised instead of hanging.
+//
+// Arithmetic is the same as in the two-launch path (nfx_k2_edgeflux.cu, nfx_k3_reduce.cu): same per-column
+// sums, same per-row lane order and shuffle tree -> bit-identical series.
+#include <algorithm>
+
+#include "nfx_common.cuh"
+#include "nfx_stream_ops.cuh"
+
+namespace nfx {
+
+namespace {
+
+using namespace dev;
+
+constexpr int kFusedBlock = 256;
+constexpr int kK3Rows = kFusedBlock / 32;   // transects per K3 item
+constexpr unsigned kSpinLimit = 1u << 27;
+
+struct FusedArgs {
+    const void* u;
+    const void* v;
+    const double* dz;
+    const double* arc1;
+    const double* arc2;
+    double* ring;           // ring_slots slots of slot_elems doubles: [eU(panel) | eV(panel)]
+    double* out;            // (nt, npanels, M) partial sums (== the series when npanels == 1)
+    const int64_t* rowptr;  // (npanels*M + 1)
+    const int32_t* idx;
+    const double* w;
+    int* sync;              // [0] work counter, [1] error flag, [2 .. 2+nb) K2 tiles done, [2+nb .. 2+2nb) K3 items done
+    int64_t ncell, panel, slot_elems;
+    int nt, nz, ntransects, npanels, nbatches, ntiles, nk3, ring_slots;
+    double scale, fill;
+    int use_scale, has_fill;
+};
+
+__device__ __forceinline__ int ld_acquire(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// thread 0 spins until *flag >= target, then the CTA continues; returns false on overflow (error raised)
+__device__ __forceinline__ bool cta_wait(const int* flag, int target, int* err, int* s_ok) {
+    if (threadIdx.x == 0) {
+        unsigned spins = 0;
+        int ok = 1;
+        while (ld_acquire(flag) < target) {
+            __nanosleep(64);
+            if (++spins > kSpinLimit || ld_acquire(err) != 0) {
+                atomicExch(err, 1);
+                ok = 0;
+                break;
+            }
+        }
+        *s_ok = ok;
+    }
+    __syncthreads();
+    const bool ok = *s_ok != 0;
+    __syncthreads();
+    return ok;
+}
+
+template <typename T, int VEC, int UNROLL>
+__global__ void __launch_bounds__(kFusedBlock)
+k23_fused(const FusedArgs a) {
+    extern __shared__ double s_dz[];
+    __shared__ int s_item;
+    __shared__ int s_ok;
+    for (int k = threadIdx.x; k < a.nz; k += kFusedBlock) s_dz[k] = a.dz[k];
+    __syncthreads();
+    using P = Pack<T, VEC>;
+    using V = typename P::type;
+    const T* __restrict__ u = reinterpret_cast<const T*>(a.u);
+    const T* __restrict__ v = reinterpret_cast<const T*>(a.v);
+    int* counter = a.sync;
+    int* err = a.sync + 1;
+    int* k2done = a.sync + 2;
+    int* k3done = a.sync + 2 + a.nbatches;
+    const int per_batch = a.ntiles + a.nk3;
+    const int64_t nitems = (int64_t)(a.nbatches + 1) * per_batch;
+    const uint64_t pol = l2_evict_last_policy();
+    const T fill = (T)a.fill;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+
+    for (;;) {
+        if (threadIdx.x == 0) s_item = atomicAdd(counter, 1);
+        __syncthreads();
+        const int64_t item = s_item;
+        __syncthreads();
+        if (item >= nitems) break;
+        const int bb = (int)(item / per_batch);
+        const int r = (int)(item - (int64_t)bb * per_batch);
+        if (r < a.ntiles) {
+            // ------------------------------- K2 tile of batch bb -------------------------------
+            const int b = bb;
+            if (b >= a.nbatches) continue;
+            if (b >= a.ring_slots && !cta_wait(k3done + (b - a.ring_slots), a.nk3, err, &s_ok)) break;
+            const int64_t t = b / a.npanels;
+            const int q = b - (int)t * a.npanels;
+            const int64_t pc0 = (int64_t)q * a.panel;
+            const int64_t pc = min(a.panel, a.ncell - pc0);
+            const int64_t cl = ((int64_t)r * kFusedBlock + threadIdx.x) * VEC;   // column inside the panel
+            if (cl < pc) {
+                const int64_t c = pc0 + cl;
+                const T* pu = u + t * a.nz * a.ncell + c;
+                const T* pv = v + t * a.nz * a.ncell + c;
+                double su[VEC], sv[VEC];
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) {
+                    su[e] = 0.0;
+                    sv[e] = 0.0;
+                }
+                int k = 0;
+                for (; k + UNROLL <= a.nz; k += UNROLL) {
+                    V ru[UNROLL], rv[UNROLL];
+#pragma unroll
+                    for (int qq = 0; qq < UNROLL; ++qq) {
+                        ru[qq] = ld_stream(reinterpret_cast<const V*>(pu + (int64_t)(k + qq) * a.ncell));
+                        rv[qq] = ld_stream(reinterpret_cast<const V*>(pv + (int64_t)(k + qq) * a.ncell));
+                    }
+#pragma unroll
+                    for (int qq = 0; qq < UNROLL; ++qq) {
+                        pin(ru[qq]);
+                        pin(rv[qq]);
+                    }
+#pragma unroll
+                    for (int qq = 0; qq < UNROLL; ++qq) {
+                        T x[VEC], y[VEC];
+                        P::unpack(ru[qq], x);
+                        P::unpack(rv[qq], y);
+                        const double d = s_dz[k + qq];
+#pragma unroll
+                        for (int e = 0; e < VEC; ++e) {
+                            su[e] = __dadd_rn(su[e], __dmul_rn(d, clean<T>(x[e], fill, a.has_fill)));
+                            sv[e] = __dadd_rn(sv[e], __dmul_rn(d, clean<T>(y[e], fill, a.has_fill)));
+                        }
+                    }
+                }
+                for (; k < a.nz; ++k) {
+                    T x[VEC], y[VEC];
+                    P::unpack(ld_stream(reinterpret_cast<const V*>(pu + (int64_t)k * a.ncell)), x);
+                    P::unpack(ld_stream(reinterpret_cast<const V*>(pv + (int64_t)k * a.ncell)), y);
+                    const double d = s_dz[k];
+#pragma unroll
+                    for (int e = 0; e < VEC; ++e) {
+                        su[e] = __dadd_rn(su[e], __dmul_rn(d, clean<T>(x[e], fill, a.has_fill)));
+                        sv[e] = __dadd_rn(sv[e], __dmul_rn(d, clean<T>(y[e], fill, a.has_fill)));
+                    }
+                }
+                double* ou = a.ring + (int64_t)(b % a.ring_slots) * a.slot_elems + cl;
+                double* ov = ou + pc;
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) {
+                    double fu = __dmul_rn(su[e], a.arc1[c + e]);
+                    double fv = __dmul_rn(-sv[e], a.arc2[c + e]);
+                    if (a.use_scale) {
+                        fu = __dmul_rn(fu, a.scale);
+                        fv = __dmul_rn(fv, a.scale);
+                    }
+                    su[e] = fu;
+                    sv[e] = fv;
+                }
+                if constexpr (VEC % 2 == 0) {
+#pragma unroll
+                    for (int e = 0; e < VEC; e += 2) {
+                        st_stream2(ou + e, su[e], su[e + 1 < VEC ? e + 1 : e], 1, pol);
+                        st_stream2(ov + e, sv[e], sv[e + 1 < VEC ? e + 1 : e], 1, pol);
+                    }
+                } else {
+#pragma unroll
+                    for (int e = 0; e < VEC; ++e) {
+                        st_stream1(ou + e, su[e], 1, pol);
+                        st_stream1(ov + e, sv[e], 1, pol);
+                    }
+                }
+                __threadfence();
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) atomicAdd(k2done + b, 1);
+        } else {
+            // ------------------------------- K3 item of batch bb-1 -------------------------------
+            const int b = bb - 1;
+            if (b < 0) continue;
+            if (!cta_wait(k2done + b, a.ntiles, err, &s_ok)) break;
+            __threadfence();
+            const int64_t t = b / a.npanels;
+            const int q = b - (int)t * a.npanels;
+            const int m = (r - a.ntiles) * kK3Rows + wid;
+            if (m < a.ntransects) {
+                const int64_t row = (int64_t)q * a.ntransects + m;
+                const int64_t r0 = a.rowptr[row], r1 = a.rowptr[row + 1];
+                const double* d = a.ring + (int64_t)(b % a.ring_slots) * a.slot_elems;
+                double acc = 0.0;
+#pragma unroll 4
+                for (int64_t n = r0 + lane; n < r1; n += 32) acc = fma(a.w[n], __ldcg(d + a.idx[n]), acc);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                if (lane == 0) a.out[(t * a.npanels + q) * a.ntransects + m] = acc;
+            }
+            __threadfence();
+            __syncthreads();
+            if (threadIdx.x == 0) atomicAdd(k3done + b, 1);
+        }
+    }
+}
+
+template <typename T, int VEC>
+int fused_grid() {
+    static int grid = 0;
+    if (grid == 0) {
+        int dev = 0, sms = 0, per_sm = 0;
+        NFX_CUDA(cudaGetDevice(&dev));
+        NFX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        NFX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k23_fused<T, VEC, 5>, kFusedBlock,
+                                                               sizeof(double) * 128));
+        grid = sms * std::max(per_sm, 1);
+    }
+    return grid;
+}
+
+template <typename T, int VEC>
+void launch_fused(const FusedArgs& a, cudaStream_t s) {
+    k23_fused<T, VEC, 5><<<fused_grid<T, VEC>(), kFusedBlock, sizeof(double) * a.nz, s>>>(a);
+}
+
+int fused_grid_for(int dtype, int vec) {
+    if (dtype == NFX_F64) return vec == 4 ? fused_grid<double, 4>() : vec == 2 ? fused_grid<double, 2>() : fused_grid<double, 1>();
+    return vec == 8 ? fused_grid<float, 8>() : vec == 4 ? fused_grid<float, 4>() : fused_grid<float, 1>();
+}
+
+}  // namespace
+
+int fused_tile_columns(int dtype, const void* u, const void* v, int64_t ncell, int64_t panel) {
+    // widest vector the alignment of every level row and panel start allows
+    const uintptr_t bits = ((uintptr_t)u) | ((uintptr_t)v);
+    const bool a16 = (bits & 15) == 0, a32 = (bits & 31) == 0;
+    if (dtype == NFX_F64) {
+        if (a32 && ncell % 4 == 0 && panel % 4 == 0) return 4;
+        if (a16 && ncell % 2 == 0 && panel % 2 == 0) return 2;
+        return 1;
+    }
+    if (a32 && ncell % 8 == 0 && panel % 8 == 0) return 8;
+    if (a16 && ncell % 4 == 0 && panel % 4 == 0) return 4;
+    return 1;
+}
+
+void flux_series_fused(PliDev& p, const PanelPlan& pl, const void* u, const void* v, int dtype, const double* thickness,
+                       const double* arc1, const double* arc2, int nt, int nz, int sverdrup, double fill, double* out,
+                       cudaStream_t s) {
+    const int64_t ncell = p.grid->ncell;
+    const int M = p.ntransects;
+    const int vec = fused_tile_columns(dtype, u, v, ncell, pl.panel_cells);
+    FusedArgs a;
+    a.u = u;
+    a.v = v;
+    a.dz = thickness;
+    a.arc1 = arc1;
+    a.arc2 = arc2;
+    a.ncell = ncell;
+    a.panel = pl.panel_cells;
+    a.slot_elems = 2 * std::min(pl.panel_cells, ncell);
+    a.nt = nt;
+    a.nz = nz;
+    a.ntransects = M;
+    a.npanels = pl.npanels;
+    a.nbatches = nt * pl.npanels;
+    a.ntiles = (int)((std::min(pl.panel_cells, ncell) + (int64_t)kFusedBlock * vec - 1) / ((int64_t)kFusedBlock * vec));
+    a.nk3 = (M + kK3Rows - 1) / kK3Rows;
+    a.scale = 6371000.0 / 1.e6;
+    a.fill = fill;
+    a.use_scale = sverdrup;
+    a.has_fill = !(fill != fill);
+    a.rowptr = pl.rowptr.p;
+    a.idx = pl.idx.p;
+    a.w = pl.w.p;
+    a.out = out;
+    NFX_REQUIRE(nz <= 6000, "edgeflux: at most 6000 levels");
+    NFX_REQUIRE((int64_t)(a.nbatches + 1) * (a.ntiles + a.nk3) < 2000000000ll, "fused pass: too many work items");
+    // enough slots that every resident CTA finds a K2 tile while the K3 of older batches drains (x2 margin),
+    // but no more than ~64 MB of evict-last lines in the 126 MB L2
+    const int resident = fused_grid_for(dtype, vec);
+    int slots = (2 * resident + a.ntiles - 1) / a.ntiles + 1;
+    const int64_t cap = std::max<int64_t>(3, ((int64_t)64 << 20) / (a.slot_elems * 8));
+    slots = (int)std::min<int64_t>(std::max(slots, 3), cap);
+    a.ring_slots = slots;
+    p.ring.ensure((size_t)(a.slot_elems * slots));
+    NFX_CUDA(cudaMemsetAsync(out, 0xFF, sizeof(double) * (size_t)nt * pl.npanels * M, s));   // NaN: a pass that
+    // aborts (bounded spin overflow) must not leave plausible numbers behind
+    p.fused_sync.ensure((size_t)(2 + 2 * a.nbatches));
+    a.ring = p.ring.p;
+    a.sync = p.fused_sync.p;
+    NFX_CUDA(cudaMemsetAsync(a.sync, 0, sizeof(int) * (2 + 2 * a.nbatches), s));
+    if (dtype == NFX_F64) {
+        if (vec == 4) launch_fused<double, 4>(a, s);
+        else if (vec == 2) launch_fused<double, 2>(a, s);
+        else launch_fused<double, 1>(a, s);
+    } else {
+        if (vec == 8) launch_fused<float, 8>(a, s);
+        else if (vec == 4) launch_fused<float, 4>(a, s);
+        else launch_fused<float, 1>(a, s);
+    }
+    count_launch();
+    NFX_CUDA(cudaGetLastError());
+}
+
+// error flag of the last fused pass (1 = a bounded spin overflowed); synchronises the stream
+int fused_error_flag(PliDev& p, cudaStream_t s) {
+    int h[2] = {0, 0};
+    if (!p.fused_sync.p) return 0;
+    NFX_CUDA(cudaMemcpyAsync(h, p.fused_sync.p, sizeof h, cudaMemcpyDeviceToHost, s));
+    NFX_CUDA(cudaStreamSynchronize(s));
+    return h[1];
+}
+
+}  // namespace nfx

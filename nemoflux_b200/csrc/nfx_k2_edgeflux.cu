@@ -20,141 +20,21 @@
 #include <algorithm>
 
 #include "nfx_common.cuh"
+#include "nfx_stream_ops.cuh"
 
 namespace nfx {
 
 namespace {
 
-__device__ __forceinline__ double2 ld_stream(const double2* p) {
-    double2 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];"
-                 : "=d"(r.x), "=d"(r.y)
-                 : "l"(p));
-    return r;
-}
-// 256-bit global load (sm_100+): 4 doubles per instruction, with the L2 evict-first hint that only
-// this width accepts -- the u/v stream is read exactly once
-struct __align__(32) double4x {
-    double x, y, z, w;
-};
-struct __align__(32) float8x {
-    float a[8];
-};
-__device__ __forceinline__ double4x ld_stream(const double4x* p) {
-    double4x r;
-    asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v4.f64 {%0, %1, %2, %3}, [%4];"
-                 : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w)
-                 : "l"(p));
-    return r;
-}
-__device__ __forceinline__ float8x ld_stream(const float8x* p) {
-    float8x r;
-    asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                 : "=f"(r.a[0]), "=f"(r.a[1]), "=f"(r.a[2]), "=f"(r.a[3]), "=f"(r.a[4]), "=f"(r.a[5]), "=f"(r.a[6]),
-                   "=f"(r.a[7])
-                 : "l"(p));
-    return r;
-}
-__device__ __forceinline__ double ld_stream(const double* p) {
-    double r;
-    asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(r) : "l"(p));
-    return r;
-}
-__device__ __forceinline__ float4 ld_stream(const float4* p) {
-    float4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
-                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
-                 : "l"(p));
-    return r;
-}
-__device__ __forceinline__ float ld_stream(const float* p) {
-    float r;
-    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
-    return r;
-}
-
-// Register fence: every load of a batch is issued (volatile asm keeps program order) before the
-// first value is consumed, so UNROLL*2 wide loads are in flight per thread instead of one.
-__device__ __forceinline__ void pin(double& x) { asm volatile("" : "+d"(x)); }
-__device__ __forceinline__ void pin(float& x) { asm volatile("" : "+f"(x)); }
-__device__ __forceinline__ void pin(double2& r) { asm volatile("" : "+d"(r.x), "+d"(r.y)); }
-__device__ __forceinline__ void pin(float4& r) { asm volatile("" : "+f"(r.x), "+f"(r.y), "+f"(r.z), "+f"(r.w)); }
-__device__ __forceinline__ void pin(double4x& r) { asm volatile("" : "+d"(r.x), "+d"(r.y), "+d"(r.z), "+d"(r.w)); }
-__device__ __forceinline__ void pin(float8x& r) {
-    asm volatile(""
-                 : "+f"(r.a[0]), "+f"(r.a[1]), "+f"(r.a[2]), "+f"(r.a[3]), "+f"(r.a[4]), "+f"(r.a[5]), "+f"(r.a[6]),
-                   "+f"(r.a[7]));
-}
-
-// eflux is written once and read later by K3: streaming (evict-first) stores.  Measured with
-// tools/readbw.cu: default write-back stores cost 10 % of the read stream (DRAM read/write turnarounds for
-// 1.3 % of the traffic), evict-first stores 5 %.
-__device__ __forceinline__ void st_stream2(double* p, double a, double b) {
-    __stcs(reinterpret_cast<double2*>(p), make_double2(a, b));
-}
-
-template <typename T, int VEC>
-struct Pack;
-template <>
-struct Pack<double, 2> {
-    using type = double2;
-    __device__ static void unpack(const double2& p, double (&o)[2]) {
-        o[0] = p.x;
-        o[1] = p.y;
-    }
-};
-template <>
-struct Pack<double, 4> {
-    using type = double4x;
-    __device__ static void unpack(const double4x& p, double (&o)[4]) {
-        o[0] = p.x;
-        o[1] = p.y;
-        o[2] = p.z;
-        o[3] = p.w;
-    }
-};
-template <>
-struct Pack<float, 8> {
-    using type = float8x;
-    __device__ static void unpack(const float8x& p, float (&o)[8]) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) o[i] = p.a[i];
-    }
-};
-template <>
-struct Pack<double, 1> {
-    using type = double;
-    __device__ static void unpack(const double& p, double (&o)[1]) { o[0] = p; }
-};
-template <>
-struct Pack<float, 4> {
-    using type = float4;
-    __device__ static void unpack(const float4& p, float (&o)[4]) {
-        o[0] = p.x;
-        o[1] = p.y;
-        o[2] = p.z;
-        o[3] = p.w;
-    }
-};
-template <>
-struct Pack<float, 1> {
-    using type = float;
-    __device__ static void unpack(const float& p, float (&o)[1]) { o[0] = p; }
-};
-
-// land / missing values count as zero: NaN (xarray-decoded _FillValue, field.py:157) or == fill
-template <typename T>
-__device__ __forceinline__ double clean(T x, T fill, bool has_fill) {
-    const bool bad = (x != x) || (has_fill && x == fill);
-    return bad ? 0.0 : (double)x;
-}
+using namespace dev;
 
 // One thread owns VEC adjacent columns of one time step; blockIdx.y = time step.
 template <typename T, int VEC, int UNROLL, int BLOCK>
 __global__ void __launch_bounds__(BLOCK)
 k2_edgeflux_ldg(const T* __restrict__ u, const T* __restrict__ v, const double* __restrict__ dz,
                 const double* __restrict__ arc1, const double* __restrict__ arc2, double* __restrict__ eflux, int nz,
-                int64_t ncell, double scale, int use_scale, T fill, int has_fill) {
+                int64_t ncell, int64_t ld, double scale, int use_scale, T fill, int has_fill, int keep_l2) {
+    // ncell = columns handled by this launch (a panel of the grid), ld = cells per level plane (row stride of u, v)
     extern __shared__ double s_dz[];
     for (int k = threadIdx.x; k < nz; k += BLOCK) s_dz[k] = dz[k];
     __syncthreads();
@@ -163,8 +43,9 @@ k2_edgeflux_ldg(const T* __restrict__ u, const T* __restrict__ v, const double* 
     const int64_t t = blockIdx.y;
     const int64_t c0 = ((int64_t)blockIdx.x * BLOCK + threadIdx.x) * VEC;
     if (c0 >= ncell) return;  // VEC divides ncell on the vector path, so c0+VEC <= ncell
-    const T* pu = u + t * nz * ncell + c0;
-    const T* pv = v + t * nz * ncell + c0;
+    const T* pu = u + t * nz * ld + c0;
+    const T* pv = v + t * nz * ld + c0;
+    const uint64_t pol = keep_l2 ? l2_evict_last_policy() : 0;
     double su[VEC], sv[VEC];
 #pragma unroll
     for (int e = 0; e < VEC; ++e) {
@@ -176,8 +57,8 @@ k2_edgeflux_ldg(const T* __restrict__ u, const T* __restrict__ v, const double* 
         V ru[UNROLL], rv[UNROLL];
 #pragma unroll
         for (int q = 0; q < UNROLL; ++q) {
-            ru[q] = ld_stream(reinterpret_cast<const V*>(pu + (int64_t)(k + q) * ncell));
-            rv[q] = ld_stream(reinterpret_cast<const V*>(pv + (int64_t)(k + q) * ncell));
+            ru[q] = ld_stream(reinterpret_cast<const V*>(pu + (int64_t)(k + q) * ld));
+            rv[q] = ld_stream(reinterpret_cast<const V*>(pv + (int64_t)(k + q) * ld));
         }
 #pragma unroll
         for (int q = 0; q < UNROLL; ++q) {
@@ -199,8 +80,8 @@ k2_edgeflux_ldg(const T* __restrict__ u, const T* __restrict__ v, const double* 
     }
     for (; k < nz; ++k) {
         T a[VEC], b[VEC];
-        P::unpack(ld_stream(reinterpret_cast<const V*>(pu + (int64_t)k * ncell)), a);
-        P::unpack(ld_stream(reinterpret_cast<const V*>(pv + (int64_t)k * ncell)), b);
+        P::unpack(ld_stream(reinterpret_cast<const V*>(pu + (int64_t)k * ld)), a);
+        P::unpack(ld_stream(reinterpret_cast<const V*>(pv + (int64_t)k * ld)), b);
         const double d = s_dz[k];
 #pragma unroll
         for (int e = 0; e < VEC; ++e) {
@@ -223,37 +104,39 @@ k2_edgeflux_ldg(const T* __restrict__ u, const T* __restrict__ v, const double* 
     if constexpr (VEC % 2 == 0) {  // ncell even on this path -> 16-byte aligned stores
 #pragma unroll
         for (int e = 0; e < VEC; e += 2) {
-            st_stream2(ou + e, fu[e], fu[e + 1 < VEC ? e + 1 : e]);
-            st_stream2(ov + e, fv[e], fv[e + 1 < VEC ? e + 1 : e]);
+            st_stream2(ou + e, fu[e], fu[e + 1 < VEC ? e + 1 : e], keep_l2, pol);
+            st_stream2(ov + e, fv[e], fv[e + 1 < VEC ? e + 1 : e], keep_l2, pol);
         }
     } else {
 #pragma unroll
         for (int e = 0; e < VEC; ++e) {
-            __stcs(ou + e, fu[e]);
-            __stcs(ov + e, fv[e]);
+            st_stream1(ou + e, fu[e], keep_l2, pol);
+            st_stream1(ov + e, fv[e], keep_l2, pol);
         }
     }
 }
 
 template <typename T, int VEC, int UNROLL, int BLOCK>
 void launch_ldg(const T* u, const T* v, const double* dz, const double* arc1, const double* arc2, double* eflux, int nt,
-                int nz, int64_t ncell, double scale, int use_scale, T fill, int has_fill, cudaStream_t s) {
+                int nz, int64_t ncell, int64_t ld, double scale, int use_scale, T fill, int has_fill, int keep_l2,
+                cudaStream_t s) {
     const int64_t nthreads = (ncell + VEC - 1) / VEC;
     dim3 grid((unsigned)((nthreads + BLOCK - 1) / BLOCK), (unsigned)nt);
     k2_edgeflux_ldg<T, VEC, UNROLL, BLOCK><<<grid, BLOCK, sizeof(double) * nz, s>>>(u, v, dz, arc1, arc2, eflux, nz,
-                                                                                    ncell, scale, use_scale, fill,
-                                                                                    has_fill);
+                                                                                    ncell, ld, scale, use_scale, fill,
+                                                                                    has_fill, keep_l2);
 }
 
 template <typename T, int VEC>
 void dispatch_ldg(const T* u, const T* v, const double* dz, const double* arc1, const double* arc2, double* eflux, int nt,
-                  int nz, int64_t ncell, double scale, int use_scale, T fill, int has_fill, const K2Options& opt,
-                  cudaStream_t s) {
+                  int nz, int64_t ncell, int64_t ld, double scale, int use_scale, T fill, int has_fill, int keep_l2,
+                  const K2Options& opt, cudaStream_t s) {
     const int unroll = opt.unroll > 0 ? opt.unroll : 5;
     const int block = opt.block > 0 ? opt.block : 256;
 #define NFX_K2_CASE(U, B)                                                                                          \
     if (unroll == U && block == B) {                                                                               \
-        launch_ldg<T, VEC, U, B>(u, v, dz, arc1, arc2, eflux, nt, nz, ncell, scale, use_scale, fill, has_fill, s); \
+        launch_ldg<T, VEC, U, B>(u, v, dz, arc1, arc2, eflux, nt, nz, ncell, ld, scale, use_scale, fill, has_fill,  \
+                                 keep_l2, s);                                                                      \
         return;                                                                                                    \
     }
     NFX_K2_CASE(5, 256)
@@ -493,11 +376,13 @@ __global__ void k_absmax(const double* __restrict__ x, int64_t n, unsigned long 
 
 }  // namespace
 
-void edgeflux_assemble(const void* u, const void* v, int dtype, const double* thickness, const double* arc1,
-                       const double* arc2, int nt, int nz, int64_t ncell, int sverdrup, double fill, double* eflux,
-                       const K2Options& opt, cudaStream_t s) {
+// One launch over `ncols` adjacent columns (a panel of the grid, pointers already offset to its first column)
+// and `nt` time steps; ld = cells per level plane.  eflux: (nt, 2*ncols).
+void edgeflux_assemble_panel(const void* u, const void* v, int dtype, const double* thickness, const double* arc1,
+                             const double* arc2, int nt, int nz, int64_t ncols, int64_t ld, int sverdrup, double fill,
+                             double* eflux, int keep_l2, const K2Options& opt, cudaStream_t s) {
     NFX_REQUIRE(u && v && thickness && arc1 && arc2 && eflux, "edgeflux: NULL pointer");
-    NFX_REQUIRE(nt >= 0 && nz > 0 && ncell > 0, "edgeflux: bad sizes");
+    NFX_REQUIRE(nt >= 0 && nz > 0 && ncols > 0 && ld >= ncols, "edgeflux: bad sizes");
     NFX_REQUIRE(dtype == NFX_F64 || dtype == NFX_F32, "edgeflux: dtype must be NFX_F64 or NFX_F32");
     NFX_REQUIRE(nt <= 65535, "edgeflux: at most 65535 time steps per call");
     NFX_REQUIRE(nz <= 6000, "edgeflux: at most 6000 levels");
@@ -507,23 +392,23 @@ void edgeflux_assemble(const void* u, const void* v, int dtype, const double* th
     const uintptr_t addr_bits = ((uintptr_t)u) | ((uintptr_t)v) | ((uintptr_t)eflux);
     const bool aligned16 = (addr_bits & 15) == 0;
     const bool aligned32 = (addr_bits & 31) == 0 && opt.variant != NFX_K2_LDG128;
-    const bool want_tma = (opt.variant == NFX_K2_TMA);
-    if (want_tma && aligned16 && dtype == NFX_F64 && ncell % 2 == 0) {
+    const bool want_tma = (opt.variant == NFX_K2_TMA) && ld == ncols;
+    if (want_tma && aligned16 && dtype == NFX_F64 && ncols % 2 == 0) {
         const int cfg = opt.unroll;   // tile configuration selector for the sweep (0 = default)
         const double* pu = (const double*)u;
         const double* pv = (const double*)v;
 #define NFX_TMA_CASE(ID, TC, KL, ST, CT)                                                                             \
     if (cfg == ID) {                                                                                                 \
-        launch_tma<double, TC, KL, ST, CT>(pu, pv, thickness, arc1, arc2, eflux, nt, nz, ncell, scale, sverdrup, fill, \
+        launch_tma<double, TC, KL, ST, CT>(pu, pv, thickness, arc1, arc2, eflux, nt, nz, ncols, scale, sverdrup, fill, \
                                            has_fill, s);                                                             \
         count_launch();                                                                                              \
         NFX_CUDA(cudaGetLastError());                                                                                \
         return;                                                                                                      \
     }
-        NFX_TMA_CASE(0, 512, 5, 5, 256)
+        NFX_TMA_CASE(0, 1024, 5, 2, 512)
         NFX_TMA_CASE(1, 512, 5, 4, 256)
         NFX_TMA_CASE(2, 512, 3, 8, 256)
-        NFX_TMA_CASE(3, 1024, 5, 2, 512)
+        NFX_TMA_CASE(3, 512, 5, 5, 256)
         NFX_TMA_CASE(4, 1024, 3, 4, 512)
         NFX_TMA_CASE(5, 512, 5, 5, 128)
         NFX_TMA_CASE(6, 256, 5, 10, 128)
@@ -535,30 +420,36 @@ void edgeflux_assemble(const void* u, const void* v, int dtype, const double* th
     if (dtype == NFX_F64) {
         const double* pu = (const double*)u;
         const double* pv = (const double*)v;
-        if (aligned32 && ncell % 4 == 0)
-            dispatch_ldg<double, 4>(pu, pv, thickness, arc1, arc2, eflux, nt, nz, ncell, scale, sverdrup, fill,
-                                    has_fill, opt, s);
-        else if (aligned16 && ncell % 2 == 0)
-            dispatch_ldg<double, 2>(pu, pv, thickness, arc1, arc2, eflux, nt, nz, ncell, scale, sverdrup, fill,
-                                    has_fill, opt, s);
+        if (aligned32 && ncols % 4 == 0 && ld % 4 == 0)
+            dispatch_ldg<double, 4>(pu, pv, thickness, arc1, arc2, eflux, nt, nz, ncols, ld, scale, sverdrup, fill,
+                                    has_fill, keep_l2, opt, s);
+        else if (aligned16 && ncols % 2 == 0 && ld % 2 == 0)
+            dispatch_ldg<double, 2>(pu, pv, thickness, arc1, arc2, eflux, nt, nz, ncols, ld, scale, sverdrup, fill,
+                                    has_fill, keep_l2, opt, s);
         else
-            dispatch_ldg<double, 1>(pu, pv, thickness, arc1, arc2, eflux, nt, nz, ncell, scale, sverdrup, fill,
-                                    has_fill, opt, s);
+            dispatch_ldg<double, 1>(pu, pv, thickness, arc1, arc2, eflux, nt, nz, ncols, ld, scale, sverdrup, fill,
+                                    has_fill, keep_l2, opt, s);
     } else {
         const float* pu = (const float*)u;
         const float* pv = (const float*)v;
-        if (aligned32 && ncell % 8 == 0)
-            dispatch_ldg<float, 8>(pu, pv, thickness, arc1, arc2, eflux, nt, nz, ncell, scale, sverdrup, (float)fill,
-                                   has_fill, opt, s);
-        else if (aligned16 && ncell % 4 == 0)
-            dispatch_ldg<float, 4>(pu, pv, thickness, arc1, arc2, eflux, nt, nz, ncell, scale, sverdrup, (float)fill,
-                                   has_fill, opt, s);
+        if (aligned32 && ncols % 8 == 0 && ld % 8 == 0)
+            dispatch_ldg<float, 8>(pu, pv, thickness, arc1, arc2, eflux, nt, nz, ncols, ld, scale, sverdrup,
+                                   (float)fill, has_fill, keep_l2, opt, s);
+        else if (aligned16 && ncols % 4 == 0 && ld % 4 == 0)
+            dispatch_ldg<float, 4>(pu, pv, thickness, arc1, arc2, eflux, nt, nz, ncols, ld, scale, sverdrup,
+                                   (float)fill, has_fill, keep_l2, opt, s);
         else
-            dispatch_ldg<float, 1>(pu, pv, thickness, arc1, arc2, eflux, nt, nz, ncell, scale, sverdrup, (float)fill,
-                                   has_fill, opt, s);
+            dispatch_ldg<float, 1>(pu, pv, thickness, arc1, arc2, eflux, nt, nz, ncols, ld, scale, sverdrup,
+                                   (float)fill, has_fill, keep_l2, opt, s);
     }
     count_launch();
     NFX_CUDA(cudaGetLastError());
+}
+
+void edgeflux_assemble(const void* u, const void* v, int dtype, const double* thickness, const double* arc1,
+                       const double* arc2, int nt, int nz, int64_t ncell, int sverdrup, double fill, double* eflux,
+                       const K2Options& opt, cudaStream_t s) {
+    edgeflux_assemble_panel(u, v, dtype, thickness, arc1, arc2, nt, nz, ncell, ncell, sverdrup, fill, eflux, 0, opt, s);
 }
 
 void edgeflux_to_cell_by_cell(const double* eflux, int nt, int ny, int nx, double* iv, cudaStream_t s) {

@@ -15,7 +15,8 @@ namespace {
 
 __global__ void __launch_bounds__(256)
 k3_integrate(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ idx, const double* __restrict__ w,
-             int ntransects, const double* __restrict__ data, int64_t stride_t, int nt, double* __restrict__ series) {
+             int ntransects, const double* __restrict__ data, int64_t stride_t, int nt, double* __restrict__ series,
+             int64_t out_stride_t) {
     const int lane = threadIdx.x & 31;
     const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (wid >= (int64_t)nt * ntransects) return;
@@ -31,7 +32,19 @@ k3_integrate(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ idx
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) series[t * ntransects + m] = acc;
+    if (lane == 0) series[t * out_stride_t + m] = acc;
+}
+
+// series[t, m] = sum over panels (ascending, sequential -> deterministic) of partial[t, panel, m]
+__global__ void k_reduce_panels(const double* __restrict__ partial, int nt, int npanels, int ntransects,
+                                double* __restrict__ series) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)nt * ntransects) return;
+    const int64_t t = i / ntransects;
+    const int m = (int)(i - t * ntransects);
+    double acc = 0.0;
+    for (int p = 0; p < npanels; ++p) acc += partial[(t * npanels + p) * ntransects + m];
+    series[i] = acc;
 }
 
 }  // namespace
@@ -42,7 +55,26 @@ void csr_integrate(const Csr& c, int ntransects, const double* data, int64_t str
     if (nt <= 0 || ntransects <= 0) return;
     const int64_t nw = (int64_t)nt * ntransects;
     const unsigned blocks = (unsigned)((nw * 32 + 255) / 256);
-    k3_integrate<<<blocks, 256, 0, s>>>(c.rowptr.p, c.idx.p, c.w, ntransects, data, stride_t, nt, series);
+    k3_integrate<<<blocks, 256, 0, s>>>(c.rowptr.p, c.idx.p, c.w, ntransects, data, stride_t, nt, series, ntransects);
+    count_launch();
+    NFX_CUDA(cudaGetLastError());
+}
+
+// the same kernel on an arbitrary block of CSR rows (one panel of the fast path): out[t*out_stride_t + row]
+void rows_integrate(const int64_t* rowptr, const int32_t* idx, const double* w, int nrows, const double* data,
+                    int64_t stride_t, int nt, double* out, int64_t out_stride_t, cudaStream_t s) {
+    if (nt <= 0 || nrows <= 0) return;
+    const int64_t nw = (int64_t)nt * nrows;
+    const unsigned blocks = (unsigned)((nw * 32 + 255) / 256);
+    k3_integrate<<<blocks, 256, 0, s>>>(rowptr, idx, w, nrows, data, stride_t, nt, out, out_stride_t);
+    count_launch();
+    NFX_CUDA(cudaGetLastError());
+}
+
+void reduce_panels(const double* partial, int nt, int npanels, int ntransects, double* series, cudaStream_t s) {
+    const int64_t n = (int64_t)nt * ntransects;
+    if (n <= 0) return;
+    k_reduce_panels<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(partial, nt, npanels, ntransects, series);
     count_launch();
     NFX_CUDA(cudaGetLastError());
 }

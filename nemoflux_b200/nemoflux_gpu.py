@@ -258,14 +258,17 @@ class PolylineIntegral(object):
             if t.numel() != n:
                 raise ValueError(f'{name} must hold {n} values, got {t.numel()}')
         m = self.getNumberOfTransects()
-        if eflux is None:
-            eflux = torch.empty((nt, 2 * ncell), dtype=torch.float64, device=u.device)
+        if eflux is not None:       # the caller wants the (nt, 2*ncell) edge fluxes too: classic K2 -> HBM -> K3
+            _require_cuda(eflux, torch.float64, 'eflux')
+            if eflux.numel() != nt * 2 * ncell:
+                raise ValueError(f'eflux must hold nt*2*ncell = {nt * 2 * ncell} values')
         if out is None:
             out = torch.empty((nt, m), dtype=torch.float64, device=u.device)
         with torch.cuda.device(u.device):
+            # eflux NULL -> the fast path: edge fluxes stay in an L2-resident ring between K2 and K3
             _lib.call('nfx_flux_series', ctypes.byref(self._h), _t_ptr(u), _t_ptr(v), _dtype_code(str(u.dtype)),
                       _t_ptr(thickness), _t_ptr(arc1), _t_ptr(arc2), nt, nz, int(bool(sverdrup)), float(fill),
-                      _ORDERS[order], _t_ptr(eflux), _t_ptr(out), _stream_ptr())
+                      _ORDERS[order], _t_ptr(eflux) if eflux is not None else None, _t_ptr(out), _stream_ptr())
         return out
 
     def _flux_series_host(self, u, v, thickness, arc1, arc2, sverdrup, fill, order, chunk_steps):

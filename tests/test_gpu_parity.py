@@ -345,3 +345,44 @@ def test_k2_tma_variant_bit_exact(gpu, oracle, cfg):
     finally:
         _lib.set_option(_lib.NFX_OPT_K2_VARIANT, _lib.NFX_K2_AUTO)
         _lib.set_option(_lib.NFX_OPT_K2_UNROLL, 0)
+
+
+@pytest.mark.parametrize('slot_mb,shape', [(16, (72, 36, 5, 9)), (1, (300, 250, 3, 5)), (1, (64, 40, 4, 70))])
+def test_fast_series_path_matches_classic(gpu, oracle, slot_mb, shape):
+    """nfx_flux_series with eflux == NULL (edge fluxes kept in an L2-resident ring, time batches or cell panels on
+    two streams) against the classic K2 -> HBM -> K3 path and the oracle; a 1 MB ring slot forces several panels"""
+    import torch
+    from nemoflux_b200 import _lib
+    nx, ny, nz, nt = shape
+    g = oracle.DataGen(nx=nx, ny=ny, nz=nz, nt=nt, deltaDeg=(20., 30.))
+    P, arc = g.points(), oracle.arc_lengths(g.points())
+    u, v = g.uv(SF_C2)
+    rng = numpy.random.default_rng(5)
+    land = rng.random((nz, ny, nx)) < 0.1
+    u[:, land] = numpy.nan
+    v[:, land] = numpy.nan
+    transects = random_transects(rng, 9) + [tr(README_C2), tr(README_LOOP), tr([(-180, -40), (180, -40)])]
+    th = g.thickness()
+    d = 'cuda'
+    _, p = _build(gpu, P, ny, nx)
+    p.computeWeights(transects)
+    args = [torch.from_numpy(x).to(d) for x in (u, v, th, arc[:, 1].copy(), arc[:, 2].copy())]
+    try:
+        _lib.set_option(_lib.NFX_OPT_RING_SLOT_MB, slot_mb)
+        for order in ('map', 'list'):
+            fast = p.fluxSeries(*args, order=order).cpu().numpy()
+            fast2 = p.fluxSeries(*args, order=order).cpu().numpy()
+            assert numpy.array_equal(fast, fast2)                      # deterministic run to run
+            ef = torch.empty((nt, 2 * ny * nx), dtype=torch.float64, device=d)
+            classic = p.fluxSeries(*args, order=order, eflux=ef).cpu().numpy()
+            scale = _l1_scale(oracle, P, transects, u, v, th, arc, False)
+            assert (numpy.abs(fast - classic) <= 1e-13 * scale + 1e-300).all()
+            ref = oracle.flux_series(P, transects, u, v, th, order=order, use_c=True)
+            assert (numpy.abs(fast - ref) <= FLUX_RTOL * scale + 1e-300).all()
+            # the eflux the classic path returns is the K2 output
+            _, eU, eV = oracle.edgeflux_step_c(u[nt - 1], v[nt - 1], th, arc[:, 1].copy(), arc[:, 2].copy(), False)
+            assert_bitwise(ef[nt - 1].cpu().numpy(), numpy.concatenate([eU, eV]), 'eflux')
+            host = p.fluxSeries(u, v, th, arc[:, 1].copy(), arc[:, 2].copy(), order=order, chunk_steps=4)
+            assert numpy.array_equal(host, fast)
+    finally:
+        _lib.set_option(_lib.NFX_OPT_RING_SLOT_MB, 16)

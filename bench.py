@@ -40,7 +40,7 @@ UNIT = 'cell*level*timesteps/s'
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--steps', type=int, default=50)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--workload', default='C3')
@@ -65,7 +65,7 @@ def parse_args():
 # ---------------------------------------------------------------------------------------------------
 class ClockSampler(object):
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)"""
-    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+    Q = ('timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
          'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
          'clocks_event_reasons.sw_power_cap')
 
@@ -79,41 +79,54 @@ class ClockSampler(object):
             fd, self.path = tempfile.mkstemp(suffix='.csv')
             os.close(fd)
             self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
-                                          '-lms', '100', '-i', str(self.index)],
+                                          '-lms', '50', '-i', str(self.index)],
                                          stdout=open(self.path, 'w'), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
-    def stop(self):
+    def stop(self, t_begin=None, t_end=None):
+        """median SM clock / reasons of the samples taken between t_begin and t_end (time.time()); when the timed
+        region is shorter than the sampling period, of the samples under load around it"""
+        import datetime
         out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0)
         if self.proc is None:
             return out
-        time.sleep(0.15)
+        time.sleep(0.12)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, smax, reasons = [], [], set()
+        rows = []
         try:
             for line in open(self.path):
                 f = [x.strip() for x in line.split(',')]
                 if len(f) < 9:
                     continue
                 try:
-                    sm.append(float(f[1]))
-                    smax.append(float(f[2]))
+                    ts = datetime.datetime.strptime(f[0], '%Y/%m/%d %H:%M:%S.%f').timestamp()
+                    rows.append((ts, float(f[1]), float(f[2]), float(f[3]), f[5:9]))
                 except ValueError:
                     continue
-                for name, val in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[5:9]):
-                    if val.lower().startswith('active'):
-                        reasons.add(name)
             os.unlink(self.path)
         except Exception:
             pass
-        if sm:
-            out.update(sm_mhz=float(numpy.median(sm)), sm_max_mhz=float(max(smax)), reasons=sorted(reasons),
-                       samples=len(sm))
+        if not rows:
+            return out
+        sel = [r for r in rows if t_begin is not None and t_begin - 0.05 <= r[0] <= t_end + 0.05]
+        window = 'timed region'
+        if len(sel) < 2:      # fall back to the samples under load (power above idle) of the whole run
+            pmax = max(r[3] for r in rows)
+            sel = [r for r in rows if r[3] >= 0.6 * pmax] or rows
+            window = 'samples under load (warm-up + timed region)'
+        reasons = set()
+        for r in sel:
+            for name, val in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[4]):
+                if val.lower().startswith('active'):
+                    reasons.add(name)
+        out.update(sm_mhz=float(numpy.median([r[1] for r in sel])), sm_max_mhz=float(max(r[2] for r in sel)),
+                   reasons=sorted(reasons), samples=len(sel), window=window,
+                   power_w_max=float(max(r[3] for r in sel)))
         return out
 
 
@@ -287,22 +300,23 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
     e_beg, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = _lib.launch_count()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     barrier()
+    t_wall0 = time.time()
     e_beg.record()
     for i in range(args.steps):
         out = step(evs[i])
     e_end.record()
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_wall0, time.time()) if rank == 0 else None
     launches = _lib.launch_count() - launches0
     total_ms = e_beg.elapsed_time(e_end)
     k2_ms = float(numpy.mean([e[0].elapsed_time(e[1]) for e in evs]))
@@ -463,8 +477,9 @@ def run_b200(args):
                    'transects': M, 'storage_dtype': args.dtype, 'sharding': f'time x{world} {counts}',
                    'l2_policy': f'inputs per step {2 * esize * syn.units_per_step() * nt_local / 1e9:.1f} GB >> 126 MB L2',
                    'summation_order': args.order,
-                   'pass': 'classic: K2 -> eflux in HBM -> K3' if args.classic else
-                           'fused: K2/K3 batches on two streams, eflux kept in an L2-resident ring'},
+                   'pass': 'classic: K2 -> eflux in HBM -> K3 (two launches)' if args.classic else
+                           'PolylineIntegral.fluxSeries (nfx_flux_series, eflux=NULL): fused persistent K2+K3 with the '
+                           'edge fluxes in an L2-resident ring when one time step fits a ring slot, else two launches'},
         'hbm_gbs_aggregate': 2.0 * esize * units_step_all / (ms_per_step * 1e-3) / 1e9,
         'roofline': roofline, 'clocks': clocks, 'gpu_launches': int(launches),
         'one_off': {'locator_s': t_locator, 'k1_compute_weights_s': t_k1},

@@ -82,17 +82,25 @@ struct Csr {
     const double* w = nullptr;  // borrowed: PliDev::w (list order) or PliDev::map_w (map order)
 };
 
-// CSR grouped by (panel of cells, transect) for the L2-resident fast path of nfx_flux_series: row = panel*M + m,
-// idx = panel-local index into a (2, panel_cols) slab [eU | eV]; entries that always read 0 are dropped
+// Work plan of the fused K2+K3 pass: the compact CSR of every transect regrouped by panel of cells and cut into
+// sub-rows of at most kSubRow entries (bounded work per warp).  Sub-rows are ordered by (panel, transect, chunk);
+// idx is the panel-local index into a (2, panel_cols) slab [eU | eV]; entries that always read 0 are dropped.
 struct PanelPlan {
     bool built = false;
     int64_t panel_cells = 0;
     int npanels = 0;
     int64_t nnz = 0;
-    DevBuf<int64_t> rowptr;   // (npanels*M + 1)
+    int64_t nsr = 0;              // number of sub-rows
+    int max_sr_per_panel = 0;
+    DevBuf<int64_t> rowptr;       // (npanels*M + 1) entry offsets of the (panel, transect) rows
     DevBuf<int32_t> idx;
     DevBuf<double> w;
+    DevBuf<int64_t> sr_ptr;       // (nsr + 1) entry offsets of the sub-rows
+    DevBuf<int64_t> panel_sr;     // (npanels + 1) first sub-row of every panel
+    DevBuf<int64_t> tr_ptr;       // (M + 1) per transect: range in tr_sr
+    DevBuf<int64_t> tr_sr;        // (nsr) sub-row ids of every transect, ascending
 };
+constexpr int64_t kSubRow = 4096;
 
 struct PliDev {
     GridDev* grid = nullptr;   // borrowed; never dereferenced by nfx_pli_del (the grid may already be gone)
@@ -150,9 +158,10 @@ void edgeflux_absmax(const double* eflux, int nt, int64_t ncell, double* result_
 // K3 (nfx_k3_reduce.cu)
 void csr_integrate(const Csr& c, int ntransects, const double* data, int64_t stride_t, int nt, double* series,
                    cudaStream_t s);
-void rows_integrate(const int64_t* rowptr, const int32_t* idx, const double* w, int nrows, const double* data,
-                    int64_t stride_t, int nt, double* out, int64_t out_stride_t, cudaStream_t s);
-void reduce_panels(const double* partial, int nt, int npanels, int ntransects, double* series, cudaStream_t s);
+void rows_integrate(const int64_t* rowptr, const int32_t* idx, const double* w, int nrows, int64_t nnz,
+                    const double* data, int64_t stride_t, int nt, double* out, int64_t out_stride_t, cudaStream_t s);
+void reduce_subrows(const double* partial, int nt, int64_t nsr, const int64_t* tr_ptr, const int64_t* tr_sr,
+                    int ntransects, double* series, cudaStream_t s);
 void build_panel_plan(PliDev& p, int order, int64_t panel_cells, cudaStream_t s);
 
 // K2+K3 fused persistent pass (nfx_k23_fused.cu)
@@ -160,5 +169,6 @@ void flux_series_fused(PliDev& p, const PanelPlan& pl, const void* u, const void
                        const double* arc1, const double* arc2, int nt, int nz, int sverdrup, double fill, double* out,
                        cudaStream_t s);
 int fused_error_flag(PliDev& p, cudaStream_t s);
+int k3_group_for(int64_t nnz, int64_t nrows);
 
 }  // namespace nfx

@@ -625,28 +625,72 @@ void build_panel_plan(PliDev& p, int order, int64_t panel_cells, cudaStream_t s)
     pl.rowptr.ensure((size_t)nrows + 1);
     if (M == 0 || c.nnz == 0) {
         NFX_CUDA(cudaMemsetAsync(pl.rowptr.p, 0, sizeof(int64_t) * (nrows + 1), s));
+        pl.sr_ptr.ensure(1);
+        pl.panel_sr.ensure((size_t)npanels + 1);
+        pl.tr_ptr.ensure((size_t)M + 1);
+        pl.tr_sr.ensure(1);
+        NFX_CUDA(cudaMemsetAsync(pl.sr_ptr.p, 0, sizeof(int64_t), s));
+        NFX_CUDA(cudaMemsetAsync(pl.panel_sr.p, 0, sizeof(int64_t) * (npanels + 1), s));
+        NFX_CUDA(cudaMemsetAsync(pl.tr_ptr.p, 0, sizeof(int64_t) * (M + 1), s));
         pl.nnz = 0;
+        pl.nsr = 0;
+        pl.max_sr_per_panel = 0;
         pl.built = true;
         return;
     }
-    DevBuf<int64_t> counts, tmp;
+    DevBuf<int64_t> counts;
     counts.alloc((size_t)nrows);
     k_panel_rows<false><<<nblk(M, 64), 64, 0, s>>>(c.rowptr.p, c.idx.p, c.w, M, ncell, panel_cells, npanels, counts.p,
                                                   nullptr, nullptr, nullptr);
     count_launch();
     NFX_CUDA(cudaGetLastError());
-    exclusive_scan(counts.p, pl.rowptr.p, nrows, tmp, s);
-    int64_t nnz = 0;
-    NFX_CUDA(cudaMemcpyAsync(&nnz, pl.rowptr.p + nrows, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    // the index arrays are small (npanels*M rows): build them on the host
+    std::vector<int64_t> h_cnt((size_t)nrows), h_rowptr((size_t)nrows + 1, 0);
+    NFX_CUDA(cudaMemcpyAsync(h_cnt.data(), counts.p, sizeof(int64_t) * nrows, cudaMemcpyDeviceToHost, s));
     NFX_CUDA(cudaStreamSynchronize(s));
+    for (int64_t r = 0; r < nrows; ++r) h_rowptr[r + 1] = h_rowptr[r] + h_cnt[r];
+    const int64_t nnz = h_rowptr[nrows];
+    std::vector<int64_t> sr_ptr, panel_sr((size_t)npanels + 1, 0), tr_ptr((size_t)M + 1, 0), tr_sr;
+    std::vector<std::vector<int64_t>> per_tr((size_t)M);
+    int max_sr = 0;
+    for (int q = 0; q < npanels; ++q) {
+        panel_sr[q] = (int64_t)sr_ptr.size();
+        for (int m = 0; m < M; ++m) {
+            const int64_t a = h_rowptr[(int64_t)q * M + m], b = h_rowptr[(int64_t)q * M + m + 1];
+            for (int64_t e = a; e < b; e += kSubRow) {
+                per_tr[m].push_back((int64_t)sr_ptr.size());
+                sr_ptr.push_back(e);
+            }
+        }
+        max_sr = std::max<int>(max_sr, (int)((int64_t)sr_ptr.size() - panel_sr[q]));
+    }
+    panel_sr[npanels] = (int64_t)sr_ptr.size();
+    const int64_t nsr = (int64_t)sr_ptr.size();
+    sr_ptr.push_back(nnz);
+    for (int m = 0; m < M; ++m) {
+        tr_ptr[m + 1] = tr_ptr[m] + (int64_t)per_tr[m].size();
+        tr_sr.insert(tr_sr.end(), per_tr[m].begin(), per_tr[m].end());
+    }
     pl.nnz = nnz;
+    pl.nsr = nsr;
+    pl.max_sr_per_panel = max_sr;
     pl.idx.ensure((size_t)std::max<int64_t>(nnz, 1));
     pl.w.ensure((size_t)std::max<int64_t>(nnz, 1));
+    pl.sr_ptr.ensure((size_t)nsr + 1);
+    pl.panel_sr.ensure((size_t)npanels + 1);
+    pl.tr_ptr.ensure((size_t)M + 1);
+    pl.tr_sr.ensure((size_t)std::max<int64_t>(nsr, 1));
+    NFX_CUDA(cudaMemcpyAsync(pl.rowptr.p, h_rowptr.data(), sizeof(int64_t) * (nrows + 1), cudaMemcpyHostToDevice, s));
+    NFX_CUDA(cudaMemcpyAsync(pl.sr_ptr.p, sr_ptr.data(), sizeof(int64_t) * (nsr + 1), cudaMemcpyHostToDevice, s));
+    NFX_CUDA(cudaMemcpyAsync(pl.panel_sr.p, panel_sr.data(), sizeof(int64_t) * (npanels + 1), cudaMemcpyHostToDevice, s));
+    NFX_CUDA(cudaMemcpyAsync(pl.tr_ptr.p, tr_ptr.data(), sizeof(int64_t) * (M + 1), cudaMemcpyHostToDevice, s));
+    if (nsr > 0)
+        NFX_CUDA(cudaMemcpyAsync(pl.tr_sr.p, tr_sr.data(), sizeof(int64_t) * nsr, cudaMemcpyHostToDevice, s));
     k_panel_rows<true><<<nblk(M, 64), 64, 0, s>>>(c.rowptr.p, c.idx.p, c.w, M, ncell, panel_cells, npanels, nullptr,
                                                  pl.rowptr.p, pl.idx.p, pl.w.p);
     count_launch();
     NFX_CUDA(cudaGetLastError());
-    NFX_CUDA(cudaStreamSynchronize(s));
+    NFX_CUDA(cudaStreamSynchronize(s));   // the host vectors go out of scope
     pl.built = true;
 }
 

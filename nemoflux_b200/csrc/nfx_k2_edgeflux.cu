@@ -46,6 +46,7 @@ k2_edgeflux_ldg(const T* __restrict__ u, const T* __restrict__ v, const double* 
     const T* pu = u + t * nz * ld + c0;
     const T* pv = v + t * nz * ld + c0;
     const uint64_t pol = keep_l2 ? l2_evict_last_policy() : 0;
+    const uint64_t pol_ef = l2_evict_first_policy();
     double su[VEC], sv[VEC];
 #pragma unroll
     for (int e = 0; e < VEC; ++e) {
@@ -57,8 +58,8 @@ k2_edgeflux_ldg(const T* __restrict__ u, const T* __restrict__ v, const double* 
         V ru[UNROLL], rv[UNROLL];
 #pragma unroll
         for (int q = 0; q < UNROLL; ++q) {
-            ru[q] = ld_stream(reinterpret_cast<const V*>(pu + (int64_t)(k + q) * ld));
-            rv[q] = ld_stream(reinterpret_cast<const V*>(pv + (int64_t)(k + q) * ld));
+            ru[q] = ld_stream(reinterpret_cast<const V*>(pu + (int64_t)(k + q) * ld), pol_ef);
+            rv[q] = ld_stream(reinterpret_cast<const V*>(pv + (int64_t)(k + q) * ld), pol_ef);
         }
 #pragma unroll
         for (int q = 0; q < UNROLL; ++q) {
@@ -80,8 +81,8 @@ k2_edgeflux_ldg(const T* __restrict__ u, const T* __restrict__ v, const double* 
     }
     for (; k < nz; ++k) {
         T a[VEC], b[VEC];
-        P::unpack(ld_stream(reinterpret_cast<const V*>(pu + (int64_t)k * ld)), a);
-        P::unpack(ld_stream(reinterpret_cast<const V*>(pv + (int64_t)k * ld)), b);
+        P::unpack(ld_stream(reinterpret_cast<const V*>(pu + (int64_t)k * ld), pol_ef), a);
+        P::unpack(ld_stream(reinterpret_cast<const V*>(pv + (int64_t)k * ld), pol_ef), b);
         const double d = s_dz[k];
 #pragma unroll
         for (int e = 0; e < VEC; ++e) {

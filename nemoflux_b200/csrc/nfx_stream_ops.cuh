@@ -55,6 +55,41 @@ __device__ __forceinline__ float ld_stream(const float* p) {
     return r;
 }
 
+// the same loads with an explicit L2 evict-first policy (createpolicy): narrower than 256 bits the instruction
+// takes the hint only through .L2::cache_hint.  The u/v stream is read once: it must not displace the edge-flux
+// ring (evict-last) or the CSR lists in L2.
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ double2 ld_stream(const double2* p, uint64_t pol) {
+    double2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;"
+                 : "=d"(r.x), "=d"(r.y)
+                 : "l"(p), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ double ld_stream(const double* p, uint64_t pol) {
+    double r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(r) : "l"(p), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ float4 ld_stream(const float4* p, uint64_t pol) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(p), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ float ld_stream(const float* p, uint64_t pol) {
+    float r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(r) : "l"(p), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ double4x ld_stream(const double4x* p, uint64_t) { return ld_stream(p); }
+__device__ __forceinline__ float8x ld_stream(const float8x* p, uint64_t) { return ld_stream(p); }
+
 // Register fence: every load of a batch is issued (volatile asm keeps program order) before the
 // first value is consumed, so UNROLL*2 wide loads are in flight per thread instead of one.
 __device__ __forceinline__ void pin(double& x) { asm volatile("" : "+d"(x)); }

@@ -369,6 +369,7 @@ def test_fast_series_path_matches_classic(gpu, oracle, slot_mb, shape):
     args = [torch.from_numpy(x).to(d) for x in (u, v, th, arc[:, 1].copy(), arc[:, 2].copy())]
     try:
         _lib.set_option(_lib.NFX_OPT_RING_SLOT_MB, slot_mb)
+        _lib.set_option(_lib.NFX_OPT_FAST_SERIES, 2)           # always the fused pass, also with several panels
         for order in ('map', 'list'):
             fast = p.fluxSeries(*args, order=order).cpu().numpy()
             fast2 = p.fluxSeries(*args, order=order).cpu().numpy()
@@ -385,4 +386,5 @@ def test_fast_series_path_matches_classic(gpu, oracle, slot_mb, shape):
             host = p.fluxSeries(u, v, th, arc[:, 1].copy(), arc[:, 2].copy(), order=order, chunk_steps=4)
             assert numpy.array_equal(host, fast)
     finally:
-        _lib.set_option(_lib.NFX_OPT_RING_SLOT_MB, 16)
+        _lib.set_option(_lib.NFX_OPT_RING_SLOT_MB, 8)
+        _lib.set_option(_lib.NFX_OPT_FAST_SERIES, 1)

@@ -341,8 +341,10 @@ def run_b200(args):
     peak = float(peaks.get('hbm_gbs', 6650.0))
     k2_bytes = 2.0 * esize * syn.units_per_step() * nt_local            # per launch (one rank)
     achieved = k2_bytes / (k2_ms * 1e-3) / 1e9
-    roofline = {'bound': 'hbm', 'kernel': 'k2_edgeflux' if args.classic else
-                'k2_edgeflux (timed as the fused K2+K3 pass of nfx_flux_series: K3 launches are inside the interval)',
+    fused_used = (not args.classic) and args.dtype == 'f64' and syn.ncell * 16 <= (args.ring_slot_mb or 8) * (1 << 20)
+    roofline = {'bound': 'hbm', 'kernel': 'k2_edgeflux_ldg' if args.classic else
+                ('k23_fused (persistent K2+K3, one launch per step; algorithmic bytes = the u/v stream)' if fused_used
+                 else 'k2_edgeflux_ldg + k3_integrate (timed together, two launches)'),
                 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                 'frac': achieved / peak, 'traffic': None,
                 'peak_source': 'MEASURED_PEAKS.json hbm_gbs (of measured)' if peaks else 'fallback 6650 GB/s',
@@ -352,7 +354,7 @@ def run_b200(args):
     if os.path.exists(tr_path):
         try:
             tr = json.load(open(tr_path))
-            key = f'{args.workload}_{args.dtype}'
+            key = f'{args.workload}_{args.dtype}' + ('_fused' if fused_used else '')
             if key in tr:    # ncu dram bytes per launch were measured on a reduced nt: scale per time step
                 roofline['traffic'] = tr[key]['dram_bytes_per_timestep'] * nt_local
                 roofline['traffic_source'] = tr[key].get('source', 'profiles/')

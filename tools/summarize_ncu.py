@@ -33,6 +33,7 @@ def main():
     ap.add_argument('--dtype', default='f64')
     ap.add_argument('--nt', type=int, default=16)
     ap.add_argument('--cmd', default='')
+    ap.add_argument('--fused', action='store_true')
     a = ap.parse_args()
     os.makedirs('profiles', exist_ok=True)
     md = [f'# ncu summary {a.tag}', '', f'command: `{a.cmd}` (one B200, --clock-control none)', '']
@@ -47,7 +48,8 @@ def main():
             x = agg.setdefault(name, [0, 0.0])
             x[0] += 1
             x[1] += float(r[vi].replace(',', ''))
-        step = {k: v for k, v in agg.items() if 'k2_edgeflux' in k or 'k3_integrate' in k}
+        step = {k: v for k, v in agg.items() if 'k2_edgeflux' in k or 'k3_integrate' in k or 'k23_fused' in k
+                or 'k_reduce_subrows' in k}
         tot_step = sum(v[1] for v in step.values())
         md += ['## launch list (gpu__time_duration.sum, ns; cold-cache, serialised: compare shares)', '',
                '| kernel | launches | total ns | ns/launch | share of the step kernels |', '|---|---|---|---|---|']
@@ -87,8 +89,9 @@ def main():
                    f'{sum(traffic) / len(traffic):.4e} B for {a.nt} time steps = {per_step:.4e} B per time step.', '']
             tpath = 'profiles/k2_traffic.json'
             tr = json.load(open(tpath)) if os.path.exists(tpath) else {}
-            tr[f'{a.workload}_{a.dtype}'] = {'dram_bytes_per_timestep': per_step,
-                                            'source': f'profiles/{a.tag}_k2_raw.csv (ncu --set full, nt={a.nt})'}
+            key = f'{a.workload}_{a.dtype}' + ('_fused' if a.fused else '')
+            tr[key] = {'dram_bytes_per_timestep': per_step,
+                       'source': f'profiles/{a.tag}_k2_raw.csv (ncu --set full, nt={a.nt})'}
             json.dump(tr, open(tpath, 'w'), indent=1)
     open(f'profiles/{a.tag}_ncu_summary.md', 'w').write('\n'.join(md) + '\n')
     print('\n'.join(md))

@@ -59,6 +59,8 @@ def parse_args():
     ap.add_argument('--classic', action='store_true',
                     help='K2 -> eflux in HBM -> K3 as two launches (default: the fused pass that keeps eflux in L2)')
     ap.add_argument('--ring-slot-mb', type=int, default=0)
+    ap.add_argument('--no-pad', action='store_true',
+                    help='store u/v densely; default: level planes padded to 32 bytes when ncell*itemsize is not')
     return ap.parse_args()
 
 
@@ -270,7 +272,9 @@ def run_b200(args):
     thickness = torch.from_numpy(syn.thickness).to(dev)
     arc1 = torch.from_numpy(syn.arc1).to(dev)
     arc2 = torch.from_numpy(syn.arc2).to(dev)
-    u, v = syn.fill_device(t0_rank, nt_local, dev, tdtype)
+    pad = 0 if args.no_pad else (4 if args.dtype == 'f64' else 8)
+    u, v = syn.fill_device(t0_rank, nt_local, dev, tdtype, pad=pad)
+    padded = u.dim() == 3
     eflux = torch.empty((nt_local, 2 * syn.ncell), dtype=torch.float64, device=dev) if args.classic else None
     series_pad = torch.zeros((cmax, M), dtype=torch.float64, device=dev)       # padded to the largest shard
     series = series_pad[:nt_local]
@@ -341,7 +345,8 @@ def run_b200(args):
     peak = float(peaks.get('hbm_gbs', 6650.0))
     k2_bytes = 2.0 * esize * syn.units_per_step() * nt_local            # per launch (one rank)
     achieved = k2_bytes / (k2_ms * 1e-3) / 1e9
-    fused_used = (not args.classic) and args.dtype == 'f64' and syn.ncell * 16 <= (args.ring_slot_mb or 8) * (1 << 20)
+    fused_used = (not args.classic) and args.dtype == 'f64' and (
+        syn.ncell * 16 <= (args.ring_slot_mb or 8) * (1 << 20) or padded or syn.ncell % 4 == 0)
     roofline = {'bound': 'hbm', 'kernel': 'k2_edgeflux_ldg' if args.classic else
                 ('k23_fused (persistent K2+K3, one launch per step; algorithmic bytes = the u/v stream)' if fused_used
                  else 'k2_edgeflux_ldg + k3_integrate (timed together, two launches)'),
@@ -368,8 +373,8 @@ def run_b200(args):
     if not args.no_e2e and not big_steps:
         hu = torch.empty((ne, syn.nz, syn.ny, syn.nx), dtype=tdtype).pin_memory()
         hv = torch.empty_like(hu).pin_memory()
-        hu.copy_(u[:ne])
-        hv.copy_(v[:ne])
+        hu.view(ne, syn.nz, syn.ncell).copy_(u[:ne].reshape(ne, syn.nz, syn.ncell))
+        hv.view(ne, syn.nz, syn.ncell).copy_(v[:ne].reshape(ne, syn.nz, syn.ncell))
         torch.cuda.synchronize()
         th_h, a1_h, a2_h = syn.thickness, syn.arc1, syn.arc2
         for _ in range(2):
@@ -477,6 +482,8 @@ def run_b200(args):
                                f'{M} transects, u/v stored {args.dtype} resident in HBM',
                    'nx': syn.nx, 'ny': syn.ny, 'nz': syn.nz, 'nt_per_gpu': nt_local, 'nt_total': nt_total,
                    'transects': M, 'storage_dtype': args.dtype, 'sharding': f'time x{world} {counts}',
+                   'device_layout': f'(nt, nz, ld={u.stride(1)}) level planes padded to 32 B' if padded
+                                    else '(nt, nz, ny, nx) dense',
                    'l2_policy': f'inputs per step {2 * esize * syn.units_per_step() * nt_local / 1e9:.1f} GB >> 126 MB L2',
                    'summation_order': args.order,
                    'pass': 'classic: K2 -> eflux in HBM -> K3 (two launches)' if args.classic else

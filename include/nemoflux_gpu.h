@@ -114,6 +114,12 @@ int nfx_pli_get_integrals_device(nfx_pli** self, const double* data, int nt, int
 int nfx_edgeflux_assemble(const void* u, const void* v, int dtype, const double* thickness, const double* arc1,
                           const double* arc2, int nt, int nz, int64_t ncell, int sverdrup, double fill,
                           double* eflux, void* stream);
+/* the same with a padded level plane: u, v are (nt, nz, ld) with ld >= ncell cells per plane in memory (the
+ * device layout is the caller's: ld % 4 == 0 gives 32-byte aligned rows and 256-bit loads for every grid size,
+ * ORCA025/ORCA12 planes are only 16-byte aligned when stored densely) */
+int nfx_edgeflux_assemble_ld(const void* u, const void* v, int dtype, const double* thickness, const double* arc1,
+                             const double* arc2, int nt, int nz, int64_t ncell, int64_t ld, int sverdrup, double fill,
+                             double* eflux, void* stream);
 /* the (ncell,4) mint layout of field.py:209-223 from the compact one: south edges of row 0 are 0,
  * west edges x-periodic.  eflux device (nt, 2*ncell) -> iv device (nt, ncell, 4) */
 int nfx_edgeflux_to_cell_by_cell(const double* eflux, int nt, int ny, int nx, double* iv, void* stream);
@@ -130,6 +136,9 @@ int nfx_pli_integrate(nfx_pli** self, const double* eflux, int nt, int order, do
 int nfx_flux_series(nfx_pli** self, const void* u, const void* v, int dtype, const double* thickness,
                     const double* arc1, const double* arc2, int nt, int nz, int sverdrup, double fill, int order,
                     double* eflux, double* series, void* stream);
+int nfx_flux_series_ld(nfx_pli** self, const void* u, const void* v, int dtype, const double* thickness,
+                       const double* arc1, const double* arc2, int nt, int nz, int64_t ld, int sverdrup, double fill,
+                       int order, double* eflux, double* series, void* stream);
 /* everything from HOST buffers (the call a non-CUDA host makes): u, v host (nt,nz,ny,nx), thickness
  * host (nz), arc1/arc2 host (ncell); series host (nt, ntransects).  Streams time chunks through
  * double-buffered device staging (host buffers may be pinned or pageable). chunk_steps <= 0 = auto */

@@ -48,11 +48,15 @@ SIGNATURES = {
     'nfx_pli_get_integrals': [P(c_vp), c_vp, c_int, c_int, c_vp],
     'nfx_pli_get_integrals_device': [P(c_vp), c_vp, c_int, c_int, c_vp, c_vp],
     'nfx_edgeflux_assemble': [c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_int, c_i64, c_int, c_dbl, c_vp, c_vp],
+    'nfx_edgeflux_assemble_ld': [c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_int, c_i64, c_i64, c_int, c_dbl, c_vp,
+                                 c_vp],
     'nfx_edgeflux_to_cell_by_cell': [c_vp, c_int, c_int, c_int, c_vp, c_vp],
     'nfx_edgeflux_absmax': [c_vp, c_int, c_i64, P(c_dbl), c_vp],
     'nfx_pli_integrate': [P(c_vp), c_vp, c_int, c_int, c_vp, c_vp],
     'nfx_flux_series': [P(c_vp), c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_dbl, c_int, c_vp, c_vp,
                         c_vp],
+    'nfx_flux_series_ld': [P(c_vp), c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_int, c_i64, c_int, c_dbl, c_int, c_vp,
+                           c_vp, c_vp],
     'nfx_flux_series_host': [P(c_vp), c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_dbl, c_int, c_int,
                              c_vp],
 }

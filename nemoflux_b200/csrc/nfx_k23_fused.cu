@@ -19,6 +19,7 @@
 // Arithmetic is the same as in the two-launch path (nfx_k2_edgeflux.cu, nfx_k3_reduce.cu): same per-column
 // sums, same per-row lane order and shuffle tree -> bit-identical series.
 #include <algorithm>
+#include <cstdlib>
 
 #include "nfx_common.cuh"
 #include "nfx_stream_ops.cuh"
@@ -47,8 +48,9 @@ struct FusedArgs {
     const int32_t* idx;
     const double* w;
     int* sync;              // [0] work counter, [1] error flag, [2 .. 2+nb) K2 tiles done, [2+nb .. 2+2nb) K3 items done
-    int64_t ncell, panel, slot_elems;
+    int64_t ncell, ld, panel, slot_elems;   // ld = cells per level plane in memory (>= ncell)
     int nt, nz, ntransects, npanels, nbatches, ntiles, nk3, ring_slots;
+    int debug_skip_k3;      // NFX_DEBUG_FUSED_SKIP_K3 (experiments only)
     double scale, fill;
     int use_scale, has_fill;
 };
@@ -126,8 +128,8 @@ k23_fused(const FusedArgs a) {
             const int64_t cl = ((int64_t)r * kFusedBlock + threadIdx.x) * VEC;   // column inside the panel
             if (cl < pc) {
                 const int64_t c = pc0 + cl;
-                const T* pu = u + t * a.nz * a.ncell + c;
-                const T* pv = v + t * a.nz * a.ncell + c;
+                const T* pu = u + t * a.nz * a.ld + c;
+                const T* pv = v + t * a.nz * a.ld + c;
                 double su[VEC], sv[VEC];
 #pragma unroll
                 for (int e = 0; e < VEC; ++e) {
@@ -139,8 +141,8 @@ k23_fused(const FusedArgs a) {
                     V ru[UNROLL], rv[UNROLL];
 #pragma unroll
                     for (int qq = 0; qq < UNROLL; ++qq) {
-                        ru[qq] = ld_stream(reinterpret_cast<const V*>(pu + (int64_t)(k + qq) * a.ncell), pol_ef);
-                        rv[qq] = ld_stream(reinterpret_cast<const V*>(pv + (int64_t)(k + qq) * a.ncell), pol_ef);
+                        ru[qq] = ld_stream(reinterpret_cast<const V*>(pu + (int64_t)(k + qq) * a.ld), pol_ef);
+                        rv[qq] = ld_stream(reinterpret_cast<const V*>(pv + (int64_t)(k + qq) * a.ld), pol_ef);
                     }
 #pragma unroll
                     for (int qq = 0; qq < UNROLL; ++qq) {
@@ -162,8 +164,8 @@ k23_fused(const FusedArgs a) {
                 }
                 for (; k < a.nz; ++k) {
                     T x[VEC], y[VEC];
-                    P::unpack(ld_stream(reinterpret_cast<const V*>(pu + (int64_t)k * a.ncell), pol_ef), x);
-                    P::unpack(ld_stream(reinterpret_cast<const V*>(pv + (int64_t)k * a.ncell), pol_ef), y);
+                    P::unpack(ld_stream(reinterpret_cast<const V*>(pu + (int64_t)k * a.ld), pol_ef), x);
+                    P::unpack(ld_stream(reinterpret_cast<const V*>(pv + (int64_t)k * a.ld), pol_ef), y);
                     const double d = s_dz[k];
 #pragma unroll
                     for (int e = 0; e < VEC; ++e) {
@@ -173,26 +175,27 @@ k23_fused(const FusedArgs a) {
                 }
                 double* ou = a.ring + (int64_t)(b % a.ring_slots) * a.slot_elems + cl;
                 double* ov = ou + pc;
+                const int nvalid = (int)min((int64_t)VEC, pc - cl);   // the last vector may hang over the panel end
 #pragma unroll
                 for (int e = 0; e < VEC; ++e) {
-                    double fu = __dmul_rn(su[e], a.arc1[c + e]);
-                    double fv = __dmul_rn(-sv[e], a.arc2[c + e]);
-                    if (a.use_scale) {
-                        fu = __dmul_rn(fu, a.scale);
-                        fv = __dmul_rn(fv, a.scale);
+                    if (e < nvalid) {
+                        double fu = __dmul_rn(su[e], a.arc1[c + e]);
+                        double fv = __dmul_rn(-sv[e], a.arc2[c + e]);
+                        if (a.use_scale) {
+                            fu = __dmul_rn(fu, a.scale);
+                            fv = __dmul_rn(fv, a.scale);
+                        }
+                        su[e] = fu;
+                        sv[e] = fv;
                     }
-                    su[e] = fu;
-                    sv[e] = fv;
                 }
-                if constexpr (VEC % 2 == 0) {
+                const bool pair_ok = (VEC % 2 == 0) && ((pc & 1) == 0) && ((a.slot_elems & 1) == 0);
 #pragma unroll
-                    for (int e = 0; e < VEC; e += 2) {
+                for (int e = 0; e < VEC; ++e) {
+                    if (pair_ok && (e % 2 == 0) && e + 1 < nvalid) {
                         st_stream2(ou + e, su[e], su[e + 1 < VEC ? e + 1 : e], 1, pol);
                         st_stream2(ov + e, sv[e], sv[e + 1 < VEC ? e + 1 : e], 1, pol);
-                    }
-                } else {
-#pragma unroll
-                    for (int e = 0; e < VEC; ++e) {
+                    } else if (e < nvalid && !(pair_ok && (e % 2 == 1))) {
                         st_stream1(ou + e, su[e], 1, pol);
                         st_stream1(ov + e, sv[e], 1, pol);
                     }
@@ -214,7 +217,7 @@ k23_fused(const FusedArgs a) {
             {
                 // one warp per sub-row (<= kSubRow entries): lane-strided partial sums, fixed shuffle tree
                 const int64_t sr = a.panel_sr[q] + (int64_t)(r - a.ntiles) * kWarps + wid;
-                if (sr < a.panel_sr[q + 1]) {
+                if (sr < a.panel_sr[q + 1] && !a.debug_skip_k3) {
                     const int64_t r0 = a.sr_ptr[sr], r1 = a.sr_ptr[sr + 1];
                     const double* d = a.ring + (int64_t)(b % a.ring_slots) * a.slot_elems;
                     double acc = 0.0;
@@ -266,26 +269,31 @@ int k3_group_for(int64_t nnz, int64_t nrows) {
     return avg >= 4096 ? 8 : avg >= 1024 ? 4 : avg >= 256 ? 2 : 1;
 }
 
-int fused_tile_columns(int dtype, const void* u, const void* v, int64_t ncell, int64_t panel) {
+int fused_tile_columns(int dtype, const void* u, const void* v, int64_t ncell, int64_t ld, int64_t panel) {
     // widest vector the alignment of every level row and panel start allows
     const uintptr_t bits = ((uintptr_t)u) | ((uintptr_t)v);
     const bool a16 = (bits & 15) == 0, a32 = (bits & 31) == 0;
+    // rows start at multiples of ld, panels at multiples of `panel`; the last panel ends at ncell
+    // (a vector may hang over the end of the last panel when the plane is padded: ld >= ncell rounded up)
+    auto fits = [&](int64_t vec) {
+        return ld % vec == 0 && (panel % vec == 0 || panel == ncell) && (ncell % vec == 0 || ld >= (ncell + vec - 1) / vec * vec);
+    };
     if (dtype == NFX_F64) {
-        if (a32 && ncell % 4 == 0 && panel % 4 == 0) return 4;
-        if (a16 && ncell % 2 == 0 && panel % 2 == 0) return 2;
+        if (a32 && fits(4)) return 4;
+        if (a16 && fits(2)) return 2;
         return 1;
     }
-    if (a32 && ncell % 8 == 0 && panel % 8 == 0) return 8;
-    if (a16 && ncell % 4 == 0 && panel % 4 == 0) return 4;
+    if (a32 && fits(8)) return 8;
+    if (a16 && fits(4)) return 4;
     return 1;
 }
 
 void flux_series_fused(PliDev& p, const PanelPlan& pl, const void* u, const void* v, int dtype, const double* thickness,
-                       const double* arc1, const double* arc2, int nt, int nz, int sverdrup, double fill, double* out,
-                       cudaStream_t s) {
+                       const double* arc1, const double* arc2, int nt, int nz, int64_t ld, int sverdrup, double fill,
+                       double* out, cudaStream_t s) {
     const int64_t ncell = p.grid->ncell;
     const int M = p.ntransects;
-    const int vec = fused_tile_columns(dtype, u, v, ncell, pl.panel_cells);
+    const int vec = fused_tile_columns(dtype, u, v, ncell, ld, pl.panel_cells);
     FusedArgs a;
     a.u = u;
     a.v = v;
@@ -293,6 +301,7 @@ void flux_series_fused(PliDev& p, const PanelPlan& pl, const void* u, const void
     a.arc1 = arc1;
     a.arc2 = arc2;
     a.ncell = ncell;
+    a.ld = ld;
     a.panel = pl.panel_cells;
     a.slot_elems = 2 * std::min(pl.panel_cells, ncell);
     a.nt = nt;
@@ -321,6 +330,10 @@ void flux_series_fused(PliDev& p, const PanelPlan& pl, const void* u, const void
     int slots = (2 * resident + a.ntiles - 1) / a.ntiles + 1;
     const int64_t cap = std::max<int64_t>(3, ((int64_t)64 << 20) / (a.slot_elems * 8));
     slots = (int)std::min<int64_t>(std::max(slots, 3), cap);
+    static const int dbg_slots = getenv("NFX_DEBUG_RING_SLOTS") ? atoi(getenv("NFX_DEBUG_RING_SLOTS")) : 0;
+    static const int dbg_skip = getenv("NFX_DEBUG_FUSED_SKIP_K3") ? atoi(getenv("NFX_DEBUG_FUSED_SKIP_K3")) : 0;
+    if (dbg_slots > 0) slots = dbg_slots;
+    a.debug_skip_k3 = dbg_skip;
     a.ring_slots = slots;
     p.ring.ensure((size_t)(a.slot_elems * slots));
     NFX_CUDA(cudaMemsetAsync(out, 0xFF, sizeof(double) * (size_t)nt * std::max<int64_t>(pl.nsr, 1), s));   // NaN: a pass that

@@ -42,7 +42,7 @@ k2_edgeflux_ldg(const T* __restrict__ u, const T* __restrict__ v, const double* 
     using V = typename P::type;
     const int64_t t = blockIdx.y;
     const int64_t c0 = ((int64_t)blockIdx.x * BLOCK + threadIdx.x) * VEC;
-    if (c0 >= ncell) return;  // VEC divides ncell on the vector path, so c0+VEC <= ncell
+    if (c0 >= ncell) return;
     const T* pu = u + t * nz * ld + c0;
     const T* pv = v + t * nz * ld + c0;
     const uint64_t pol = keep_l2 ? l2_evict_last_policy() : 0;
@@ -92,25 +92,31 @@ k2_edgeflux_ldg(const T* __restrict__ u, const T* __restrict__ v, const double* 
     }
     double* ou = eflux + t * 2 * ncell + c0;
     double* ov = ou + ncell;
+    // the last vector of a row may hang over the end of the grid (padded planes, ld > ncell): loads are safe,
+    // metric factors and stores are only touched for the nvalid real columns
+    const int nvalid = (int)min((int64_t)VEC, ncell - c0);
     double fu[VEC], fv[VEC];
 #pragma unroll
     for (int e = 0; e < VEC; ++e) {
-        fu[e] = __dmul_rn(su[e], arc1[c0 + e]);
-        fv[e] = __dmul_rn(-sv[e], arc2[c0 + e]);
-        if (use_scale) {
-            fu[e] = __dmul_rn(fu[e], scale);
-            fv[e] = __dmul_rn(fv[e], scale);
+        fu[e] = 0.0;
+        fv[e] = 0.0;
+        if (e < nvalid) {
+            fu[e] = __dmul_rn(su[e], arc1[c0 + e]);
+            fv[e] = __dmul_rn(-sv[e], arc2[c0 + e]);
+            if (use_scale) {
+                fu[e] = __dmul_rn(fu[e], scale);
+                fv[e] = __dmul_rn(fv[e], scale);
+            }
         }
     }
-    if constexpr (VEC % 2 == 0) {  // ncell even on this path -> 16-byte aligned stores
+    // 16-byte stores need even (t*2*ncell + c0) and (ncell): true whenever ncell is even and VEC is even
+    const bool pair_ok = (VEC % 2 == 0) && ((ncell & 1) == 0);
 #pragma unroll
-        for (int e = 0; e < VEC; e += 2) {
+    for (int e = 0; e < VEC; ++e) {
+        if (pair_ok && (e % 2 == 0) && e + 1 < nvalid) {
             st_stream2(ou + e, fu[e], fu[e + 1 < VEC ? e + 1 : e], keep_l2, pol);
             st_stream2(ov + e, fv[e], fv[e + 1 < VEC ? e + 1 : e], keep_l2, pol);
-        }
-    } else {
-#pragma unroll
-        for (int e = 0; e < VEC; ++e) {
+        } else if (e < nvalid && !(pair_ok && (e % 2 == 1))) {   // odd e: already written with e-1
             st_stream1(ou + e, fu[e], keep_l2, pol);
             st_stream1(ov + e, fv[e], keep_l2, pol);
         }
@@ -421,10 +427,10 @@ void edgeflux_assemble_panel(const void* u, const void* v, int dtype, const doub
     if (dtype == NFX_F64) {
         const double* pu = (const double*)u;
         const double* pv = (const double*)v;
-        if (aligned32 && ncols % 4 == 0 && ld % 4 == 0)
+        if (aligned32 && ld % 4 == 0 && (ncols % 4 == 0 || ld >= (ncols + 3) / 4 * 4))
             dispatch_ldg<double, 4>(pu, pv, thickness, arc1, arc2, eflux, nt, nz, ncols, ld, scale, sverdrup, fill,
                                     has_fill, keep_l2, opt, s);
-        else if (aligned16 && ncols % 2 == 0 && ld % 2 == 0)
+        else if (aligned16 && ld % 2 == 0 && (ncols % 2 == 0 || ld >= (ncols + 1) / 2 * 2))
             dispatch_ldg<double, 2>(pu, pv, thickness, arc1, arc2, eflux, nt, nz, ncols, ld, scale, sverdrup, fill,
                                     has_fill, keep_l2, opt, s);
         else
@@ -433,10 +439,10 @@ void edgeflux_assemble_panel(const void* u, const void* v, int dtype, const doub
     } else {
         const float* pu = (const float*)u;
         const float* pv = (const float*)v;
-        if (aligned32 && ncols % 8 == 0 && ld % 8 == 0)
+        if (aligned32 && ld % 8 == 0 && (ncols % 8 == 0 || ld >= (ncols + 7) / 8 * 8))
             dispatch_ldg<float, 8>(pu, pv, thickness, arc1, arc2, eflux, nt, nz, ncols, ld, scale, sverdrup,
                                    (float)fill, has_fill, keep_l2, opt, s);
-        else if (aligned16 && ncols % 4 == 0 && ld % 4 == 0)
+        else if (aligned16 && ld % 4 == 0 && (ncols % 4 == 0 || ld >= (ncols + 3) / 4 * 4))
             dispatch_ldg<float, 4>(pu, pv, thickness, arc1, arc2, eflux, nt, nz, ncols, ld, scale, sverdrup,
                                    (float)fill, has_fill, keep_l2, opt, s);
         else

@@ -245,14 +245,17 @@ class PolylineIntegral(object):
 
     def _flux_series_device(self, u, v, thickness, arc1, arc2, sverdrup, fill, order, eflux, out):
         torch = _torch()
-        if u.dim() == 3:
-            u, v = u.unsqueeze(0), v.unsqueeze(0)
-        if u.dim() != 4 or u.shape != v.shape:
-            raise ValueError("uo/vo shape does not match (t, z, y, x) or (z, y, x)")
+        ncells = self._grid.getNumberOfCells() if self._grid is not None else -1
+        if u.dim() == 3 and u.shape[2] != ncells and u.shape[1] * u.shape[2] == ncells:
+            u, v = u.unsqueeze(0), v.unsqueeze(0)          # (z, y, x): one time step (field.py:130)
         for name, t in (('u', u), ('v', v)):
-            _require_cuda(t, u.dtype, name)
-        nt, nz, ny, nx = u.shape
-        ncell = ny * nx
+            if not isinstance(t, torch.Tensor) or not t.is_cuda:
+                raise TypeError(f'{name} must be a CUDA tensor (there is no CPU fallback)')
+        if u.dtype != v.dtype or u.shape != v.shape or u.stride() != v.stride():
+            raise ValueError('uo and vo must have the same dtype, shape and strides')
+        nt, nz, ncell, ld = _plane_layout(u, 'uo')
+        if ncell != ncells:
+            raise ValueError(f'uo has {ncell} cells per level, the grid has {ncells}')
         for name, t, n in (('thickness', thickness, nz), ('arc1', arc1, ncell), ('arc2', arc2, ncell)):
             _require_cuda(t, torch.float64, name)
             if t.numel() != n:
@@ -266,8 +269,8 @@ class PolylineIntegral(object):
             out = torch.empty((nt, m), dtype=torch.float64, device=u.device)
         with torch.cuda.device(u.device):
             # eflux NULL -> the fast path: edge fluxes stay in an L2-resident ring between K2 and K3
-            _lib.call('nfx_flux_series', ctypes.byref(self._h), _t_ptr(u), _t_ptr(v), _dtype_code(str(u.dtype)),
-                      _t_ptr(thickness), _t_ptr(arc1), _t_ptr(arc2), nt, nz, int(bool(sverdrup)), float(fill),
+            _lib.call('nfx_flux_series_ld', ctypes.byref(self._h), _t_ptr(u), _t_ptr(v), _dtype_code(str(u.dtype)),
+                      _t_ptr(thickness), _t_ptr(arc1), _t_ptr(arc2), nt, nz, ld, int(bool(sverdrup)), float(fill),
                       _ORDERS[order], _t_ptr(eflux) if eflux is not None else None, _t_ptr(out), _stream_ptr())
         return out
 
@@ -307,6 +310,25 @@ def _to_numpy(x):
     return numpy.asarray(x)
 
 
+def _plane_layout(t, name, ncell_expected=None):
+    """(nt, nz, ncell, ld) of a uo/vo device tensor: (nt, nz, ny, nx) contiguous, or (nt, nz, ncell) whose level
+    planes are padded in memory (stride(1) = ld >= ncell, stride(2) = 1, stride(0) = nz*ld)"""
+    if t.dim() == 4:
+        if not t.is_contiguous():
+            raise ValueError(f'{name} must be contiguous')
+        nt, nz = t.shape[0], t.shape[1]
+        ncell = t.shape[2] * t.shape[3]
+        return nt, nz, ncell, ncell
+    if t.dim() == 3:
+        nt, nz, ncell = t.shape
+        ld = t.stride(1) if nz > 1 else (t.stride(0) if nt > 1 else ncell)
+        ok = t.stride(2) == 1 and ld >= ncell and (nt == 1 or t.stride(0) == nz * ld) and (nz == 1 or t.stride(1) == ld)
+        if not ok:
+            raise ValueError(f'{name}: unsupported strides {t.stride()} for shape {tuple(t.shape)}')
+        return nt, nz, ncell, ld
+    raise ValueError(f"{name} shape does not match (t, z, y, x) or (t, z, ncell)")
+
+
 def _require_cuda(t, dtype, name):
     torch = _torch()
     if not isinstance(t, torch.Tensor) or not t.is_cuda:
@@ -319,14 +341,15 @@ def _require_cuda(t, dtype, name):
 
 # -- K2 as a free function (Field.readField + Field.computeIntegratedFlux for many time steps) ------------
 def edgeFluxAssemble(u, v, thickness, arc1, arc2, sverdrup=False, fill=float('nan'), out=None):
-    """u, v cuda (nt, nz, ny, nx) or (nt, nz, ncell); returns eflux cuda (nt, 2*ncell): [eU | eV] signed"""
+    """u, v cuda (nt, nz, ny, nx) or (nt, nz, ncell) (level planes may be padded in memory, see _plane_layout);
+    returns eflux cuda (nt, 2*ncell): [eU | eV] signed"""
     torch = _torch()
     for name, t in (('u', u), ('v', v)):
-        _require_cuda(t, u.dtype, name)
-    if u.shape != v.shape or u.dim() not in (3, 4):
-        raise ValueError('u and v must both be (nt, nz, ny, nx) or (nt, nz, ncell)')
-    nt, nz = u.shape[0], u.shape[1]
-    ncell = int(numpy.prod(u.shape[2:]))
+        if not isinstance(t, torch.Tensor) or not t.is_cuda:
+            raise TypeError(f'{name} must be a CUDA tensor (there is no CPU fallback)')
+    if u.dtype != v.dtype or u.shape != v.shape or u.stride() != v.stride():
+        raise ValueError('u and v must have the same dtype, shape and strides')
+    nt, nz, ncell, ld = _plane_layout(u, 'u')
     for name, t, n in (('thickness', thickness, nz), ('arc1', arc1, ncell), ('arc2', arc2, ncell)):
         _require_cuda(t, torch.float64, name)
         if t.numel() != n:
@@ -334,8 +357,8 @@ def edgeFluxAssemble(u, v, thickness, arc1, arc2, sverdrup=False, fill=float('na
     if out is None:
         out = torch.empty((nt, 2 * ncell), dtype=torch.float64, device=u.device)
     with torch.cuda.device(u.device):
-        _lib.call('nfx_edgeflux_assemble', _t_ptr(u), _t_ptr(v), _dtype_code(str(u.dtype)), _t_ptr(thickness),
-                  _t_ptr(arc1), _t_ptr(arc2), nt, nz, ncell, int(bool(sverdrup)), float(fill), _t_ptr(out),
+        _lib.call('nfx_edgeflux_assemble_ld', _t_ptr(u), _t_ptr(v), _dtype_code(str(u.dtype)), _t_ptr(thickness),
+                  _t_ptr(arc1), _t_ptr(arc2), nt, nz, ncell, ld, int(bool(sverdrup)), float(fill), _t_ptr(out),
                   _stream_ptr())
     return out
 

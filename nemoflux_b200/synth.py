@@ -113,16 +113,22 @@ class OrcaSynth(object):
             v[self.mask] = numpy.nan
         return u.astype(dtype, copy=False), v.astype(dtype, copy=False)
 
-    def fill_device(self, t0, nt_local, device, dtype=None, out=None):
-        """u, v cuda tensors (nt_local, nz, ny, nx) for time steps t0 .. t0+nt_local-1"""
+    def fill_device(self, t0, nt_local, device, dtype=None, out=None, pad=0):
+        """u, v cuda tensors (nt_local, nz, ny, nx) for time steps t0 .. t0+nt_local-1.
+        pad > 0: level planes padded in memory to a multiple of `pad` cells -- the tensors are then
+        (nt_local, nz, ncell) views with stride(1) = ld (32-byte aligned rows for pad = 4 doubles / 8 floats)"""
         import torch
         dtype = dtype or torch.float64
         shape = (nt_local, self.nz, self.ny, self.nx)
-        if out is None:
+        if out is not None:
+            u, v = out
+        elif pad and self.ncell % pad != 0:
+            ld = (self.ncell + pad - 1) // pad * pad
+            u = torch.zeros((nt_local, self.nz, ld), dtype=dtype, device=device)[:, :, :self.ncell]
+            v = torch.zeros((nt_local, self.nz, ld), dtype=dtype, device=device)[:, :, :self.ncell]
+        else:
             u = torch.empty(shape, dtype=dtype, device=device)
             v = torch.empty(shape, dtype=dtype, device=device)
-        else:
-            u, v = out
         U1, V1, U2, V2 = (torch.from_numpy(a).to(device) for a in (self.U1, self.V1, self.U2, self.V2))
         mask = torch.from_numpy(self.mask).to(device) if self.mask is not None else None
         # work on slabs of levels so that the temporaries stay small next to an ORCA12 time step (7.9 GB)
@@ -143,7 +149,7 @@ class OrcaSynth(object):
                     acc[:n].add_(tmp[:n])
                     if mask is not None:
                         acc[:n].masked_fill_(mask[k0:k1], nan)
-                    dst[i, k0:k1].copy_(acc[:n])
+                    dst[i, k0:k1].copy_(acc[:n].reshape(dst[i, k0:k1].shape))
         return u, v
 
     # ---- transects -----------------------------------------------------------------------------------

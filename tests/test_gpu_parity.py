@@ -388,3 +388,49 @@ def test_fast_series_path_matches_classic(gpu, oracle, slot_mb, shape):
     finally:
         _lib.set_option(_lib.NFX_OPT_RING_SLOT_MB, 8)
         _lib.set_option(_lib.NFX_OPT_FAST_SERIES, 1)
+
+
+@pytest.mark.parametrize('dtype', [numpy.float64, numpy.float32])
+def test_padded_level_planes(gpu, oracle, dtype):
+    """u/v stored with padded level planes (ld > ncell, 32-byte aligned rows): same bits as the dense layout,
+    through K2 alone, the two-launch series and the fused series (several panels forced by a 1 MB ring slot)"""
+    import torch
+    from nemoflux_b200 import _lib
+    nx, ny, nz, nt = 301, 251, 4, 5                 # ncell = 75551, odd
+    g = oracle.DataGen(nx=nx, ny=ny, nz=nz, nt=nt, deltaDeg=(20., 30.))
+    P, arc = g.points(), oracle.arc_lengths(g.points())
+    u, v = g.uv(SF_C2)
+    u, v = u.astype(dtype), v.astype(dtype)
+    u[:, :, 100:120, 50:90] = numpy.nan
+    ncell = nx * ny
+    pad = 4 if dtype == numpy.float64 else 8
+    ld = (ncell + pad - 1) // pad * pad
+    d = 'cuda'
+    tdt = torch.float64 if dtype == numpy.float64 else torch.float32
+    up = torch.full((nt, nz, ld), 7.0, dtype=tdt, device=d)[:, :, :ncell]
+    vp = torch.full((nt, nz, ld), 7.0, dtype=tdt, device=d)[:, :, :ncell]
+    up.copy_(torch.from_numpy(u.reshape(nt, nz, ncell)))
+    vp.copy_(torch.from_numpy(v.reshape(nt, nz, ncell)))
+    th, a1, a2 = (torch.from_numpy(x).to(d) for x in (g.thickness(), arc[:, 1].copy(), arc[:, 2].copy()))
+    dense = [torch.from_numpy(x).to(d) for x in (u, v)]
+    ef_dense = gpu.edgeFluxAssemble(dense[0], dense[1], th, a1, a2).cpu().numpy()
+    ef_pad = gpu.edgeFluxAssemble(up, vp, th, a1, a2).cpu().numpy()
+    assert_bitwise(ef_pad, ef_dense, 'padded vs dense K2')
+    transects = random_transects(numpy.random.default_rng(3), 6) + [tr(README_C2)]
+    _, p = _build(gpu, P, ny, nx)
+    p.computeWeights(transects)
+    try:
+        _lib.set_option(_lib.NFX_OPT_RING_SLOT_MB, 1)
+        for mode in (0, 2):
+            _lib.set_option(_lib.NFX_OPT_FAST_SERIES, mode)
+            s_dense = p.fluxSeries(dense[0], dense[1], th, a1, a2).cpu().numpy()
+            s_pad = p.fluxSeries(up, vp, th, a1, a2).cpu().numpy()
+            assert numpy.array_equal(s_pad, s_dense)
+        ref = oracle.flux_series(P, transects, u.astype(numpy.float64), v.astype(numpy.float64), g.thickness(), use_c=True)
+        scale = _l1_scale(oracle, P, transects, u.astype(numpy.float64), v.astype(numpy.float64), g.thickness(), arc, False)
+        assert (numpy.abs(s_pad - ref) <= FLUX_RTOL * scale + 1e-300).all()
+    finally:
+        _lib.set_option(_lib.NFX_OPT_RING_SLOT_MB, 8)
+        _lib.set_option(_lib.NFX_OPT_FAST_SERIES, 1)
+    with pytest.raises(ValueError):
+        gpu.edgeFluxAssemble(up.transpose(0, 1), vp.transpose(0, 1), th, a1, a2)

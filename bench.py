@@ -46,6 +46,9 @@ def parse_args():
     ap.add_argument('--workload', default='C3')
     ap.add_argument('--nt-local', type=int, default=0, help='time steps resident per rank (0 = the workload\'s nt)')
     ap.add_argument('--nt-total', type=int, default=0, help='strong scaling: shard this many time steps over the ranks')
+    ap.add_argument('--balance', action='store_true',
+                    help='with --nt-total: shard at (time step, panel of cells) granularity so that every rank gets the '
+                         'same number of batches (73 snapshots over 8 GPUs: 9.125 steps each instead of 10,9,..,9)')
     ap.add_argument('--force-host-samples', action='store_true', help='run e2e / cpu samples even for >12 GB time steps')
     ap.add_argument('--dtype', default='f64', choices=['f64', 'f32'], help='storage type of uo/vo (compute is f64)')
     ap.add_argument('--e2e-steps', type=int, default=24, help='time steps of the host-buffer (e2e) sample')
@@ -269,16 +272,28 @@ def run_b200(args):
     torch.cuda.synchronize()
     t_k1 = time.perf_counter() - tk
 
+    bal = None
+    if args.balance and args.nt_total > 0 and world > 1:
+        npanels, panel_cells = pli.getNumberOfPanels()
+        bal = nfx_dist.shard_batches(nt_total, npanels, world, rank)
+        bal['npanels'] = npanels
+        t0_rank, nt_local = bal['t_first'], bal['nt_touched']
+        counts = [nfx_dist.shard_batches(nt_total, npanels, world, r)['nt_touched'] for r in range(world)]
+        cmax = max(counts)
+        _lib.set_option(_lib.NFX_OPT_FAST_SERIES, 2)
     thickness = torch.from_numpy(syn.thickness).to(dev)
     arc1 = torch.from_numpy(syn.arc1).to(dev)
     arc2 = torch.from_numpy(syn.arc2).to(dev)
     pad = 0 if args.no_pad else (4 if args.dtype == 'f64' else 8)
     u, v = syn.fill_device(t0_rank, nt_local, dev, tdtype, pad=pad)
     padded = u.dim() == 3
+    nt_resident = nt_local
     eflux = torch.empty((nt_local, 2 * syn.ncell), dtype=torch.float64, device=dev) if args.classic else None
     series_pad = torch.zeros((cmax, M), dtype=torch.float64, device=dev)       # padded to the largest shard
     series = series_pad[:nt_local]
     gathered = torch.empty((world * cmax, M), dtype=torch.float64, device=dev) if world > 1 else None
+    full_series = torch.zeros((nt_total, M), dtype=torch.float64, device=dev) if bal is not None else None
+    shards_all = [nfx_dist.shard_batches(nt_total, bal['npanels'], world, r) for r in range(world)] if bal else None
 
     def step(ev=None):
         if ev is not None:
@@ -288,6 +303,12 @@ def run_b200(args):
             if ev is not None:
                 ev[1].record()
             pli.integrate(eflux, order=args.order, out=series)                           # K3
+        elif bal is not None:
+            # balanced sharding: this rank's batch range, partial sums; combined after the allgather
+            pli.fluxSeries(u, v, thickness, arc1, arc2, order=args.order, out=series,
+                           batch_range=(bal['b0'], bal['b1']))
+            if ev is not None:
+                ev[1].record()
         else:
             # the public call: K2 + K3 batches, edge fluxes kept in an L2-resident ring (nfx_flux_series, eflux=NULL)
             pli.fluxSeries(u, v, thickness, arc1, arc2, order=args.order, out=series)
@@ -297,6 +318,14 @@ def run_b200(args):
             ev[2].record()
         if world > 1:
             dist.all_gather_into_tensor(gathered, series_pad)
+            if bal is not None:          # time steps shared by two ranks: add the partial sums in rank order
+                full_series.zero_()
+                for r in range(world):
+                    sh = shards_all[r]
+                    if sh['nt_touched']:
+                        full_series[sh['t_first']:sh['t_first'] + sh['nt_touched']] += \
+                            gathered[r * cmax:r * cmax + sh['nt_touched']]
+                return full_series
         return gathered if world > 1 else series
 
     def barrier():
@@ -333,7 +362,7 @@ def run_b200(args):
     units_step_all = syn.units_per_step() * nt_total
     value = units_step_all / (ms_per_step * 1e-3)
     final_series = out.cpu().numpy().copy()
-    if world > 1:                                      # drop the padding of the shorter shards
+    if world > 1 and bal is None:                      # drop the padding of the shorter shards
         final_series = numpy.concatenate([final_series[r * cmax:r * cmax + counts[r]] for r in range(world)], 0)
 
     # ---- roofline of K2 -------------------------------------------------------------------------------
@@ -344,6 +373,8 @@ def run_b200(args):
         pass
     peak = float(peaks.get('hbm_gbs', 6650.0))
     k2_bytes = 2.0 * esize * syn.units_per_step() * nt_local            # per launch (one rank)
+    if bal is not None:
+        k2_bytes = 2.0 * esize * syn.units_per_step() * (bal['b1'] - bal['b0']) / bal['npanels']
     achieved = k2_bytes / (k2_ms * 1e-3) / 1e9
     fused_used = (not args.classic) and args.dtype == 'f64' and (
         syn.ncell * 16 <= (args.ring_slot_mb or 8) * (1 << 20) or padded or syn.ncell % 4 == 0)
@@ -406,6 +437,8 @@ def run_b200(args):
     # ---- everything below: rank 0 only, outside the timed region -----------------------------------------
     # properties at full size: linear in (t+1); closed loops 0; node-to-node = analytic value
     parity = {}
+    if bal is not None:
+        nt_local = nt_total                                        # the combined series covers every time step
     s0 = final_series[:nt_local]                                   # rank 0's own shard: t = 0..nt_local-1
     tfac = numpy.arange(1, nt_local + 1, dtype=numpy.float64)[:, None]
     lin = numpy.abs(s0 - s0[0:1] * tfac).max() / max(numpy.abs(s0).max(), 1e-300)
@@ -478,10 +511,12 @@ def run_b200(args):
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
         'warmup': max(args.warmup, 3), 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': scaling,
         'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-        'config': {'workload': f'{args.workload}: {syn.label}, {nt_local} time steps per GPU ({nt_total} total), '
+        'config': {'workload': f'{args.workload}: {syn.label}, {nt_resident} time steps resident per GPU ({nt_total} total), '
                                f'{M} transects, u/v stored {args.dtype} resident in HBM',
-                   'nx': syn.nx, 'ny': syn.ny, 'nz': syn.nz, 'nt_per_gpu': nt_local, 'nt_total': nt_total,
-                   'transects': M, 'storage_dtype': args.dtype, 'sharding': f'time x{world} {counts}',
+                   'nx': syn.nx, 'ny': syn.ny, 'nz': syn.nz, 'nt_per_gpu': nt_resident, 'nt_total': nt_total,
+                   'transects': M, 'storage_dtype': args.dtype,
+                   'sharding': (f'(time step, panel) batches x{world}, {bal["npanels"]} panels per step, balanced'
+                                if bal is not None else f'time x{world} {counts}'),
                    'device_layout': f'(nt, nz, ld={u.stride(1)}) level planes padded to 32 B' if padded
                                     else '(nt, nz, ny, nx) dense',
                    'l2_policy': f'inputs per step {2 * esize * syn.units_per_step() * nt_local / 1e9:.1f} GB >> 126 MB L2',

@@ -139,6 +139,15 @@ int nfx_flux_series(nfx_pli** self, const void* u, const void* v, int dtype, con
 int nfx_flux_series_ld(nfx_pli** self, const void* u, const void* v, int dtype, const double* thickness,
                        const double* arc1, const double* arc2, int nt, int nz, int64_t ld, int sverdrup, double fill,
                        int order, double* eflux, double* series, void* stream);
+/* Finer-than-time-step sharding over GPUs.  The fused pass works on batches b = t*npanels + q (time step t of
+ * the nt resident ones, panel q of npanels panels of panel_cells consecutive cells); this call runs only the
+ * batches [batch_begin, batch_end) and returns PARTIAL sums in series (nt, ntransects): complete for the time
+ * steps whose panels all lie in the range, contributions of the missing panels are 0.  The owner of the other
+ * panels adds its part (nemoflux_b200/dist.py).  Always the fused pass. */
+int nfx_pli_get_num_panels(nfx_pli** self, int* npanels, int64_t* panel_cells);
+int nfx_flux_series_range(nfx_pli** self, const void* u, const void* v, int dtype, const double* thickness,
+                          const double* arc1, const double* arc2, int nt, int nz, int64_t ld, int sverdrup, double fill,
+                          int order, int64_t batch_begin, int64_t batch_end, double* series, void* stream);
 /* everything from HOST buffers (the call a non-CUDA host makes): u, v host (nt,nz,ny,nx), thickness
  * host (nz), arc1/arc2 host (ncell); series host (nt, ntransects).  Streams time chunks through
  * double-buffered device staging (host buffers may be pinned or pageable). chunk_steps <= 0 = auto */

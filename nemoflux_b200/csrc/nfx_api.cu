@@ -81,7 +81,8 @@ static int64_t fused_panel_cells(int64_t ncell) {
 
 static void flux_series_fast(PliDev& p, const void* u, const void* v, int dtype, const double* thickness,
                              const double* arc1, const double* arc2, int nt, int nz, int64_t ld, int sverdrup,
-                             double fill, int order, double* series, cudaStream_t stream) {
+                             double fill, int order, double* series, cudaStream_t stream, int64_t batch_begin = 0,
+                             int64_t batch_end = -1) {
     NFX_REQUIRE(order == NFX_ORDER_LIST || order == NFX_ORDER_MAP, "order must be NFX_ORDER_LIST or NFX_ORDER_MAP");
     NFX_REQUIRE(p.csr[order][0].rowptr.p != nullptr, "computeWeights was not called");
     NFX_REQUIRE(p.has_compact, "nfx_grid_set_cgrid_shape must be called before computeWeights for the flux path");
@@ -92,7 +93,9 @@ static void flux_series_fast(PliDev& p, const void* u, const void* v, int dtype,
     PanelPlan& pl = p.plan[order];
     if (!pl.built || pl.panel_cells != panel) build_panel_plan(p, order, panel, stream);
     p.partial.ensure((size_t)nt * std::max<int64_t>(pl.nsr, 1));
-    flux_series_fused(p, pl, u, v, dtype, thickness, arc1, arc2, nt, nz, ld, sverdrup, fill, p.partial.p, stream);
+    if (batch_end < 0) batch_end = (int64_t)nt * pl.npanels;
+    flux_series_fused(p, pl, u, v, dtype, thickness, arc1, arc2, nt, nz, ld, sverdrup, fill, batch_begin, batch_end,
+                      p.partial.p, stream);
     reduce_subrows(p.partial.p, nt, pl.nsr, pl.tr_ptr.p, pl.tr_sr.p, M, series, stream);
 }
 
@@ -467,6 +470,32 @@ int nfx_flux_series_ld(nfx_pli** self, const void* u, const void* v, int dtype, 
         edgeflux_assemble_panel(u, v, dtype, thickness, arc1, arc2, nt, nz, ncell, ld, sverdrup, fill, eflux, 0, g_k2opt,
                                 (cudaStream_t)stream);
         csr_integrate(c, p.ntransects, eflux, ncell * 2, nt, series, (cudaStream_t)stream);
+    });
+}
+
+int nfx_pli_get_num_panels(nfx_pli** self, int* npanels, int64_t* panel_cells) {
+    return guarded([&] {
+        NFX_REQUIRE(self && *self && npanels, "NULL pointer");
+        PliDev& p = (*self)->d;
+        NFX_REQUIRE(p.grid && p.grid->ncell > 0, "setGrid / setPoints was not called");
+        const int64_t pc = fused_panel_cells(p.grid->ncell);
+        *npanels = (int)((p.grid->ncell + pc - 1) / pc);
+        if (panel_cells) *panel_cells = pc;
+    });
+}
+
+int nfx_flux_series_range(nfx_pli** self, const void* u, const void* v, int dtype, const double* thickness,
+                          const double* arc1, const double* arc2, int nt, int nz, int64_t ld, int sverdrup, double fill,
+                          int order, int64_t batch_begin, int64_t batch_end, double* series, void* stream) {
+    return guarded([&] {
+        NFX_REQUIRE(self && *self, "NULL handle");
+        PliDev& p = (*self)->d;
+        NFX_REQUIRE(p.grid, "setGrid was not called");
+        DeviceGuard g(p.grid->device);
+        NFX_REQUIRE(u && v && thickness && arc1 && arc2 && series, "NULL pointer");
+        NFX_REQUIRE(ld >= p.grid->ncell, "ld must be >= the number of cells");
+        flux_series_fast(p, u, v, dtype, thickness, arc1, arc2, nt, nz, ld, sverdrup, fill, order, series,
+                         (cudaStream_t)stream, batch_begin, batch_end);
     });
 }
 

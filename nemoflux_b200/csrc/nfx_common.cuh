@@ -99,6 +99,7 @@ struct PanelPlan {
     DevBuf<int64_t> panel_sr;     // (npanels + 1) first sub-row of every panel
     DevBuf<int64_t> tr_ptr;       // (M + 1) per transect: range in tr_sr
     DevBuf<int64_t> tr_sr;        // (nsr) sub-row ids of every transect, ascending
+    std::vector<int64_t> h_panel_sr;   // host copy of panel_sr
 };
 constexpr int64_t kSubRow = 4096;
 
@@ -167,7 +168,7 @@ void build_panel_plan(PliDev& p, int order, int64_t panel_cells, cudaStream_t s)
 // K2+K3 fused persistent pass (nfx_k23_fused.cu)
 void flux_series_fused(PliDev& p, const PanelPlan& pl, const void* u, const void* v, int dtype, const double* thickness,
                        const double* arc1, const double* arc2, int nt, int nz, int64_t ld, int sverdrup, double fill,
-                       double* out, cudaStream_t s);
+                       int64_t batch_begin, int64_t batch_end, double* out, cudaStream_t s);
 int fused_tile_columns(int dtype, const void* u, const void* v, int64_t ncell, int64_t ld, int64_t panel);
 int fused_error_flag(PliDev& p, cudaStream_t s);
 int k3_group_for(int64_t nnz, int64_t nrows);

@@ -635,6 +635,7 @@ void build_panel_plan(PliDev& p, int order, int64_t panel_cells, cudaStream_t s)
         pl.nnz = 0;
         pl.nsr = 0;
         pl.max_sr_per_panel = 0;
+        pl.h_panel_sr.assign((size_t)npanels + 1, 0);
         pl.built = true;
         return;
     }
@@ -674,6 +675,7 @@ void build_panel_plan(PliDev& p, int order, int64_t panel_cells, cudaStream_t s)
     pl.nnz = nnz;
     pl.nsr = nsr;
     pl.max_sr_per_panel = max_sr;
+    pl.h_panel_sr = panel_sr;
     pl.idx.ensure((size_t)std::max<int64_t>(nnz, 1));
     pl.w.ensure((size_t)std::max<int64_t>(nnz, 1));
     pl.sr_ptr.ensure((size_t)nsr + 1);

@@ -50,6 +50,7 @@ struct FusedArgs {
     int* sync;              // [0] work counter, [1] error flag, [2 .. 2+nb) K2 tiles done, [2+nb .. 2+2nb) K3 items done
     int64_t ncell, ld, panel, slot_elems;   // ld = cells per level plane in memory (>= ncell)
     int nt, nz, ntransects, npanels, nbatches, ntiles, nk3, ring_slots;
+    int batch_begin;        // first (time step, panel) batch of this call: batch index = batch_begin + b
     int debug_skip_k3;      // NFX_DEBUG_FUSED_SKIP_K3 (experiments only)
     double scale, fill;
     int use_scale, has_fill;
@@ -121,8 +122,8 @@ k23_fused(const FusedArgs a) {
             const int b = bb;
             if (b >= a.nbatches) continue;
             if (b >= a.ring_slots && !cta_wait(k3done + (b - a.ring_slots), a.nk3, err, &s_ok)) break;
-            const int64_t t = b / a.npanels;
-            const int q = b - (int)t * a.npanels;
+            const int64_t t = (a.batch_begin + b) / a.npanels;
+            const int q = (a.batch_begin + b) - (int)t * a.npanels;
             const int64_t pc0 = (int64_t)q * a.panel;
             const int64_t pc = min(a.panel, a.ncell - pc0);
             const int64_t cl = ((int64_t)r * kFusedBlock + threadIdx.x) * VEC;   // column inside the panel
@@ -212,8 +213,8 @@ k23_fused(const FusedArgs a) {
             if (b < 0) continue;
             if (!cta_wait(k2done + b, a.ntiles, err, &s_ok)) break;
             __threadfence();
-            const int64_t t = b / a.npanels;
-            const int q = b - (int)t * a.npanels;
+            const int64_t t = (a.batch_begin + b) / a.npanels;
+            const int q = (a.batch_begin + b) - (int)t * a.npanels;
             {
                 // one warp per sub-row (<= kSubRow entries): lane-strided partial sums, fixed shuffle tree
                 const int64_t sr = a.panel_sr[q] + (int64_t)(r - a.ntiles) * kWarps + wid;
@@ -290,7 +291,7 @@ int fused_tile_columns(int dtype, const void* u, const void* v, int64_t ncell, i
 
 void flux_series_fused(PliDev& p, const PanelPlan& pl, const void* u, const void* v, int dtype, const double* thickness,
                        const double* arc1, const double* arc2, int nt, int nz, int64_t ld, int sverdrup, double fill,
-                       double* out, cudaStream_t s) {
+                       int64_t batch_begin, int64_t batch_end, double* out, cudaStream_t s) {
     const int64_t ncell = p.grid->ncell;
     const int M = p.ntransects;
     const int vec = fused_tile_columns(dtype, u, v, ncell, ld, pl.panel_cells);
@@ -308,7 +309,10 @@ void flux_series_fused(PliDev& p, const PanelPlan& pl, const void* u, const void
     a.nz = nz;
     a.ntransects = M;
     a.npanels = pl.npanels;
-    a.nbatches = nt * pl.npanels;
+    NFX_REQUIRE(batch_begin >= 0 && batch_begin <= batch_end && batch_end <= (int64_t)nt * pl.npanels,
+                "fused pass: bad batch range");
+    a.batch_begin = (int)batch_begin;
+    a.nbatches = (int)(batch_end - batch_begin);
     const int64_t item_cols = (int64_t)kFusedBlock * vec;
     a.ntiles = (int)((std::min(pl.panel_cells, ncell) + item_cols - 1) / item_cols);
     a.nk3 = std::max(1, (pl.max_sr_per_panel + kWarps - 1) / kWarps);
@@ -337,7 +341,23 @@ void flux_series_fused(PliDev& p, const PanelPlan& pl, const void* u, const void
     a.ring_slots = slots;
     p.ring.ensure((size_t)(a.slot_elems * slots));
     NFX_CUDA(cudaMemsetAsync(out, 0xFF, sizeof(double) * (size_t)nt * std::max<int64_t>(pl.nsr, 1), s));   // NaN: a pass that
-    // aborts (bounded spin overflow) must not leave plausible numbers behind
+    // aborts (bounded spin overflow) must not leave plausible numbers behind.  Sub-rows of batches outside
+    // [batch_begin, batch_end) belong to other ranks: they contribute 0 here.
+    if (pl.nsr > 0) {
+        auto zero_rows = [&](int64_t b0, int64_t b1) {   // batches [b0, b1) -> contiguous runs of sub-rows per time step
+            while (b0 < b1) {
+                const int64_t t = b0 / pl.npanels, q0 = b0 - t * pl.npanels;
+                const int64_t q1 = std::min<int64_t>(pl.npanels, q0 + (b1 - b0));
+                const int64_t r0 = pl.h_panel_sr[q0], r1 = pl.h_panel_sr[q1];
+                if (r1 > r0)
+                    NFX_CUDA(cudaMemsetAsync(out + t * pl.nsr + r0, 0, sizeof(double) * (size_t)(r1 - r0), s));
+                b0 += q1 - q0;
+            }
+        };
+        zero_rows(0, batch_begin);
+        zero_rows(batch_end, (int64_t)nt * pl.npanels);
+    }
+    if (a.nbatches == 0) return;
     p.fused_sync.ensure((size_t)(2 + 2 * a.nbatches));
     a.ring = p.ring.p;
     a.sync = p.fused_sync.p;

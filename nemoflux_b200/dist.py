@@ -56,6 +56,62 @@ def allgather_series(local, nt, group=None):
     return torch.cat([out[r * cmax:r * cmax + counts[r]] for r in range(world)], dim=0)
 
 
+def shard_batches(nt, npanels, world, rank):
+    """Balanced sharding at (time step, panel of cells) granularity.
+
+    The flattened batch space b = t*npanels + q (nt*npanels batches) is cut into `world` contiguous ranges of
+    equal length (+-1 batch): 73 snapshots x 26 panels over 8 ranks -> 237 or 238 batches = 9.125 time steps each
+    instead of 10,9,...,9.  Returns dict(t_first, nt_touched, b0, b1): the rank needs the time steps
+    t_first .. t_first+nt_touched-1 in memory and runs the LOCAL batch range [b0, b1) (indices relative to
+    t_first*npanels) with PolylineIntegral.fluxSeries(batch_range=(b0, b1))."""
+    if world <= 0 or not (0 <= rank < world):
+        raise ValueError(f'bad rank {rank} of {world}')
+    total = int(nt) * int(npanels)
+    base, rem = divmod(total, world)
+    g0 = rank * base + min(rank, rem)
+    g1 = g0 + base + (1 if rank < rem else 0)
+    if g1 == g0:
+        return dict(t_first=0, nt_touched=0, b0=0, b1=0, g0=g0, g1=g1)
+    t_first = g0 // npanels
+    t_last = (g1 - 1) // npanels
+    return dict(t_first=t_first, nt_touched=t_last - t_first + 1, b0=g0 - t_first * npanels,
+                b1=g1 - t_first * npanels, g0=g0, g1=g1)
+
+
+def combine_partial_series(partial, nt, npanels, group=None):
+    """partial: this rank's (nt_touched, M) partial sums from fluxSeries(batch_range=...) for its shard_batches
+    range -> the full (nt, M) series on every rank.  One all_gather of the (padded) partial blocks; a time step
+    shared by several ranks is summed in rank order (deterministic)."""
+    import torch
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+    else:
+        world, rank = 1, 0
+    shards = [shard_batches(nt, npanels, world, r) for r in range(world)]
+    need = shards[rank]['nt_touched']
+    if partial.shape[0] != need:
+        raise ValueError(f'rank {rank} must hold {need} time steps, got {partial.shape[0]}')
+    m = partial.shape[1]
+    cmax = max(max(s['nt_touched'] for s in shards), 1)
+    padded = torch.zeros((cmax, m), dtype=partial.dtype, device=partial.device)
+    padded[:partial.shape[0]] = partial
+    if world > 1:
+        gathered = torch.empty((world * cmax, m), dtype=partial.dtype, device=partial.device)
+        if partial.is_cuda:
+            dist.all_gather_into_tensor(gathered, padded, group=group)
+        else:
+            dist.all_gather(list(gathered.view(world, cmax, m).unbind(0)), padded, group=group)
+    else:
+        gathered = padded
+    out = torch.zeros((nt, m), dtype=partial.dtype, device=partial.device)
+    for r, s in enumerate(shards):                      # rank order -> the same sum on every rank
+        n = s['nt_touched']
+        if n:
+            out[s['t_first']:s['t_first'] + n] += gathered[r * cmax:r * cmax + n]
+    return out
+
+
 def allreduce_max(value, device=None, group=None):
     """max over ranks of a python float (Field.maxAbsFlux semantics, field.py:234)"""
     import torch

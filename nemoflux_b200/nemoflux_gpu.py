@@ -230,20 +230,31 @@ class PolylineIntegral(object):
                       _t_ptr(out), _stream_ptr())
         return out
 
+    def getNumberOfPanels(self):
+        """(npanels, panel_cells) of the fused pass: batches are (time step, panel) pairs, see fluxSeries(batch_range=)"""
+        n, pc = ctypes.c_int(), ctypes.c_int64()
+        _lib.call('nfx_pli_get_num_panels', ctypes.byref(self._h), ctypes.byref(n), ctypes.byref(pc))
+        return n.value, pc.value
+
     def fluxSeries(self, u, v, thickness, arc1, arc2, sverdrup=False, fill=float('nan'), order='map', eflux=None,
-                   out=None, chunk_steps=0):
+                   out=None, chunk_steps=0, batch_range=None):
         """flux time series of every transect: (nt, M).
 
         u, v: (nt, nz, ny, nx) [or (nz, ny, nx)] float64/float32, either cuda tensors (device path: K2+K3 on
         the current stream, returns a cuda tensor) or host numpy arrays / CPU tensors (streams time chunks
         through double-buffered device staging, returns a numpy array).  thickness (nz), arc1/arc2 (ncell)
-        on the same side as u, v.  Needs Grid.setCGridShape before computeWeights."""
+        on the same side as u, v.  Needs Grid.setCGridShape before computeWeights.
+
+        batch_range=(b0, b1) (device tensors only): run only the batches b = t*npanels + q in [b0, b1) and return
+        PARTIAL sums -- the building block of the balanced multi-GPU sharding in nemoflux_b200.dist."""
         torch = _torch()
         if isinstance(u, torch.Tensor) and u.is_cuda:
-            return self._flux_series_device(u, v, thickness, arc1, arc2, sverdrup, fill, order, eflux, out)
+            return self._flux_series_device(u, v, thickness, arc1, arc2, sverdrup, fill, order, eflux, out, batch_range)
+        if batch_range is not None:
+            raise ValueError('batch_range needs CUDA tensors')
         return self._flux_series_host(u, v, thickness, arc1, arc2, sverdrup, fill, order, chunk_steps)
 
-    def _flux_series_device(self, u, v, thickness, arc1, arc2, sverdrup, fill, order, eflux, out):
+    def _flux_series_device(self, u, v, thickness, arc1, arc2, sverdrup, fill, order, eflux, out, batch_range=None):
         torch = _torch()
         ncells = self._grid.getNumberOfCells() if self._grid is not None else -1
         if u.dim() == 3 and u.shape[2] != ncells and u.shape[1] * u.shape[2] == ncells:
@@ -267,6 +278,14 @@ class PolylineIntegral(object):
                 raise ValueError(f'eflux must hold nt*2*ncell = {nt * 2 * ncell} values')
         if out is None:
             out = torch.empty((nt, m), dtype=torch.float64, device=u.device)
+        if batch_range is not None:
+            if eflux is not None:
+                raise ValueError('batch_range and eflux cannot be combined')
+            with torch.cuda.device(u.device):
+                _lib.call('nfx_flux_series_range', ctypes.byref(self._h), _t_ptr(u), _t_ptr(v), _dtype_code(str(u.dtype)),
+                          _t_ptr(thickness), _t_ptr(arc1), _t_ptr(arc2), nt, nz, ld, int(bool(sverdrup)), float(fill),
+                          _ORDERS[order], int(batch_range[0]), int(batch_range[1]), _t_ptr(out), _stream_ptr())
+            return out
         with torch.cuda.device(u.device):
             # eflux NULL -> the fast path: edge fluxes stay in an L2-resident ring between K2 and K3
             _lib.call('nfx_flux_series_ld', ctypes.byref(self._h), _t_ptr(u), _t_ptr(v), _dtype_code(str(u.dtype)),

@@ -434,3 +434,45 @@ def test_padded_level_planes(gpu, oracle, dtype):
         _lib.set_option(_lib.NFX_OPT_FAST_SERIES, 1)
     with pytest.raises(ValueError):
         gpu.edgeFluxAssemble(up.transpose(0, 1), vp.transpose(0, 1), th, a1, a2)
+
+
+def test_batch_range_partials_add_up(gpu, oracle):
+    """balanced multi-GPU sharding, emulated on one GPU: every 'rank' runs its (time step, panel) batch range on
+    the time steps it touches; the partial series add up to the full one"""
+    import torch
+    from nemoflux_b200 import _lib, dist
+    nx, ny, nz, nt = 300, 250, 3, 7
+    g = oracle.DataGen(nx=nx, ny=ny, nz=nz, nt=nt, deltaDeg=(20., 30.))
+    P, arc = g.points(), oracle.arc_lengths(g.points())
+    u, v = g.uv(SF_C2)
+    transects = random_transects(numpy.random.default_rng(11), 7) + [tr(README_C2), tr(README_LOOP)]
+    d = 'cuda'
+    _, p = _build(gpu, P, ny, nx)
+    p.computeWeights(transects)
+    th, a1, a2 = (torch.from_numpy(x).to(d) for x in (g.thickness(), arc[:, 1].copy(), arc[:, 2].copy()))
+    ud, vd = torch.from_numpy(u).to(d), torch.from_numpy(v).to(d)
+    try:
+        _lib.set_option(_lib.NFX_OPT_RING_SLOT_MB, 1)
+        _lib.set_option(_lib.NFX_OPT_FAST_SERIES, 2)
+        npanels, pc = p.getNumberOfPanels()
+        assert npanels == 2 and pc % 1024 == 0
+        full = p.fluxSeries(ud, vd, th, a1, a2).cpu().numpy()
+        scale = _l1_scale(oracle, P, transects, u, v, g.thickness(), arc, False)
+        for world in (1, 2, 3, 5):
+            total = numpy.zeros_like(full)
+            for r in range(world):
+                s = dist.shard_batches(nt, npanels, world, r)
+                t0, n = s['t_first'], s['nt_touched']
+                if n == 0:
+                    continue
+                part = p.fluxSeries(ud[t0:t0 + n], vd[t0:t0 + n], th, a1, a2, batch_range=(s['b0'], s['b1']))
+                total[t0:t0 + n] += part.cpu().numpy()
+            assert (numpy.abs(total - full) <= 1e-13 * scale + 1e-300).all(), world
+        # an empty range gives zeros, a bad one is refused
+        z = p.fluxSeries(ud[:2], vd[:2], th, a1, a2, batch_range=(1, 1)).cpu().numpy()
+        assert (z == 0).all()
+        with pytest.raises(RuntimeError):
+            p.fluxSeries(ud[:2], vd[:2], th, a1, a2, batch_range=(0, 2 * npanels + 1))
+    finally:
+        _lib.set_option(_lib.NFX_OPT_RING_SLOT_MB, 8)
+        _lib.set_option(_lib.NFX_OPT_FAST_SERIES, 1)

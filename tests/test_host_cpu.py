@@ -180,6 +180,23 @@ def test_shard_time_partitions():
         dist.shard_time(10, 2, 2)
 
 
+def test_shard_batches_balanced():
+    from nemoflux_b200 import dist
+    for nt, npanels, world in ((73, 26, 8), (7, 2, 3), (5, 1, 8), (365, 3, 4)):
+        covered = 0
+        sizes = []
+        for r in range(world):
+            s = dist.shard_batches(nt, npanels, world, r)
+            assert s['g0'] == covered
+            covered = s['g1']
+            sizes.append(s['g1'] - s['g0'])
+            if s['nt_touched']:
+                assert s['t_first'] * npanels + s['b0'] == s['g0'] and s['t_first'] * npanels + s['b1'] == s['g1']
+                assert 0 <= s['b0'] < npanels and s['b1'] <= s['nt_touched'] * npanels
+        assert covered == nt * npanels and max(sizes) - min(sizes) <= 1
+    assert [dist.shard_batches(73, 26, 8, r)['nt_touched'] for r in range(8)] == [10] * 8      # 9.125 steps each
+
+
 WORKER = r'''
 import os, sys
 import numpy, torch
@@ -197,6 +214,15 @@ out = nd.sharded_flux_series(compute_local, nt)
 assert out.shape == (nt, m) and torch.equal(out, full), (rank, out)
 mx = nd.allreduce_max(float(rank + 1))
 assert mx == world
+# balanced sharding: 3 panels per time step, the partial sums of shared time steps add up
+npanels = 3
+contrib = torch.arange(nt * npanels * m, dtype=torch.float64).reshape(nt, npanels, m) + 1.0
+s = nd.shard_batches(nt, npanels, world, rank)
+part = torch.zeros((s['nt_touched'], m), dtype=torch.float64)
+for b in range(s['b0'], s['b1']):
+    part[b // npanels] += contrib[s['t_first'] + b // npanels, b % npanels]
+tot = nd.combine_partial_series(part, nt, npanels)
+assert torch.equal(tot, contrib.sum(1)), (rank, tot)
 dist.barrier()
 dist.destroy_process_group()
 print('ok', rank)

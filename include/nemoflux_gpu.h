@@ -120,6 +120,16 @@ int nfx_edgeflux_assemble(const void* u, const void* v, int dtype, const double*
 int nfx_edgeflux_assemble_ld(const void* u, const void* v, int dtype, const double* thickness, const double* arc1,
                              const double* arc2, int nt, int nz, int64_t ncell, int64_t ld, int sverdrup, double fill,
                              double* eflux, void* stream);
+/* SURVEY 8f rank 4 -- per-column, per-level vertical scale factors (NEMO e3u/e3v: partial cells, z*) instead of
+ * the 1-D layer thickness of field.py:51: U = sum_k e3u[t,k,c]*u[t,k,c].  e3u, e3v: device, dtype and plane
+ * layout of u, v, (e3_nt, nz, ld) with e3_nt = 1 (time-invariant, e.g. e3u_0 of mesh_mask) or nt.
+ * Algorithmic bytes double (4 streamed arrays). */
+int nfx_edgeflux_assemble_e3(const void* u, const void* v, const void* e3u, const void* e3v, int dtype, int e3_nt,
+                             const double* arc1, const double* arc2, int nt, int nz, int64_t ncell, int64_t ld,
+                             int sverdrup, double fill, double* eflux, void* stream);
+int nfx_flux_series_e3(nfx_pli** self, const void* u, const void* v, const void* e3u, const void* e3v, int dtype,
+                       int e3_nt, const double* arc1, const double* arc2, int nt, int nz, int64_t ld, int sverdrup,
+                       double fill, int order, double* eflux, double* series, void* stream);
 /* the (ncell,4) mint layout of field.py:209-223 from the compact one: south edges of row 0 are 0,
  * west edges x-periodic.  eflux device (nt, 2*ncell) -> iv device (nt, ncell, 4) */
 int nfx_edgeflux_to_cell_by_cell(const double* eflux, int nt, int ny, int nx, double* iv, void* stream);

@@ -50,6 +50,10 @@ SIGNATURES = {
     'nfx_edgeflux_assemble': [c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_int, c_i64, c_int, c_dbl, c_vp, c_vp],
     'nfx_edgeflux_assemble_ld': [c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_int, c_i64, c_i64, c_int, c_dbl, c_vp,
                                  c_vp],
+    'nfx_edgeflux_assemble_e3': [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_vp, c_int, c_int, c_i64, c_i64, c_int,
+                                 c_dbl, c_vp, c_vp],
+    'nfx_flux_series_e3': [P(c_vp), c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_vp, c_int, c_int, c_i64, c_int, c_dbl,
+                           c_int, c_vp, c_vp, c_vp],
     'nfx_edgeflux_to_cell_by_cell': [c_vp, c_int, c_int, c_int, c_vp, c_vp],
     'nfx_edgeflux_absmax': [c_vp, c_int, c_i64, P(c_dbl), c_vp],
     'nfx_pli_integrate': [P(c_vp), c_vp, c_int, c_int, c_vp, c_vp],

@@ -419,6 +419,43 @@ int nfx_edgeflux_assemble_ld(const void* u, const void* v, int dtype, const doub
     });
 }
 
+int nfx_edgeflux_assemble_e3(const void* u, const void* v, const void* e3u, const void* e3v, int dtype, int e3_nt,
+                             const double* arc1, const double* arc2, int nt, int nz, int64_t ncell, int64_t ld,
+                             int sverdrup, double fill, double* eflux, void* stream) {
+    return guarded([&] {
+        int dev;
+        require_gpu(&dev);
+        NFX_REQUIRE(e3u && e3v, "e3u / e3v is NULL");
+        NFX_REQUIRE(ld >= ncell, "ld must be >= ncell");
+        NFX_REQUIRE(e3_nt == 1 || e3_nt == nt, "e3u/e3v must hold 1 (time-invariant) or nt time steps");
+        edgeflux_assemble_panel(u, v, dtype, nullptr, arc1, arc2, nt, nz, ncell, ld, sverdrup, fill, eflux, 0, g_k2opt,
+                                (cudaStream_t)stream, e3u, e3v, e3_nt == 1 ? 0 : (int64_t)nz * ld);
+    });
+}
+
+int nfx_flux_series_e3(nfx_pli** self, const void* u, const void* v, const void* e3u, const void* e3v, int dtype,
+                       int e3_nt, const double* arc1, const double* arc2, int nt, int nz, int64_t ld, int sverdrup,
+                       double fill, int order, double* eflux, double* series, void* stream) {
+    return guarded([&] {
+        NFX_REQUIRE(self && *self, "NULL handle");
+        PliDev& p = (*self)->d;
+        NFX_REQUIRE(p.grid, "setGrid was not called");
+        DeviceGuard g(p.grid->device);
+        NFX_REQUIRE(u && v && e3u && e3v && arc1 && arc2 && series, "NULL pointer");
+        const int64_t ncell = p.grid->ncell;
+        NFX_REQUIRE(ld >= ncell, "ld must be >= the number of cells");
+        NFX_REQUIRE(e3_nt == 1 || e3_nt == nt, "e3u/e3v must hold 1 (time-invariant) or nt time steps");
+        const Csr& c = pick_csr(p, order, 1);
+        if (eflux == nullptr) {
+            p.stage_eflux[0].ensure((size_t)nt * 2 * ncell);
+            eflux = p.stage_eflux[0].p;
+        }
+        edgeflux_assemble_panel(u, v, dtype, nullptr, arc1, arc2, nt, nz, ncell, ld, sverdrup, fill, eflux, 0, g_k2opt,
+                                (cudaStream_t)stream, e3u, e3v, e3_nt == 1 ? 0 : (int64_t)nz * ld);
+        csr_integrate(c, p.ntransects, eflux, ncell * 2, nt, series, (cudaStream_t)stream);
+    });
+}
+
 int nfx_edgeflux_to_cell_by_cell(const double* eflux, int nt, int ny, int nx, double* iv, void* stream) {
     return guarded([&] {
         int dev;

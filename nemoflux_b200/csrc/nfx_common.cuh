@@ -152,7 +152,8 @@ void edgeflux_assemble(const void* u, const void* v, int dtype, const double* th
                        const K2Options& opt, cudaStream_t s);
 void edgeflux_assemble_panel(const void* u, const void* v, int dtype, const double* thickness, const double* arc1,
                              const double* arc2, int nt, int nz, int64_t ncols, int64_t ld, int sverdrup, double fill,
-                             double* eflux, int keep_l2, const K2Options& opt, cudaStream_t s);
+                             double* eflux, int keep_l2, const K2Options& opt, cudaStream_t s,
+                             const void* e3u = nullptr, const void* e3v = nullptr, int64_t e3_tstride = 0);
 void edgeflux_to_cell_by_cell(const double* eflux, int nt, int ny, int nx, double* iv, cudaStream_t s);
 void edgeflux_absmax(const double* eflux, int nt, int64_t ncell, double* result_host, cudaStream_t s);
 

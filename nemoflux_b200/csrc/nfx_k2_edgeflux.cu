@@ -29,15 +29,20 @@ namespace {
 using namespace dev;
 
 // One thread owns VEC adjacent columns of one time step; blockIdx.y = time step.
-template <typename T, int VEC, int UNROLL, int BLOCK>
+// E3: per-column, per-level scale factors e3u/e3v (NEMO's vertical metric, partial cells / z*) replace the 1-D
+// layer thickness dz[k] of field.py:51 -- two more streamed arrays, same layout as u/v.
+template <typename T, int VEC, int UNROLL, int BLOCK, bool E3>
 __global__ void __launch_bounds__(BLOCK)
 k2_edgeflux_ldg(const T* __restrict__ u, const T* __restrict__ v, const double* __restrict__ dz,
                 const double* __restrict__ arc1, const double* __restrict__ arc2, double* __restrict__ eflux, int nz,
-                int64_t ncell, int64_t ld, double scale, int use_scale, T fill, int has_fill, int keep_l2) {
+                int64_t ncell, int64_t ld, double scale, int use_scale, T fill, int has_fill, int keep_l2,
+                const T* __restrict__ e3u, const T* __restrict__ e3v, int64_t e3_tstride) {
     // ncell = columns handled by this launch (a panel of the grid), ld = cells per level plane (row stride of u, v)
     extern __shared__ double s_dz[];
-    for (int k = threadIdx.x; k < nz; k += BLOCK) s_dz[k] = dz[k];
-    __syncthreads();
+    if constexpr (!E3) {
+        for (int k = threadIdx.x; k < nz; k += BLOCK) s_dz[k] = dz[k];
+        __syncthreads();
+    }
     using P = Pack<T, VEC>;
     using V = typename P::type;
     const int64_t t = blockIdx.y;
@@ -45,6 +50,8 @@ k2_edgeflux_ldg(const T* __restrict__ u, const T* __restrict__ v, const double* 
     if (c0 >= ncell) return;
     const T* pu = u + t * nz * ld + c0;
     const T* pv = v + t * nz * ld + c0;
+    const T* pe = E3 ? e3u + t * e3_tstride + c0 : nullptr;   // e3_tstride = 0: time-invariant scale factors
+    const T* pf = E3 ? e3v + t * e3_tstride + c0 : nullptr;
     const uint64_t pol = keep_l2 ? l2_evict_last_policy() : 0;
     const uint64_t pol_ef = l2_evict_first_policy();
     double su[VEC], sv[VEC];
@@ -55,39 +62,59 @@ k2_edgeflux_ldg(const T* __restrict__ u, const T* __restrict__ v, const double* 
     }
     int k = 0;
     for (; k + UNROLL <= nz; k += UNROLL) {
-        V ru[UNROLL], rv[UNROLL];
+        V ru[UNROLL], rv[UNROLL], re[E3 ? UNROLL : 1], rf[E3 ? UNROLL : 1];
 #pragma unroll
         for (int q = 0; q < UNROLL; ++q) {
             ru[q] = ld_stream(reinterpret_cast<const V*>(pu + (int64_t)(k + q) * ld), pol_ef);
             rv[q] = ld_stream(reinterpret_cast<const V*>(pv + (int64_t)(k + q) * ld), pol_ef);
+            if constexpr (E3) {
+                re[q] = ld_stream(reinterpret_cast<const V*>(pe + (int64_t)(k + q) * ld), pol_ef);
+                rf[q] = ld_stream(reinterpret_cast<const V*>(pf + (int64_t)(k + q) * ld), pol_ef);
+            }
         }
 #pragma unroll
         for (int q = 0; q < UNROLL; ++q) {
             pin(ru[q]);
             pin(rv[q]);
+            if constexpr (E3) {
+                pin(re[q]);
+                pin(rf[q]);
+            }
         }
 #pragma unroll
         for (int q = 0; q < UNROLL; ++q) {
-            T a[VEC], b[VEC];
+            T a[VEC], b[VEC], ea[VEC], eb[VEC];
             P::unpack(ru[q], a);
             P::unpack(rv[q], b);
-            const double d = s_dz[k + q];
+            if constexpr (E3) {
+                P::unpack(re[q], ea);
+                P::unpack(rf[q], eb);
+            }
+            const double d = E3 ? 0.0 : s_dz[k + q];
 #pragma unroll
             for (int e = 0; e < VEC; ++e) {
-                su[e] = __dadd_rn(su[e], __dmul_rn(d, clean<T>(a[e], fill, has_fill)));
-                sv[e] = __dadd_rn(sv[e], __dmul_rn(d, clean<T>(b[e], fill, has_fill)));
+                const double du = E3 ? clean<T>(ea[e], fill, has_fill) : d;
+                const double dv = E3 ? clean<T>(eb[e], fill, has_fill) : d;
+                su[e] = __dadd_rn(su[e], __dmul_rn(du, clean<T>(a[e], fill, has_fill)));
+                sv[e] = __dadd_rn(sv[e], __dmul_rn(dv, clean<T>(b[e], fill, has_fill)));
             }
         }
     }
     for (; k < nz; ++k) {
-        T a[VEC], b[VEC];
+        T a[VEC], b[VEC], ea[VEC], eb[VEC];
         P::unpack(ld_stream(reinterpret_cast<const V*>(pu + (int64_t)k * ld), pol_ef), a);
         P::unpack(ld_stream(reinterpret_cast<const V*>(pv + (int64_t)k * ld), pol_ef), b);
-        const double d = s_dz[k];
+        if constexpr (E3) {
+            P::unpack(ld_stream(reinterpret_cast<const V*>(pe + (int64_t)k * ld), pol_ef), ea);
+            P::unpack(ld_stream(reinterpret_cast<const V*>(pf + (int64_t)k * ld), pol_ef), eb);
+        }
+        const double d = E3 ? 0.0 : s_dz[k];
 #pragma unroll
         for (int e = 0; e < VEC; ++e) {
-            su[e] = __dadd_rn(su[e], __dmul_rn(d, clean<T>(a[e], fill, has_fill)));
-            sv[e] = __dadd_rn(sv[e], __dmul_rn(d, clean<T>(b[e], fill, has_fill)));
+            const double du = E3 ? clean<T>(ea[e], fill, has_fill) : d;
+            const double dv = E3 ? clean<T>(eb[e], fill, has_fill) : d;
+            su[e] = __dadd_rn(su[e], __dmul_rn(du, clean<T>(a[e], fill, has_fill)));
+            sv[e] = __dadd_rn(sv[e], __dmul_rn(dv, clean<T>(b[e], fill, has_fill)));
         }
     }
     double* ou = eflux + t * 2 * ncell + c0;
@@ -123,38 +150,44 @@ k2_edgeflux_ldg(const T* __restrict__ u, const T* __restrict__ v, const double* 
     }
 }
 
+struct E3Args {
+    const void* e3u = nullptr;
+    const void* e3v = nullptr;
+    int64_t tstride = 0;
+};
+
 template <typename T, int VEC, int UNROLL, int BLOCK>
 void launch_ldg(const T* u, const T* v, const double* dz, const double* arc1, const double* arc2, double* eflux, int nt,
                 int nz, int64_t ncell, int64_t ld, double scale, int use_scale, T fill, int has_fill, int keep_l2,
-                cudaStream_t s) {
+                const E3Args& e3, cudaStream_t s) {
     const int64_t nthreads = (ncell + VEC - 1) / VEC;
     dim3 grid((unsigned)((nthreads + BLOCK - 1) / BLOCK), (unsigned)nt);
-    k2_edgeflux_ldg<T, VEC, UNROLL, BLOCK><<<grid, BLOCK, sizeof(double) * nz, s>>>(u, v, dz, arc1, arc2, eflux, nz,
-                                                                                    ncell, ld, scale, use_scale, fill,
-                                                                                    has_fill, keep_l2);
+    if (e3.e3u)
+        k2_edgeflux_ldg<T, VEC, UNROLL, BLOCK, true><<<grid, BLOCK, sizeof(double) * nz, s>>>(
+            u, v, dz, arc1, arc2, eflux, nz, ncell, ld, scale, use_scale, fill, has_fill, keep_l2, (const T*)e3.e3u,
+            (const T*)e3.e3v, e3.tstride);
+    else
+        k2_edgeflux_ldg<T, VEC, UNROLL, BLOCK, false><<<grid, BLOCK, sizeof(double) * nz, s>>>(
+            u, v, dz, arc1, arc2, eflux, nz, ncell, ld, scale, use_scale, fill, has_fill, keep_l2, nullptr, nullptr, 0);
 }
 
 template <typename T, int VEC>
 void dispatch_ldg(const T* u, const T* v, const double* dz, const double* arc1, const double* arc2, double* eflux, int nt,
                   int nz, int64_t ncell, int64_t ld, double scale, int use_scale, T fill, int has_fill, int keep_l2,
-                  const K2Options& opt, cudaStream_t s) {
+                  const E3Args& e3, const K2Options& opt, cudaStream_t s) {
     const int unroll = opt.unroll > 0 ? opt.unroll : 5;
     const int block = opt.block > 0 ? opt.block : 256;
 #define NFX_K2_CASE(U, B)                                                                                          \
     if (unroll == U && block == B) {                                                                               \
         launch_ldg<T, VEC, U, B>(u, v, dz, arc1, arc2, eflux, nt, nz, ncell, ld, scale, use_scale, fill, has_fill,  \
-                                 keep_l2, s);                                                                      \
+                                 keep_l2, e3, s);                                                                  \
         return;                                                                                                    \
     }
     NFX_K2_CASE(5, 256)
     NFX_K2_CASE(3, 256)
-    NFX_K2_CASE(8, 256)
     NFX_K2_CASE(15, 256)
     NFX_K2_CASE(5, 128)
-    NFX_K2_CASE(8, 128)
-    NFX_K2_CASE(15, 128)
     NFX_K2_CASE(5, 512)
-    NFX_K2_CASE(3, 512)
 #undef NFX_K2_CASE
     throw Error(NFX_E_INVALID, "edgeflux: unsupported (unroll, block) option pair");
 }
@@ -387,8 +420,15 @@ __global__ void k_absmax(const double* __restrict__ x, int64_t n, unsigned long 
 // and `nt` time steps; ld = cells per level plane.  eflux: (nt, 2*ncols).
 void edgeflux_assemble_panel(const void* u, const void* v, int dtype, const double* thickness, const double* arc1,
                              const double* arc2, int nt, int nz, int64_t ncols, int64_t ld, int sverdrup, double fill,
-                             double* eflux, int keep_l2, const K2Options& opt, cudaStream_t s) {
-    NFX_REQUIRE(u && v && thickness && arc1 && arc2 && eflux, "edgeflux: NULL pointer");
+                             double* eflux, int keep_l2, const K2Options& opt, cudaStream_t s, const void* e3u,
+                             const void* e3v, int64_t e3_tstride) {
+    NFX_REQUIRE(u && v && arc1 && arc2 && eflux, "edgeflux: NULL pointer");
+    NFX_REQUIRE((e3u == nullptr) == (e3v == nullptr), "edgeflux: e3u and e3v go together");
+    NFX_REQUIRE(thickness || e3u, "edgeflux: needs the layer thickness or e3u/e3v");
+    E3Args e3;
+    e3.e3u = e3u;
+    e3.e3v = e3v;
+    e3.tstride = e3_tstride;
     NFX_REQUIRE(nt >= 0 && nz > 0 && ncols > 0 && ld >= ncols, "edgeflux: bad sizes");
     NFX_REQUIRE(dtype == NFX_F64 || dtype == NFX_F32, "edgeflux: dtype must be NFX_F64 or NFX_F32");
     NFX_REQUIRE(nt <= 65535, "edgeflux: at most 65535 time steps per call");
@@ -396,10 +436,11 @@ void edgeflux_assemble_panel(const void* u, const void* v, int dtype, const doub
     if (nt == 0) return;
     const double scale = 6371000.0 / 1.e6;  // field.py:12,226
     const int has_fill = !(fill != fill);
-    const uintptr_t addr_bits = ((uintptr_t)u) | ((uintptr_t)v) | ((uintptr_t)eflux);
+    const uintptr_t addr_bits = ((uintptr_t)u) | ((uintptr_t)v) | ((uintptr_t)eflux) | ((uintptr_t)e3u) | ((uintptr_t)e3v) |
+                                (uintptr_t)(e3_tstride * (dtype == NFX_F64 ? 8 : 4));
     const bool aligned16 = (addr_bits & 15) == 0;
     const bool aligned32 = (addr_bits & 31) == 0 && opt.variant != NFX_K2_LDG128;
-    const bool want_tma = (opt.variant == NFX_K2_TMA) && ld == ncols;
+    const bool want_tma = (opt.variant == NFX_K2_TMA) && ld == ncols && !e3u;
     if (want_tma && aligned16 && dtype == NFX_F64 && ncols % 2 == 0) {
         const int cfg = opt.unroll;   // tile configuration selector for the sweep (0 = default)
         const double* pu = (const double*)u;
@@ -429,25 +470,25 @@ void edgeflux_assemble_panel(const void* u, const void* v, int dtype, const doub
         const double* pv = (const double*)v;
         if (aligned32 && ld % 4 == 0 && (ncols % 4 == 0 || ld >= (ncols + 3) / 4 * 4))
             dispatch_ldg<double, 4>(pu, pv, thickness, arc1, arc2, eflux, nt, nz, ncols, ld, scale, sverdrup, fill,
-                                    has_fill, keep_l2, opt, s);
+                                    has_fill, keep_l2, e3, opt, s);
         else if (aligned16 && ld % 2 == 0 && (ncols % 2 == 0 || ld >= (ncols + 1) / 2 * 2))
             dispatch_ldg<double, 2>(pu, pv, thickness, arc1, arc2, eflux, nt, nz, ncols, ld, scale, sverdrup, fill,
-                                    has_fill, keep_l2, opt, s);
+                                    has_fill, keep_l2, e3, opt, s);
         else
             dispatch_ldg<double, 1>(pu, pv, thickness, arc1, arc2, eflux, nt, nz, ncols, ld, scale, sverdrup, fill,
-                                    has_fill, keep_l2, opt, s);
+                                    has_fill, keep_l2, e3, opt, s);
     } else {
         const float* pu = (const float*)u;
         const float* pv = (const float*)v;
         if (aligned32 && ld % 8 == 0 && (ncols % 8 == 0 || ld >= (ncols + 7) / 8 * 8))
             dispatch_ldg<float, 8>(pu, pv, thickness, arc1, arc2, eflux, nt, nz, ncols, ld, scale, sverdrup,
-                                   (float)fill, has_fill, keep_l2, opt, s);
+                                   (float)fill, has_fill, keep_l2, e3, opt, s);
         else if (aligned16 && ld % 4 == 0 && (ncols % 4 == 0 || ld >= (ncols + 3) / 4 * 4))
             dispatch_ldg<float, 4>(pu, pv, thickness, arc1, arc2, eflux, nt, nz, ncols, ld, scale, sverdrup,
-                                   (float)fill, has_fill, keep_l2, opt, s);
+                                   (float)fill, has_fill, keep_l2, e3, opt, s);
         else
             dispatch_ldg<float, 1>(pu, pv, thickness, arc1, arc2, eflux, nt, nz, ncols, ld, scale, sverdrup,
-                                   (float)fill, has_fill, keep_l2, opt, s);
+                                   (float)fill, has_fill, keep_l2, e3, opt, s);
     }
     count_launch();
     NFX_CUDA(cudaGetLastError());
@@ -456,7 +497,8 @@ void edgeflux_assemble_panel(const void* u, const void* v, int dtype, const doub
 void edgeflux_assemble(const void* u, const void* v, int dtype, const double* thickness, const double* arc1,
                        const double* arc2, int nt, int nz, int64_t ncell, int sverdrup, double fill, double* eflux,
                        const K2Options& opt, cudaStream_t s) {
-    edgeflux_assemble_panel(u, v, dtype, thickness, arc1, arc2, nt, nz, ncell, ncell, sverdrup, fill, eflux, 0, opt, s);
+    edgeflux_assemble_panel(u, v, dtype, thickness, arc1, arc2, nt, nz, ncell, ncell, sverdrup, fill, eflux, 0, opt, s,
+                            nullptr, nullptr, 0);
 }
 
 void edgeflux_to_cell_by_cell(const double* eflux, int nt, int ny, int nx, double* iv, cudaStream_t s) {

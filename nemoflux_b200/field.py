@@ -113,18 +113,36 @@ class Field(object):
         self.arcLengths[:] = geo.cellArcLengths(self.gr.getPoints())
 
     def _slab(self, nc, fieldName, t0, n):
-        """(n, nz, ny, nx) block of time steps with missing values as NaN (xarray semantics, field.py:149-157)"""
+        """(n, nz, ny, nx) block of time steps AS STORED: the missing-value marker (_FillValue, 1e20 in NEMO and
+        datagen.py:191) is not decoded on the host -- K2 maps it (and NaN) to 0, which is what xarray's decoding
+        followed by fillna(0.0) does in the reference (field.py:149-157)"""
         var = nc[fieldName]
         try:
             if len(var.shape) == 4:
-                a = var[t0:t0 + n]
+                a = var.raw(slice(t0, t0 + n))
             elif len(var.shape) == 3:
-                a = var[...][None]
+                a = var.raw()[None]
             else:
-                a = var[...][None, None]
+                a = var.raw()[None, None]
         except Exception:
             raise RuntimeError(f'ERROR: could not read {fieldName} field')
         return numpy.ascontiguousarray(a)
+
+    def _uv_slabs(self, t0, n):
+        """u, v blocks and the one missing-value marker K2 is given; if vo uses another marker than uo it is
+        rewritten to NaN on the host (NEMO uses 1e20 for both)"""
+        u = self._slab(self.ncU, 'uo', t0, n)
+        v = self._slab(self.ncV, 'vo', t0, n)
+        fu, fv = self._fill(self.ncU, 'uo'), self._fill(self.ncV, 'vo')
+        if fv == fv and fv != fu:
+            v = numpy.where(v == v.dtype.type(fv), numpy.nan, v)
+        return u, v, fu
+
+    def _fill(self, nc, fieldName):
+        fv = nc[fieldName].fill_value()
+        if nc[fieldName].dtype.itemsize == 4 and fv == fv:
+            fv = float(numpy.float32(fv))          # compare in the storage precision
+        return fv
 
     def readField(self, nc, fieldName):
         """vertically integrated field of the current time index, (ny, nx) host array (field.py:145-163);
@@ -132,7 +150,7 @@ class Field(object):
         import torch
         a = torch.from_numpy(self._slab(nc, fieldName, self.timeIndex, 1)).to(self.device)
         ones = torch.ones(self.ny * self.nx, dtype=torch.float64, device=self.device)
-        ef = nemoflux_gpu.edgeFluxAssemble(a, a, self._d_thickness, ones, ones)
+        ef = nemoflux_gpu.edgeFluxAssemble(a, a, self._d_thickness, ones, ones, fill=self._fill(nc, fieldName))
         return ef[0, :self.ny * self.nx].reshape(self.ny, self.nx).cpu().numpy()
 
     def getUV(self):
@@ -142,9 +160,10 @@ class Field(object):
     def update(self):
         """edge fluxes and transect fluxes of self.timeIndex (field.py:112-120): K2 + K3 on the device"""
         import torch
-        u = torch.from_numpy(self._slab(self.ncU, 'uo', self.timeIndex, 1)).to(self.device)
-        v = torch.from_numpy(self._slab(self.ncV, 'vo', self.timeIndex, 1)).to(self.device)
-        eflux = nemoflux_gpu.edgeFluxAssemble(u, v, self._d_thickness, self._d_arc1, self._d_arc2, sverdrup=self.sverdrup)
+        uh, vh, fill = self._uv_slabs(self.timeIndex, 1)
+        u, v = torch.from_numpy(uh).to(self.device), torch.from_numpy(vh).to(self.device)
+        eflux = nemoflux_gpu.edgeFluxAssemble(u, v, self._d_thickness, self._d_arc1, self._d_arc2, sverdrup=self.sverdrup,
+                                              fill=fill)
         self.fluxes = self.pli.integrate(eflux).cpu().numpy()[0]
         ncell = self.ny * self.nx
         self.integratedVelocity[:] = nemoflux_gpu.edgeFluxToCellByCell(eflux, self.ny, self.nx)[0].cpu().numpy()
@@ -184,10 +203,9 @@ class Field(object):
         n = chunk_steps if chunk_steps > 0 else max(1, min(self.nt, (1 << 30) // max(step_bytes, 1)))
         for t0 in range(0, self.nt, n):
             m = min(n, self.nt - t0)
-            u = self._slab(self.ncU, 'uo', t0, m)
-            v = self._slab(self.ncV, 'vo', t0, m)
+            u, v, fill = self._uv_slabs(t0, m)
             out[t0:t0 + m] = self.pli.fluxSeries(u, v, self.thickness, self.arcLengths[:, 1].copy(),
-                                                 self.arcLengths[:, 2].copy(), sverdrup=self.sverdrup)
+                                                 self.arcLengths[:, 2].copy(), sverdrup=self.sverdrup, fill=fill)
         return out
 
     def close(self):

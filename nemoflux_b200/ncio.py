@@ -33,7 +33,15 @@ class Variable(object):
         return a
 
     def raw(self, idx=Ellipsis):
+        """values as stored (native byte order), missing values NOT decoded: pair with fill_value()"""
         return self._native(numpy.array(self._data[idx]))
+
+    def fill_value(self):
+        """the value that marks missing data (_FillValue / missing_value), NaN when there is none"""
+        for key in ('_FillValue', 'missing_value'):
+            if key in self.attrs:
+                return float(numpy.asarray(self.attrs[key]).reshape(-1)[0])
+        return float('nan')
 
     def __getitem__(self, idx):
         """values with missing data decoded to NaN (floating point variables only)"""

@@ -237,7 +237,7 @@ class PolylineIntegral(object):
         return n.value, pc.value
 
     def fluxSeries(self, u, v, thickness, arc1, arc2, sverdrup=False, fill=float('nan'), order='map', eflux=None,
-                   out=None, chunk_steps=0, batch_range=None):
+                   out=None, chunk_steps=0, batch_range=None, e3u=None, e3v=None):
         """flux time series of every transect: (nt, M).
 
         u, v: (nt, nz, ny, nx) [or (nz, ny, nx)] float64/float32, either cuda tensors (device path: K2+K3 on
@@ -246,15 +246,20 @@ class PolylineIntegral(object):
         on the same side as u, v.  Needs Grid.setCGridShape before computeWeights.
 
         batch_range=(b0, b1) (device tensors only): run only the batches b = t*npanels + q in [b0, b1) and return
-        PARTIAL sums -- the building block of the balanced multi-GPU sharding in nemoflux_b200.dist."""
+        PARTIAL sums -- the building block of the balanced multi-GPU sharding in nemoflux_b200.dist.
+
+        e3u, e3v (device tensors only): per-column vertical scale factors, (1 or nt, nz, cells) with the dtype and
+        plane layout of uo/vo; they replace the 1-D thickness (two-launch path)."""
         torch = _torch()
         if isinstance(u, torch.Tensor) and u.is_cuda:
-            return self._flux_series_device(u, v, thickness, arc1, arc2, sverdrup, fill, order, eflux, out, batch_range)
-        if batch_range is not None:
-            raise ValueError('batch_range needs CUDA tensors')
+            return self._flux_series_device(u, v, thickness, arc1, arc2, sverdrup, fill, order, eflux, out, batch_range,
+                                            e3u, e3v)
+        if batch_range is not None or e3u is not None or e3v is not None:
+            raise ValueError('batch_range / e3u / e3v need CUDA tensors')
         return self._flux_series_host(u, v, thickness, arc1, arc2, sverdrup, fill, order, chunk_steps)
 
-    def _flux_series_device(self, u, v, thickness, arc1, arc2, sverdrup, fill, order, eflux, out, batch_range=None):
+    def _flux_series_device(self, u, v, thickness, arc1, arc2, sverdrup, fill, order, eflux, out, batch_range=None,
+                            e3u=None, e3v=None):
         torch = _torch()
         ncells = self._grid.getNumberOfCells() if self._grid is not None else -1
         if u.dim() == 3 and u.shape[2] != ncells and u.shape[1] * u.shape[2] == ncells:
@@ -267,11 +272,27 @@ class PolylineIntegral(object):
         nt, nz, ncell, ld = _plane_layout(u, 'uo')
         if ncell != ncells:
             raise ValueError(f'uo has {ncell} cells per level, the grid has {ncells}')
-        for name, t, n in (('thickness', thickness, nz), ('arc1', arc1, ncell), ('arc2', arc2, ncell)):
+        use_e3 = e3u is not None or e3v is not None
+        checks = [('arc1', arc1, ncell), ('arc2', arc2, ncell)] + ([] if use_e3 else [('thickness', thickness, nz)])
+        for name, t, n in checks:
             _require_cuda(t, torch.float64, name)
             if t.numel() != n:
                 raise ValueError(f'{name} must hold {n} values, got {t.numel()}')
         m = self.getNumberOfTransects()
+        if use_e3:
+            if batch_range is not None:
+                raise ValueError('batch_range and e3u/e3v cannot be combined')
+            e3_nt = _check_e3(e3u, e3v, u, nt, nz, ncell, ld)
+            if eflux is not None:
+                _require_cuda(eflux, torch.float64, 'eflux')
+            if out is None:
+                out = torch.empty((nt, m), dtype=torch.float64, device=u.device)
+            with torch.cuda.device(u.device):
+                _lib.call('nfx_flux_series_e3', ctypes.byref(self._h), _t_ptr(u), _t_ptr(v), _t_ptr(e3u), _t_ptr(e3v),
+                          _dtype_code(str(u.dtype)), e3_nt, _t_ptr(arc1), _t_ptr(arc2), nt, nz, ld, int(bool(sverdrup)),
+                          float(fill), _ORDERS[order], _t_ptr(eflux) if eflux is not None else None, _t_ptr(out),
+                          _stream_ptr())
+            return out
         if eflux is not None:       # the caller wants the (nt, 2*ncell) edge fluxes too: classic K2 -> HBM -> K3
             _require_cuda(eflux, torch.float64, 'eflux')
             if eflux.numel() != nt * 2 * ncell:
@@ -348,6 +369,22 @@ def _plane_layout(t, name, ncell_expected=None):
     raise ValueError(f"{name} shape does not match (t, z, y, x) or (t, z, ncell)")
 
 
+def _check_e3(e3u, e3v, u, nt, nz, ncell, ld):
+    """e3u/e3v: same dtype and plane layout as u, 1 or nt time steps; returns e3_nt"""
+    torch = _torch()
+    if e3u is None or e3v is None:
+        raise ValueError('e3u and e3v go together')
+    for name, t in (('e3u', e3u), ('e3v', e3v)):
+        if not isinstance(t, torch.Tensor) or not t.is_cuda or t.dtype != u.dtype:
+            raise TypeError(f'{name} must be a CUDA tensor with the dtype of uo/vo')
+        ent, enz, encell, eld = _plane_layout(t, name)
+        if (enz, encell) != (nz, ncell) or ent not in (1, nt) or (eld != ld and enz > 1):
+            raise ValueError(f'{name} must be (1 or nt, nz, cells) with the plane layout of uo/vo')
+    if e3u.shape[0] != e3v.shape[0]:
+        raise ValueError('e3u and e3v must hold the same number of time steps')
+    return int(e3u.shape[0])
+
+
 def _require_cuda(t, dtype, name):
     torch = _torch()
     if not isinstance(t, torch.Tensor) or not t.is_cuda:
@@ -359,7 +396,7 @@ def _require_cuda(t, dtype, name):
 
 
 # -- K2 as a free function (Field.readField + Field.computeIntegratedFlux for many time steps) ------------
-def edgeFluxAssemble(u, v, thickness, arc1, arc2, sverdrup=False, fill=float('nan'), out=None):
+def edgeFluxAssemble(u, v, thickness, arc1, arc2, sverdrup=False, fill=float('nan'), out=None, e3u=None, e3v=None):
     """u, v cuda (nt, nz, ny, nx) or (nt, nz, ncell) (level planes may be padded in memory, see _plane_layout);
     returns eflux cuda (nt, 2*ncell): [eU | eV] signed"""
     torch = _torch()
@@ -369,12 +406,21 @@ def edgeFluxAssemble(u, v, thickness, arc1, arc2, sverdrup=False, fill=float('na
     if u.dtype != v.dtype or u.shape != v.shape or u.stride() != v.stride():
         raise ValueError('u and v must have the same dtype, shape and strides')
     nt, nz, ncell, ld = _plane_layout(u, 'u')
-    for name, t, n in (('thickness', thickness, nz), ('arc1', arc1, ncell), ('arc2', arc2, ncell)):
+    use_e3 = e3u is not None or e3v is not None
+    checks = [('arc1', arc1, ncell), ('arc2', arc2, ncell)] + ([] if use_e3 else [('thickness', thickness, nz)])
+    for name, t, n in checks:
         _require_cuda(t, torch.float64, name)
         if t.numel() != n:
             raise ValueError(f'{name} must hold {n} values, got {t.numel()}')
     if out is None:
         out = torch.empty((nt, 2 * ncell), dtype=torch.float64, device=u.device)
+    if use_e3:      # per-column vertical scale factors replace the 1-D thickness (which is ignored)
+        e3_nt = _check_e3(e3u, e3v, u, nt, nz, ncell, ld)
+        with torch.cuda.device(u.device):
+            _lib.call('nfx_edgeflux_assemble_e3', _t_ptr(u), _t_ptr(v), _t_ptr(e3u), _t_ptr(e3v),
+                      _dtype_code(str(u.dtype)), e3_nt, _t_ptr(arc1), _t_ptr(arc2), nt, nz, ncell, ld,
+                      int(bool(sverdrup)), float(fill), _t_ptr(out), _stream_ptr())
+        return out
     with torch.cuda.device(u.device):
         _lib.call('nfx_edgeflux_assemble_ld', _t_ptr(u), _t_ptr(v), _dtype_code(str(u.dtype)), _t_ptr(thickness),
                   _t_ptr(arc1), _t_ptr(arc2), nt, nz, ncell, ld, int(bool(sverdrup)), float(fill), _t_ptr(out),

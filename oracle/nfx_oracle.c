@@ -467,6 +467,37 @@ void orc_edgeflux_step(const double* u, const double* v, const double* thickness
     }
 }
 
+/* per-column vertical scale factors e3u/e3v (nz,ncell) instead of thickness[k]; not in the
+ * reference (field.py:51 has a 1-D thickness only) -- this defines the extension: missing e3 counts as 0 too */
+void orc_edgeflux_step_e3(const double* u, const double* v, const double* e3u, const double* e3v, const double* arc1,
+                          const double* arc2, int nz, int ny, int nx, int sverdrup, double fill, double* eU, double* eV) {
+    const int64_t ncell = (int64_t)ny * nx;
+    const double scale = 6371000.0 / 1.e6;
+    const int has_fill = !(fill != fill);
+#pragma omp parallel for schedule(static)
+    for (int64_t c = 0; c < ncell; ++c) {
+        double su = 0.0, sv = 0.0;
+        for (int k = 0; k < nz; ++k) {
+            double a = u[(int64_t)k * ncell + c], b = v[(int64_t)k * ncell + c];
+            double ea = e3u[(int64_t)k * ncell + c], eb = e3v[(int64_t)k * ncell + c];
+            if (a != a || (has_fill && a == fill)) a = 0.0;
+            if (b != b || (has_fill && b == fill)) b = 0.0;
+            if (ea != ea || (has_fill && ea == fill)) ea = 0.0;
+            if (eb != eb || (has_fill && eb == fill)) eb = 0.0;
+            su = su + ea * a;
+            sv = sv + eb * b;
+        }
+        double fu = su * arc1[c];
+        double fv = (-sv) * arc2[c];
+        if (sverdrup) {
+            fu = fu * scale;
+            fv = fv * scale;
+        }
+        eU[c] = fu;
+        eV[c] = fv;
+    }
+}
+
 /* float32-storage variant (real NEMO files store uo/vo as float32; accumulation stays fp64) */
 void orc_edgeflux_step_f32(const float* u, const float* v, const double* thickness, const double* arc1,
                            const double* arc2, int nz, int ny, int nx, int sverdrup, float fill, double* eU,

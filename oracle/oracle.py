@@ -55,6 +55,8 @@ def lib():
         fp = ctypes.POINTER(ctypes.c_float)
         L.orc_edgeflux_step_f32.argtypes = [fp, fp, dp, dp, dp, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                             ctypes.c_int, ctypes.c_float, dp, dp, dp]
+        L.orc_edgeflux_step_e3.argtypes = [dp, dp, dp, dp, dp, dp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                           ctypes.c_double, dp, dp]
         L.orc_flux_index.restype = ctypes.c_int64
         L.orc_flux_index.argtypes = [ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int]
         L.orc_num_threads.restype = ctypes.c_int
@@ -260,6 +262,16 @@ def edgeflux_step_c(u_zyx, v_zyx, thickness, arc1, arc2, sverdrup=False, fill=fl
         L.orc_edgeflux_step(_dp(u), _dp(v), _dp(th), _dp(a1), _dp(a2), nz, ny, nx, int(sverdrup), fill, _dp(eU),
                             _dp(eV), _dp(iV) if want_iV else None)
     return iV, eU, eV
+
+
+def edgeflux_step_c_e3(u_zyx, v_zyx, e3u_zyx, e3v_zyx, arc1, arc2, sverdrup=False, fill=float('nan')):
+    """per-column scale factors: U = sum_k e3u[k,c]*u[k,c], sequential k, fp64"""
+    nz, ny, nx = u_zyx.shape
+    ncell = ny * nx
+    eU, eV = numpy.empty(ncell), numpy.empty(ncell)
+    arrs = [numpy.ascontiguousarray(a, numpy.float64) for a in (u_zyx, v_zyx, e3u_zyx, e3v_zyx, arc1, arc2)]
+    lib().orc_edgeflux_step_e3(*[_dp(a) for a in arrs], nz, ny, nx, int(sverdrup), fill, _dp(eU), _dp(eV))
+    return eU, eV
 
 
 # ------------------------------------------------------------------------------------------------

@@ -476,3 +476,47 @@ def test_batch_range_partials_add_up(gpu, oracle):
     finally:
         _lib.set_option(_lib.NFX_OPT_RING_SLOT_MB, 8)
         _lib.set_option(_lib.NFX_OPT_FAST_SERIES, 1)
+
+
+@pytest.mark.parametrize('dtype', [numpy.float64, numpy.float32])
+@pytest.mark.parametrize('e3_nt', [1, 3])
+def test_k2_per_column_scale_factors(gpu, oracle, dtype, e3_nt):
+    """e3u/e3v (per column and level, optionally per time step) instead of the 1-D thickness:
+    bit-exact against the oracle's definition, and identical to the thickness path when e3[t,k,c] = dz[k]"""
+    import torch
+    nt, nz, ny, nx = 3, 11, 14, 22
+    rng = numpy.random.default_rng(21)
+    u, v = _rand_uv(rng, nt, nz, ny, nx, dtype)
+    e3u = rng.uniform(0.5, 30., (e3_nt, nz, ny, nx)).astype(dtype)
+    e3v = rng.uniform(0.5, 30., (e3_nt, nz, ny, nx)).astype(dtype)
+    e3u[:, :, 3, 4] = numpy.nan                       # a missing scale factor counts as 0
+    a1 = rng.uniform(1e-3, 2e-2, ny * nx)
+    a2 = rng.uniform(1e-3, 2e-2, ny * nx)
+    d = 'cuda'
+    args = [torch.from_numpy(x).to(d) for x in (u, v)]
+    a1d, a2d = torch.from_numpy(a1).to(d), torch.from_numpy(a2).to(d)
+    ef = gpu.edgeFluxAssemble(args[0], args[1], None, a1d, a2d, sverdrup=True, e3u=torch.from_numpy(e3u).to(d),
+                              e3v=torch.from_numpy(e3v).to(d)).cpu().numpy()
+    for t in range(nt):
+        te = 0 if e3_nt == 1 else t
+        eU, eV = oracle.edgeflux_step_c_e3(u[t].astype(numpy.float64), v[t].astype(numpy.float64),
+                                           e3u[te].astype(numpy.float64), e3v[te].astype(numpy.float64), a1, a2, True)
+        assert_bitwise(ef[t, :ny * nx], eU, 'eU (e3)')
+        assert_bitwise(ef[t, ny * nx:], eV, 'eV (e3)')
+    # e3 = dz everywhere reproduces the reference's 1-D thickness path bit for bit
+    th = rng.uniform(0.5, 20., nz).astype(dtype).astype(numpy.float64)
+    e3c = numpy.broadcast_to(th.astype(dtype)[None, :, None, None], (1, nz, ny, nx)).copy()
+    ef_e3 = gpu.edgeFluxAssemble(args[0], args[1], None, a1d, a2d, e3u=torch.from_numpy(e3c).to(d),
+                                 e3v=torch.from_numpy(e3c).to(d)).cpu().numpy()
+    ef_th = gpu.edgeFluxAssemble(args[0], args[1], torch.from_numpy(th).to(d), a1d, a2d).cpu().numpy()
+    assert_bitwise(ef_e3, ef_th, 'e3 = dz')
+    # through the series call
+    g = oracle.DataGen(nx=nx, ny=ny)
+    _, p = _build(gpu, g.points(), ny, nx)
+    p.computeWeights([tr([(-150, -50), (-20, 35), (60, -40)])])
+    s_e3 = p.fluxSeries(args[0], args[1], None, a1d, a2d, e3u=torch.from_numpy(e3c).to(d), e3v=torch.from_numpy(e3c).to(d))
+    ef2 = torch.empty((nt, 2 * ny * nx), dtype=torch.float64, device=d)
+    s_th = p.fluxSeries(args[0], args[1], torch.from_numpy(th).to(d), a1d, a2d, eflux=ef2)
+    assert torch.equal(s_e3, s_th)
+    with pytest.raises(ValueError):
+        gpu.edgeFluxAssemble(args[0], args[1], None, a1d, a2d, e3u=torch.from_numpy(e3c).to(d))

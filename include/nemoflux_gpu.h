@@ -56,6 +56,7 @@ extern "C" {
 
 typedef struct nfx_grid nfx_grid;
 typedef struct nfx_pli nfx_pli;
+typedef struct nfx_vinterp nfx_vinterp;
 
 const char* nfx_last_error(void);
 int nfx_version(void);
@@ -104,6 +105,21 @@ int nfx_pli_get_integrals(nfx_pli** self, const double* data, int placement, int
 /* same with data already on the device: data device (nt, ncells, 4), results device (nt, ntransects) */
 int nfx_pli_get_integrals_device(nfx_pli** self, const double* data, int nt, int order, double* results,
                                  void* stream);
+
+/* ---- mint.VectorInterp  (field.py:90-95,119-120; the arrow glyphs of the viewer) ------------ */
+int nfx_vinterp_new(nfx_vinterp** self);
+int nfx_vinterp_del(nfx_vinterp** self);
+int nfx_vinterp_set_grid(nfx_vinterp** self, nfx_grid* grid);
+/* buildLocator(numCellsPerBucket=128, periodX=360.), field.py:92: shares the grid's bounding-box hierarchy */
+int nfx_vinterp_build_locator(nfx_vinterp** self, int num_cells_per_bucket, double period_x, int enable_folding);
+/* findPoints(points (npoints,3) host, tol2=1e-12), field.py:93: containing cell (lowest id) and parametric
+ * coordinates of every point; num_not_found may be NULL */
+int nfx_vinterp_find_points(nfx_vinterp** self, int64_t npoints, const double* xyz, double tol2, int64_t* num_not_found);
+int nfx_vinterp_get_cells(nfx_vinterp** self, int64_t* cell, double* xi);
+/* getFaceVectors(data (ncells,4) host, placement=0) -> vectors (npoints,3) host, field.py:94-95 */
+int nfx_vinterp_get_face_vectors(nfx_vinterp** self, const double* data, int placement, double* vectors);
+/* the same with data (ncells,4) and vectors (npoints,3) on the device */
+int nfx_vinterp_get_face_vectors_device(nfx_vinterp** self, const double* data, double* vectors, void* stream);
 
 /* ---- Field.readField + Field.computeIntegratedFlux  (field.py:145-163, 183-234)  = kernel K2 ----- */
 /* u, v: device (nt, nz, ncell) of dtype; thickness device (nz) = deptht_bounds[:,1]-[:,0]

@@ -47,6 +47,14 @@ SIGNATURES = {
     'nfx_pli_get_integral': [P(c_vp), c_vp, c_int, P(c_dbl)],
     'nfx_pli_get_integrals': [P(c_vp), c_vp, c_int, c_int, c_vp],
     'nfx_pli_get_integrals_device': [P(c_vp), c_vp, c_int, c_int, c_vp, c_vp],
+    'nfx_vinterp_new': [P(c_vp)],
+    'nfx_vinterp_del': [P(c_vp)],
+    'nfx_vinterp_set_grid': [P(c_vp), c_vp],
+    'nfx_vinterp_build_locator': [P(c_vp), c_int, c_dbl, c_int],
+    'nfx_vinterp_find_points': [P(c_vp), c_i64, c_vp, c_dbl, P(c_i64)],
+    'nfx_vinterp_get_cells': [P(c_vp), c_vp, c_vp],
+    'nfx_vinterp_get_face_vectors': [P(c_vp), c_vp, c_int, c_vp],
+    'nfx_vinterp_get_face_vectors_device': [P(c_vp), c_vp, c_vp, c_vp],
     'nfx_edgeflux_assemble': [c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_int, c_i64, c_int, c_dbl, c_vp, c_vp],
     'nfx_edgeflux_assemble_ld': [c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_int, c_i64, c_i64, c_int, c_dbl, c_vp,
                                  c_vp],

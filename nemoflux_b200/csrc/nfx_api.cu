@@ -131,6 +131,9 @@ struct nfx_grid {
 struct nfx_pli {
     PliDev d;
 };
+struct nfx_vinterp {
+    VInterpDev d;
+};
 
 template <typename T>
 static void d2h(T* dst, const T* src, size_t n) {
@@ -393,6 +396,109 @@ int nfx_pli_get_integral(nfx_pli** self, const double* data, int placement, doub
         return NFX_E_INVALID;
     }
     return nfx_pli_get_integrals(self, data, placement, NFX_ORDER_MAP, result);
+}
+
+// ---- mint.VectorInterp (field.py:90-95,119-120) ----------------------------------------------------------
+int nfx_vinterp_new(nfx_vinterp** self) {
+    return guarded([&] {
+        NFX_REQUIRE(self, "NULL handle");
+        int dev;
+        require_gpu(&dev);
+        *self = new nfx_vinterp();
+        (*self)->d.device = dev;
+    });
+}
+
+int nfx_vinterp_del(nfx_vinterp** self) {
+    return guarded([&] {
+        NFX_REQUIRE(self, "NULL handle");
+        if (*self) {
+            DeviceGuard g((*self)->d.device);
+            delete *self;
+        }
+        *self = nullptr;
+    });
+}
+
+int nfx_vinterp_set_grid(nfx_vinterp** self, nfx_grid* grid) {
+    return guarded([&] {
+        NFX_REQUIRE(self && *self && grid, "NULL handle");
+        (*self)->d.grid = &grid->d;
+        (*self)->d.device = grid->d.device;
+    });
+}
+
+int nfx_vinterp_build_locator(nfx_vinterp** self, int num_cells_per_bucket, double period_x, int enable_folding) {
+    return guarded([&] {
+        NFX_REQUIRE(self && *self, "NULL handle");
+        VInterpDev& vi = (*self)->d;
+        NFX_REQUIRE(vi.grid, "buildLocator: setGrid was not called");
+        NFX_REQUIRE(num_cells_per_bucket > 0 && period_x >= 0.0 && enable_folding == 0, "buildLocator: bad arguments");
+        DeviceGuard g(vi.grid->device);
+        grid_build_locator(*vi.grid, nullptr);
+        NFX_CUDA(cudaStreamSynchronize(nullptr));
+        vi.period_x = period_x;
+    });
+}
+
+int nfx_vinterp_find_points(nfx_vinterp** self, int64_t npoints, const double* xyz, double tol2, int64_t* num_not_found) {
+    return guarded([&] {
+        NFX_REQUIRE(self && *self, "NULL handle");
+        VInterpDev& vi = (*self)->d;
+        NFX_REQUIRE(vi.grid, "findPoints: setGrid was not called");
+        DeviceGuard g(vi.grid->device);
+        vinterp_find_points(vi, npoints, xyz, tol2, nullptr);
+        if (num_not_found) {
+            std::vector<int32_t> h((size_t)std::max<int64_t>(npoints, 1));
+            if (npoints) NFX_CUDA(cudaMemcpy(h.data(), vi.cell.p, sizeof(int32_t) * npoints, cudaMemcpyDeviceToHost));
+            int64_t bad = 0;
+            for (int64_t i = 0; i < npoints; ++i) bad += h[i] < 0;
+            *num_not_found = bad;
+        }
+    });
+}
+
+int nfx_vinterp_get_cells(nfx_vinterp** self, int64_t* cell, double* xi) {
+    return guarded([&] {
+        NFX_REQUIRE(self && *self, "NULL handle");
+        VInterpDev& vi = (*self)->d;
+        NFX_REQUIRE(vi.grid, "setGrid was not called");
+        DeviceGuard g(vi.grid->device);
+        if (vi.npts == 0) return;
+        if (cell) {
+            std::vector<int32_t> h((size_t)vi.npts);
+            NFX_CUDA(cudaMemcpy(h.data(), vi.cell.p, sizeof(int32_t) * vi.npts, cudaMemcpyDeviceToHost));
+            for (int64_t i = 0; i < vi.npts; ++i) cell[i] = h[i];
+        }
+        if (xi) NFX_CUDA(cudaMemcpy(xi, vi.xi.p, sizeof(double) * 2 * vi.npts, cudaMemcpyDeviceToHost));
+    });
+}
+
+int nfx_vinterp_get_face_vectors(nfx_vinterp** self, const double* data, int placement, double* vectors) {
+    return guarded([&] {
+        NFX_REQUIRE(self && *self && data && vectors, "NULL pointer");
+        NFX_REQUIRE(placement == NFX_CELL_BY_CELL_DATA, "only CELL_BY_CELL_DATA placement is supported");
+        VInterpDev& vi = (*self)->d;
+        NFX_REQUIRE(vi.grid, "getFaceVectors: setGrid was not called");
+        DeviceGuard g(vi.grid->device);
+        if (vi.npts == 0) return;
+        const size_t n = (size_t)vi.grid->ncell * 4;
+        vi.scratch_data.ensure(n);
+        vi.scratch_vec.ensure((size_t)vi.npts * 3);
+        NFX_CUDA(cudaMemcpy(vi.scratch_data.p, data, sizeof(double) * n, cudaMemcpyHostToDevice));
+        vinterp_face_vectors(vi, vi.scratch_data.p, vi.scratch_vec.p, nullptr);
+        NFX_CUDA(cudaMemcpy(vectors, vi.scratch_vec.p, sizeof(double) * 3 * vi.npts, cudaMemcpyDeviceToHost));
+    });
+}
+
+int nfx_vinterp_get_face_vectors_device(nfx_vinterp** self, const double* data, double* vectors, void* stream) {
+    return guarded([&] {
+        NFX_REQUIRE(self && *self && data && vectors, "NULL pointer");
+        VInterpDev& vi = (*self)->d;
+        NFX_REQUIRE(vi.grid, "getFaceVectors: setGrid was not called");
+        DeviceGuard g(vi.grid->device);
+        vinterp_face_vectors(vi, data, vectors, (cudaStream_t)stream);
+    });
 }
 
 // ---- K2 / K3 on device buffers -------------------------------------------------------------------------

@@ -135,6 +135,19 @@ struct PliDev {
     cudaEvent_t ev_ready[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
 };
 
+// mint.VectorInterp (nfx_k4_vinterp.cu)
+struct VInterpDev {
+    GridDev* grid = nullptr;
+    int device = 0;
+    double period_x = 360.0;
+    int64_t npts = 0;
+    DevBuf<int32_t> cell;   // containing cell of every point, -1 = not found
+    DevBuf<double> xi;      // (npts, 2) parametric coordinates
+    DevBuf<double> scratch_data, scratch_vec;
+};
+void vinterp_find_points(VInterpDev& vi, int64_t npts, const double* xyz_host, double tol2, cudaStream_t s);
+void vinterp_face_vectors(VInterpDev& vi, const double* data_dev, double* vec_dev, cudaStream_t s);
+
 // K1 (nfx_k1_intersect.cu)
 void grid_upload_points(GridDev& g, int64_t ncells, const double* points_host);
 void grid_build_locator(GridDev& g, cudaStream_t s);

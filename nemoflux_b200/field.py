@@ -9,8 +9,8 @@ Same constructor, attributes and methods as the reference class (field.py:15-234
 What differs: ONE locator is built per grid and shared by all transects (the reference builds one per
 transect, field.py:44-49); the vertical integration, edge-flux assembly and the transect integrals run in
 libnemoflux_gpu.so (K2, K3); ``fluxSeries()`` is new and evaluates every time step and transect in a few
-launches (the loop of fluxplot.py:51-59).  The VectorInterp arrow glyphs (field.py:71-95) are viz-only
-and not computed.
+launches (the loop of fluxplot.py:51-59).  ``vectorPoints`` / ``vectorValues`` (the arrow glyphs, field.py:71-95)
+come from nemoflux_gpu.VectorInterp.
 """
 import re
 
@@ -84,7 +84,30 @@ class Field(object):
         self.maxAbsFlux = 0.
         self.fluxes = numpy.zeros(len(self.plis))
 
-        uVerticallyIntegrated, vVerticallyIntegrated = None, None
+        # sample points along the target lines where the viewer draws its arrows (field.py:71-87) and the
+        # vector interpolator that feeds them (field.py:90-95)
+        vectorPoints = []
+        self.uVectors = []
+        for lonlatpts in self.lonLatZPoints:
+            for i in range(len(lonlatpts) - 1):
+                begPoint, endPoint = lonlatpts[i], lonlatpts[i + 1]
+                u = endPoint - begPoint
+                distance = numpy.sqrt(u.dot(u))
+                if distance == 0.:
+                    continue
+                u = u / distance
+                nvpts = max(2, int(distance / self.dx))
+                vdx = distance / float(nvpts - 1)
+                for j in range(nvpts):
+                    vectorPoints.append(begPoint + u * j * vdx)
+                    self.uVectors.append(u)
+        self.vectorPoints = numpy.array(vectorPoints).reshape(-1, 3)
+        self.vinterp = nemoflux_gpu.VectorInterp()
+        self.vinterp.setGrid(self.gr.getMintGrid())
+        self.vinterp.buildLocator(numCellsPerBucket=128, periodX=360.)
+        self.vinterp.findPoints(self.vectorPoints, tol2=1.e-12)
+        self.vectorValues = numpy.zeros((self.vectorPoints.shape[0], 3))
+
         self.update()
         if verbose:
             print(f'max vertically integrated edge |flux|: {self.maxAbsFlux}')
@@ -171,6 +194,7 @@ class Field(object):
         self.edgeFluxesUArray[:] = ef[:ncell]
         self.edgeFluxesVArray[:] = ef[ncell:]
         self.maxAbsFlux = max(self.maxAbsFlux, nemoflux_gpu.edgeFluxAbsMax(eflux))
+        self.vectorValues[:] = self.vinterp.getFaceVectors(self.integratedVelocity, placement=0)   # field.py:119-120
 
     def computeIntegratedFlux(self, uVerticallyIntegrated, vVerticallyIntegrated):
         """field.py:183-234 for callers that hold their own vertically integrated (ny, nx) fields"""

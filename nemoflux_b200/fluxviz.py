@@ -53,6 +53,11 @@ class FluxViz(object):
         else:
             return
         self.field.update()
+        nvpts = self.field.vectorPoints.shape[0]
+        if nvpts:      # arrows are drawn normalised by the longest one (fluxviz.py:95-97)
+            maxVectorLength = numpy.sqrt((self.field.vectorValues ** 2).sum(axis=1)).max()
+            if maxVectorLength > 0:
+                self.field.vectorValues /= maxVectorLength
         print(f'time index now {self.field.timeIndex} max |flux|: {self.field.maxAbsFlux:10.3f} nt = {self.field.nt}')
 
     def title(self):

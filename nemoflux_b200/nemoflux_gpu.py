@@ -343,6 +343,63 @@ class PolylineIntegral(object):
         return out
 
 
+class VectorInterp(object):
+    """mint.VectorInterp (field.py:90-95,119-120): vectors of the edge-flux field at arbitrary points"""
+
+    def __init__(self):
+        self._h = ctypes.c_void_p()
+        _lib.call('nfx_vinterp_new', ctypes.byref(self._h))
+        self._grid = None
+        self._npts = 0
+
+    def __del__(self):
+        try:
+            if self._h:
+                _lib.load().nfx_vinterp_del(ctypes.byref(self._h))
+        except Exception:
+            pass
+
+    def setGrid(self, grid):
+        if not isinstance(grid, Grid):
+            raise TypeError('setGrid expects a nemoflux_gpu.Grid')
+        _lib.call('nfx_vinterp_set_grid', ctypes.byref(self._h), grid._h)
+        self._grid = grid
+
+    def buildLocator(self, numCellsPerBucket=128, periodX=360., enableFolding=False):
+        _lib.call('nfx_vinterp_build_locator', ctypes.byref(self._h), int(numCellsPerBucket), float(periodX),
+                  int(bool(enableFolding)))
+
+    def findPoints(self, points, tol2=1.e-12):
+        """points (n, 3) lon, lat, ignored; returns the number of points that are in no cell"""
+        pts = numpy.ascontiguousarray(points, numpy.float64)
+        if pts.ndim != 2 or pts.shape[1] != 3:
+            raise ValueError(f'points must have shape (npoints, 3), got {pts.shape}')
+        bad = ctypes.c_int64()
+        _lib.call('nfx_vinterp_find_points', ctypes.byref(self._h), pts.shape[0], _np_ptr(pts), float(tol2),
+                  ctypes.byref(bad))
+        self._npts = pts.shape[0]
+        return bad.value
+
+    def getCells(self):
+        """(cell ids (-1 = not found), parametric coordinates (n, 2)) of the points of the last findPoints"""
+        cell = numpy.zeros(self._npts, numpy.int64)
+        xi = numpy.zeros((self._npts, 2))
+        if self._npts:
+            _lib.call('nfx_vinterp_get_cells', ctypes.byref(self._h), _np_ptr(cell), _np_ptr(xi))
+        return cell, xi
+
+    def getFaceVectors(self, data, placement=CELL_BY_CELL_DATA):
+        """data (ncells, 4) host array of edge fluxes (S, E, N, W) -> (n, 3) vectors"""
+        d = numpy.ascontiguousarray(data, numpy.float64)
+        ncell = self._grid.getNumberOfCells() if self._grid else -1
+        if d.size != ncell * 4:
+            raise ValueError(f'data must hold ncells*4 = {ncell * 4} values, got {d.size}')
+        vec = numpy.zeros((self._npts, 3))
+        if self._npts:
+            _lib.call('nfx_vinterp_get_face_vectors', ctypes.byref(self._h), _np_ptr(d), int(placement), _np_ptr(vec))
+        return vec
+
+
 def _to_numpy(x):
     torch = _torch()
     if isinstance(x, torch.Tensor):

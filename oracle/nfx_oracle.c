@@ -550,6 +550,71 @@ int64_t orc_flux_index(int64_t cell, int edge, int ny, int nx) {
     }
 }
 
+/* ---------------------------------------------------------------------------------------------
+ * mint VectorInterp.findPoints + getFaceVectors restated (call sites field.py:90-95,119-120; viz only).
+ * findPoints: the containing cell of every point (lowest cell id among the cells whose 4 CCW edge tests pass
+ * with tolerance tol; images of the point shifted by 0, -periodX, +periodX in that order) and its
+ * parametric coordinates.  getFaceVectors(data (ncell,4), placement 0): with r_xi, r_eta the tangent vectors
+ * of the bilinear map and J = (r_xi x r_eta).z,
+ *     v = [ (d3 (1-xi) + d1 xi) r_xi  -  (d0 (1-eta) + d2 eta) r_eta ] / J
+ * Sign convention pinned by pictures/simple.png (psi = x: arrows point south) and pictures/singular.png
+ * (arrows point away from the singularity).
+ * ------------------------------------------------------------------------------------------- */
+int orc_vinterp_find_points(void* hgrid, const double* xyz, int64_t npts, double periodX, double tol, int64_t* cell,
+                            double* xi) {
+    orc_grid* g = (orc_grid*)hgrid;
+    if (!g) return 1;
+    const double shifts[3] = {0.0, -periodX, periodX};
+    const int nimg = periodX > 0.0 ? 3 : 1;
+    for (int64_t n = 0; n < npts; ++n) {
+        cell[n] = -1;
+        xi[2 * n] = xi[2 * n + 1] = 0.0;
+        for (int im = 0; im < nimg && cell[n] < 0; ++im) {
+            const double px = xyz[3 * n] + shifts[im], py = xyz[3 * n + 1];
+            for (int64_t c = 0; c < g->ncell; ++c) {
+                double vx[4], vy[4];
+                for (int v = 0; v < 4; ++v) {
+                    vx[v] = g->pts[(c * 4 + v) * 3 + 0];
+                    vy[v] = g->pts[(c * 4 + v) * 3 + 1];
+                }
+                if (contains_point(vx, vy, px, py, tol)) {
+                    cell[n] = c;
+                    param_coords(vx, vy, px, py, xi + 2 * n);
+                    break;
+                }
+            }
+        }
+    }
+    return 0;
+}
+
+void orc_vinterp_face_vectors(void* hgrid, const int64_t* cell, const double* xi, int64_t npts, const double* data,
+                              double* vec) {
+    orc_grid* g = (orc_grid*)hgrid;
+    for (int64_t n = 0; n < npts; ++n) {
+        vec[3 * n] = vec[3 * n + 1] = vec[3 * n + 2] = 0.0;
+        const int64_t c = cell[n];
+        if (c < 0) continue;
+        double vx[4], vy[4];
+        for (int v = 0; v < 4; ++v) {
+            vx[v] = g->pts[(c * 4 + v) * 3 + 0];
+            vy[v] = g->pts[(c * 4 + v) * 3 + 1];
+        }
+        const double s = xi[2 * n], t = xi[2 * n + 1];
+        const double s1 = 1.0 - s, t1 = 1.0 - t;
+        const double rxx = (vx[1] - vx[0]) * t1 + (vx[2] - vx[3]) * t;
+        const double rxy = (vy[1] - vy[0]) * t1 + (vy[2] - vy[3]) * t;
+        const double rex = (vx[3] - vx[0]) * s1 + (vx[2] - vx[1]) * s;
+        const double rey = (vy[3] - vy[0]) * s1 + (vy[2] - vy[1]) * s;
+        const double jac = rxx * rey - rxy * rex;
+        const double* d = data + 4 * c;
+        const double a = d[3] * s1 + d[1] * s;
+        const double b = d[0] * t1 + d[2] * t;
+        vec[3 * n + 0] = (a * rxx - b * rex) / jac;
+        vec[3 * n + 1] = (a * rxy - b * rey) / jac;
+    }
+}
+
 int orc_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

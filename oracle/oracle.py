@@ -57,6 +57,9 @@ def lib():
                                             ctypes.c_int, ctypes.c_float, dp, dp, dp]
         L.orc_edgeflux_step_e3.argtypes = [dp, dp, dp, dp, dp, dp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                            ctypes.c_double, dp, dp]
+        L.orc_vinterp_find_points.argtypes = [ctypes.c_void_p, dp, ctypes.c_int64, ctypes.c_double, ctypes.c_double,
+                                              ctypes.POINTER(ctypes.c_int64), dp]
+        L.orc_vinterp_face_vectors.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int64), dp, ctypes.c_int64, dp, dp]
         L.orc_flux_index.restype = ctypes.c_int64
         L.orc_flux_index.argtypes = [ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int]
         L.orc_num_threads.restype = ctypes.c_int
@@ -349,6 +352,50 @@ class PolylineIntegral(object):
         tot = numpy.zeros(nseg)
         numpy.add.at(tot, self.subsegs['seg'], (self.subsegs['tb'] - self.subsegs['ta']) * self.subsegs['coeff'])
         return tot
+
+
+class VectorInterp(object):
+    """mint.VectorInterp restated (field.py:90-95): findPoints + getFaceVectors"""
+
+    def __init__(self, grid, periodX=360.):
+        self.grid, self.periodX = grid, periodX
+        self.cell = numpy.zeros(0, numpy.int64)
+        self.xi = numpy.zeros((0, 2))
+
+    def findPoints(self, points, tol2=1.e-12):
+        pts = numpy.ascontiguousarray(points, numpy.float64).reshape(-1, 3)
+        n = pts.shape[0]
+        self.cell = numpy.zeros(n, numpy.int64)
+        self.xi = numpy.zeros((n, 2))
+        tol = max(float(tol2), 10 * numpy.finfo(numpy.float64).eps)
+        lib().orc_vinterp_find_points(self.grid.h, _dp(pts), n, float(self.periodX), tol,
+                                      self.cell.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), _dp(self.xi))
+        return int((self.cell < 0).sum())
+
+    def getFaceVectors(self, data, placement=0):
+        d = numpy.ascontiguousarray(data, numpy.float64).reshape(-1)
+        vec = numpy.zeros((self.cell.shape[0], 3))
+        lib().orc_vinterp_face_vectors(self.grid.h, self.cell.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)),
+                                       _dp(self.xi), self.cell.shape[0], _dp(d), _dp(vec))
+        return vec
+
+
+def transect_vector_points(lonLatZPoints, dx):
+    """sample points along the transects and their unit direction vectors, field.py:72-87"""
+    pts, dirs = [], []
+    for line in lonLatZPoints:
+        line = numpy.asarray(line, numpy.float64)
+        for i in range(len(line) - 1):
+            beg, end = line[i], line[i + 1]
+            u = end - beg
+            dist = numpy.sqrt(u.dot(u))
+            u = u / dist
+            nv = max(2, int(dist / dx))
+            vdx = dist / float(nv - 1)
+            for j in range(nv):
+                pts.append(beg + u * j * vdx)
+                dirs.append(u)
+    return numpy.array(pts), numpy.array(dirs)
 
 
 def flux_series(points, transects, u, v, thickness, sverdrup=False, periodX=360., order='map', use_c=False):

@@ -130,3 +130,43 @@ def test_integration_md_binding_runs(gpu, oracle, tmp_path):
     assert abs(pli.getIntegral(iV, mint.CELL_BY_CELL_DATA) - 360.) < 1e-10
     with pytest.raises(RuntimeError):
         pli.buildLocator(enableFolding=True)
+
+
+def test_vector_interp_matches_oracle_and_pictures(gpu, oracle, tmp_path):
+    """mint.VectorInterp mirror (field.py:90-95): findPoints + getFaceVectors bit-exact against the oracle; the
+    directions the reference's screenshots show (simple.png: south; singular.png: away from the singularity)"""
+    from nemoflux_b200.field import Field
+    rng = numpy.random.default_rng(8)
+    for delta in ((0., 0.), (20., 30.)):
+        g = oracle.DataGen(nx=60, ny=30, deltaDeg=delta)
+        P = g.points()
+        data = rng.standard_normal((60 * 30, 4))
+        pts = numpy.zeros((400, 3))
+        pts[:, 0] = rng.uniform(-200., 200., 400)        # some need the x-period, some lie outside in y
+        pts[:, 1] = rng.uniform(-80., 95., 400)
+        pts[:40, :2] = P[rng.integers(0, P.shape[0], 40), rng.integers(0, 4, 40), :2]     # exactly on grid nodes
+        grid = gpu.Grid()
+        grid.setPoints(P)
+        vi = gpu.VectorInterp()
+        vi.setGrid(grid)
+        vi.buildLocator(numCellsPerBucket=128, periodX=360.)
+        nbad = vi.findPoints(pts, tol2=1.e-12)
+        ov = oracle.VectorInterp(oracle.Grid(P))
+        assert ov.findPoints(pts, tol2=1.e-12) == nbad
+        cell, xi = vi.getCells()
+        assert numpy.array_equal(cell, ov.cell) and (cell < 0).sum() == nbad
+        from helpers import assert_bitwise
+        assert_bitwise(xi, ov.xi, 'parametric coordinates')
+        assert_bitwise(vi.getFaceVectors(data), ov.getFaceVectors(data), 'face vectors')
+    # through Field: README simple example, arrows point south with unit length
+    T, U, V = _files(tmp_path, '--streamFunction=x')
+    f = Field(T, U, V, [tr(README_C1)], verbose=False)
+    assert f.vectorPoints.shape[0] == len(f.uVectors) > 50
+    assert numpy.allclose(f.vectorValues[:, 0], 0., atol=1e-13) and numpy.allclose(f.vectorValues[:, 1], -1., rtol=1e-12)
+    pts_ref, dirs_ref = oracle.transect_vector_points([tr(README_C1)], f.dx)
+    assert numpy.allclose(f.vectorPoints, pts_ref) and numpy.allclose(numpy.array(f.uVectors), dirs_ref)
+    T, U, V = _files(tmp_path, '--streamFunction=arctan2(y, x+180)/(2*pi)')
+    f = Field(T, U, V, [tr(README_SINGULAR)], verbose=False)
+    radial = f.vectorPoints[:, :2] - numpy.array([-180., 0.])
+    inside = numpy.linalg.norm(radial, axis=1) > 15.
+    assert ((f.vectorValues[inside, :2] * radial[inside]).sum(axis=1) > 0).all()

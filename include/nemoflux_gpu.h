@@ -75,6 +75,10 @@ int nfx_grid_get_num_cells(nfx_grid** self, int64_t* ncells);
 /* the structured shape behind the cell ids (cell = j*nx + i, horizgrid.py:17-22); needed by the
  * compact [eU|eV] flux layout (field.py:209-223), not by the mint-style calls */
 int nfx_grid_set_cgrid_shape(nfx_grid** self, int ny, int nx);
+/* arc (ncells,4) device: unit-sphere length of edge e -> e+1 (Field.computeArcLengths, field.py:170-181) with the
+ * well-conditioned haversine of the lon/lat differences.  NOT bit-compatible with the reference's arccos(a.b) (geo.py:24-27),
+ * which the parity path keeps on the host; differences are the reference's own rounding noise (~1e-16/arc). */
+int nfx_grid_arc_lengths(nfx_grid** self, double* arc, void* stream);
 
 /* ---- mint.PolylineIntegral  (field.py:45-48, field.py:102, fluxplot.py:56) ----------------------- */
 int nfx_pli_new(nfx_pli** self);

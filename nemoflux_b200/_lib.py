@@ -33,6 +33,7 @@ SIGNATURES = {
     'nfx_grid_set_points': [P(c_vp), c_i64, c_vp],
     'nfx_grid_get_num_cells': [P(c_vp), P(c_i64)],
     'nfx_grid_set_cgrid_shape': [P(c_vp), c_int, c_int],
+    'nfx_grid_arc_lengths': [P(c_vp), c_vp, c_vp],
     'nfx_pli_new': [P(c_vp)],
     'nfx_pli_del': [P(c_vp)],
     'nfx_pli_set_grid': [P(c_vp), c_vp],

@@ -234,6 +234,14 @@ int nfx_grid_set_cgrid_shape(nfx_grid** self, int ny, int nx) {
     });
 }
 
+int nfx_grid_arc_lengths(nfx_grid** self, double* arc, void* stream) {
+    return guarded([&] {
+        NFX_REQUIRE(self && *self, "NULL handle");
+        DeviceGuard g((*self)->d.device);
+        grid_arc_lengths((*self)->d, arc, (cudaStream_t)stream);
+    });
+}
+
 // ---- polyline integral -------------------------------------------------------------------------------
 int nfx_pli_new(nfx_pli** self) {
     return guarded([&] {

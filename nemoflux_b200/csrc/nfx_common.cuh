@@ -151,6 +151,7 @@ void vinterp_face_vectors(VInterpDev& vi, const double* data_dev, double* vec_de
 // K1 (nfx_k1_intersect.cu)
 void grid_upload_points(GridDev& g, int64_t ncells, const double* points_host);
 void grid_build_locator(GridDev& g, cudaStream_t s);
+void grid_arc_lengths(GridDev& g, double* arc_dev, cudaStream_t s);
 void pli_compute_weights(PliDev& p, int ntransects, const int* offsets, const double* xyz, int counterclock,
                          cudaStream_t s);
 

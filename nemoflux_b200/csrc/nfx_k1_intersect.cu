@@ -696,6 +696,25 @@ void build_panel_plan(PliDev& p, int order, int64_t panel_cells, cudaStream_t s)
     pl.built = true;
 }
 
+// ---- arc lengths on the device (optional, NOT the parity path) -----------------------------------------
+// arc[c, e] = great-circle length of edge e -> e+1 on the unit sphere from the haversine of the lon/lat
+// DIFFERENCES: hav = sin^2(dlat/2) + cos(lat1) cos(lat2) sin^2(dlon/2), arc = 2 asin(sqrt(hav)) -- accurate to a
+// few ulp for edges of any length, unlike the reference's arccos(a.b) (geo.py:24-27) whose rounding noise is
+// ~1e-16/arc.  The parity path keeps the reference formula on the host (nemoflux_b200/geo.py); this kernel
+// serves callers that want the metric factors fast (13 M cells in ~1 ms) and more accurate.
+__global__ void k_arc_lengths(const double2* __restrict__ verts, int64_t ncell, double* __restrict__ arc) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ncell * 4) return;
+    const int64_t c = i >> 2;
+    const int e = (int)(i & 3);
+    const double2 p = verts[c * 4 + e], q = verts[c * 4 + ((e + 1) & 3)];
+    const double d2r = 0.017453292519943295;
+    const double sdl = sin(0.5 * (q.x - p.x) * d2r);
+    const double sdp = sin(0.5 * (q.y - p.y) * d2r);
+    const double hav = sdp * sdp + cos(p.y * d2r) * cos(q.y * d2r) * sdl * sdl;
+    arc[i] = 2.0 * asin(fmin(1.0, sqrt(hav)));
+}
+
 // ---- host side --------------------------------------------------------------------------------------
 void grid_upload_points(GridDev& g, int64_t ncells, const double* points_host) {
     NFX_REQUIRE(ncells > 0, "nfx_grid_set_points: ncells must be positive");
@@ -711,6 +730,13 @@ void grid_upload_points(GridDev& g, int64_t ncells, const double* points_host) {
     NFX_CUDA(cudaDeviceSynchronize());
     g.ncell = ncells;
     g.locator_built = false;
+}
+
+void grid_arc_lengths(GridDev& g, double* arc_dev, cudaStream_t s) {
+    NFX_REQUIRE(g.ncell > 0 && arc_dev, "arcLengths: the grid has no points / NULL output");
+    k_arc_lengths<<<nblk(g.ncell * 4, 256), 256, 0, s>>>(g.verts.p, g.ncell, arc_dev);
+    count_launch();
+    NFX_CUDA(cudaGetLastError());
 }
 
 void grid_build_locator(GridDev& g, cudaStream_t s) {

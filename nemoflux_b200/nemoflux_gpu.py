@@ -92,6 +92,19 @@ class Grid(object):
     def getPoints(self):
         return self._points
 
+    def arcLengths(self, out=None):
+        """(ncells, 4) cuda tensor of unit-sphere edge lengths computed on the device with the well-conditioned
+        haversine form.  Not the parity path: the reference's arccos formula (geo.getArcLengthArray) carries rounding
+        noise of ~1e-16/arc, so reproducing it to 1e-12 needs the host formula (nemoflux_b200.geo.cellArcLengths)."""
+        torch = _torch()
+        n = self.getNumberOfCells()
+        if out is None:
+            out = torch.empty((n, 4), dtype=torch.float64, device='cuda')
+        _require_cuda(out, torch.float64, 'out')
+        with torch.cuda.device(out.device):
+            _lib.call('nfx_grid_arc_lengths', ctypes.byref(self._h), _t_ptr(out), _stream_ptr())
+        return out
+
 
 class PolylineIntegral(object):
     """mint.PolylineIntegral for one transect or a batch of transects sharing one locator"""

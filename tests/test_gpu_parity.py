@@ -520,3 +520,27 @@ def test_k2_per_column_scale_factors(gpu, oracle, dtype, e3_nt):
     assert torch.equal(s_e3, s_th)
     with pytest.raises(ValueError):
         gpu.edgeFluxAssemble(args[0], args[1], None, a1d, a2d, e3u=torch.from_numpy(e3c).to(d))
+
+
+def test_device_arc_lengths(gpu, oracle):
+    """the optional device metric factors: accurate to a few ulp against an extended-precision evaluation, and
+    within the reference formula's own rounding noise (~1e-16/arc) of geo.getArcLengthArray"""
+    for nx, ny, delta in ((36, 18, (0., 0.)), (720, 360, (20., 30.))):
+        g = oracle.DataGen(nx=nx, ny=ny, deltaDeg=delta, ymin=-80., ymax=80., dy=160. / ny)
+        P = g.points()
+        grid = gpu.Grid()
+        grid.setPoints(P)
+        arc = grid.arcLengths().cpu().numpy()
+        ld = numpy.longdouble
+        d2r = ld(numpy.pi) / 180
+        ref = numpy.zeros((P.shape[0], 4), ld)
+        for e in range(4):
+            p, q = P[:, e].astype(ld), P[:, (e + 1) % 4].astype(ld)
+            hav = numpy.sin((q[:, 1] - p[:, 1]) * d2r / 2) ** 2 + \
+                numpy.cos(p[:, 1] * d2r) * numpy.cos(q[:, 1] * d2r) * numpy.sin((q[:, 0] - p[:, 0]) * d2r / 2) ** 2
+            ref[:, e] = 2 * numpy.arcsin(numpy.sqrt(hav))
+        rel = numpy.abs(arc - ref.astype(numpy.float64)) / ref.astype(numpy.float64)
+        assert rel.max() < 2e-14, rel.max()            # pi/180 in double limits this, not the kernel
+        host = oracle.arc_lengths(P)                   # the reference formula
+        noise = 4 * numpy.finfo(float).eps / numpy.maximum(host, 1e-300)
+        assert (numpy.abs(arc - host) <= noise * 4 + 1e-15).all()

@@ -219,17 +219,49 @@ class Field(object):
         txt += "(Sv) " if self.sverdrup else "(A m^2/s) "
         return re.sub(r',\s*\(', ' (', txt)
 
-    def fluxSeries(self, chunk_steps=0):
+    def fluxSeries(self, chunk_steps=0, prefetch=True):
         """(nt, M) flux of every transect at every time step -- the loop of fluxplot.py:51-59 in a few launches.
-        Streams the time axis from the files through the host-buffer entry point of the C ABI."""
+
+        The time axis is streamed from the files in chunks: a reader thread fills one of two PINNED host buffers
+        (file read + byte-order conversion, numpy releases the GIL) while the previous chunk goes through the
+        host-buffer entry point of the C ABI (double-buffered H2D, K2, K3) -- file I/O, PCIe and the kernels
+        overlap."""
+        import threading
+        import torch
         out = numpy.zeros((self.nt, len(self.plis)))
-        step_bytes = 8 * self.nz * self.ny * self.nx
-        n = chunk_steps if chunk_steps > 0 else max(1, min(self.nt, (1 << 30) // max(step_bytes, 1)))
-        for t0 in range(0, self.nt, n):
-            m = min(n, self.nt - t0)
+        dtype = numpy.dtype(self.ncU['uo'].dtype).newbyteorder('=')
+        step_bytes = dtype.itemsize * self.nz * self.ny * self.nx
+        n = chunk_steps if chunk_steps > 0 else max(1, min(self.nt, (1 << 29) // max(step_bytes, 1)))
+        arc1, arc2 = self.arcLengths[:, 1].copy(), self.arcLengths[:, 2].copy()
+        tdtype = {4: torch.float32, 8: torch.float64}[dtype.itemsize]
+        shape = (n, self.nz, self.ny, self.nx)
+        bufs = [(torch.empty(shape, dtype=tdtype).pin_memory(), torch.empty(shape, dtype=tdtype).pin_memory())
+                for _ in range(2 if prefetch and self.nt > n else 1)]
+        chunks = [(t0, min(n, self.nt - t0)) for t0 in range(0, self.nt, n)]
+        state = {}
+
+        def read(i, slot):
+            t0, m = chunks[i]
             u, v, fill = self._uv_slabs(t0, m)
-            out[t0:t0 + m] = self.pli.fluxSeries(u, v, self.thickness, self.arcLengths[:, 1].copy(),
-                                                 self.arcLengths[:, 2].copy(), sverdrup=self.sverdrup, fill=fill)
+            bu, bv = bufs[slot]
+            bu.numpy()[:m] = u
+            bv.numpy()[:m] = v
+            state[i] = fill
+
+        read(0, 0)
+        for i, (t0, m) in enumerate(chunks):
+            slot = i % len(bufs)
+            th = None
+            if i + 1 < len(chunks) and len(bufs) == 2:
+                th = threading.Thread(target=read, args=(i + 1, 1 - slot))
+                th.start()
+            bu, bv = bufs[slot]
+            out[t0:t0 + m] = self.pli.fluxSeries(bu[:m], bv[:m], self.thickness, arc1, arc2, sverdrup=self.sverdrup,
+                                                 fill=state.pop(i))
+            if th is not None:
+                th.join()
+            elif i + 1 < len(chunks):
+                read(i + 1, slot)
         return out
 
     def close(self):

@@ -240,13 +240,28 @@ class Field(object):
         chunks = [(t0, min(n, self.nt - t0)) for t0 in range(0, self.nt, n)]
         state = {}
 
+        fill_u, fill_v = self._fill(self.ncU, 'uo'), self._fill(self.ncV, 'vo')
+        four_d = len(self.ncU['uo'].shape) == 4 and len(self.ncV['vo'].shape) == 4
+        from concurrent.futures import ThreadPoolExecutor
+        import os as _os
+        pool = ThreadPoolExecutor(max_workers=max(1, min(8, (_os.cpu_count() or 2) // 2)))
+
         def read(i, slot):
+            """file -> pinned buffer, one task per (variable, time step): byte-order conversion in parallel"""
             t0, m = chunks[i]
-            u, v, fill = self._uv_slabs(t0, m)
             bu, bv = bufs[slot]
-            bu.numpy()[:m] = u
-            bv.numpy()[:m] = v
-            state[i] = fill
+            if four_d and (fill_v != fill_v or fill_v == fill_u):
+                nu, nv = bu.numpy(), bv.numpy()
+                jobs = [pool.submit(self.ncU['uo'].read_into, nu[j], t0 + j) for j in range(m)]
+                jobs += [pool.submit(self.ncV['vo'].read_into, nv[j], t0 + j) for j in range(m)]
+                for job in jobs:
+                    job.result()
+                state[i] = fill_u
+            else:
+                u, v, fill = self._uv_slabs(t0, m)
+                bu.numpy()[:m] = u
+                bv.numpy()[:m] = v
+                state[i] = fill
 
         read(0, 0)
         for i, (t0, m) in enumerate(chunks):
@@ -262,6 +277,7 @@ class Field(object):
                 th.join()
             elif i + 1 < len(chunks):
                 read(i + 1, slot)
+        pool.shutdown()
         return out
 
     def close(self):

@@ -36,6 +36,11 @@ class Variable(object):
         """values as stored (native byte order), missing values NOT decoded: pair with fill_value()"""
         return self._native(numpy.array(self._data[idx]))
 
+    def read_into(self, dst, idx=Ellipsis):
+        """copy the stored values [idx] into dst (same shape), converting the byte order on the way; missing values
+        are NOT decoded.  numpy releases the GIL in the copy loop, so several slices can be read in parallel."""
+        numpy.copyto(dst, self._data[idx], casting='same_kind')
+
     def fill_value(self):
         """the value that marks missing data (_FillValue / missing_value), NaN when there is none"""
         for key in ('_FillValue', 'missing_value'):

@@ -292,6 +292,8 @@ class PolylineIntegral(object):
             if t.numel() != n:
                 raise ValueError(f'{name} must hold {n} values, got {t.numel()}')
         m = self.getNumberOfTransects()
+        if nt == 0 or m == 0:       # nothing to integrate: no launch (empty tensors have no device address)
+            return out if out is not None else torch.zeros((nt, m), dtype=torch.float64, device=u.device)
         if use_e3:
             if batch_range is not None:
                 raise ValueError('batch_range and e3u/e3v cannot be combined')

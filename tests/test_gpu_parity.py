@@ -544,3 +544,40 @@ def test_device_arc_lengths(gpu, oracle):
         host = oracle.arc_lengths(P)                   # the reference formula
         noise = 4 * numpy.finfo(float).eps / numpy.maximum(host, 1e-300)
         assert (numpy.abs(arc - host) <= noise * 4 + 1e-15).all()
+
+
+def test_series_edge_cases(gpu, oracle):
+    """degenerate inputs through both series paths: no transects, transects outside the grid, nt = 0 and 1,
+    nz = 1, an odd number of cells (scalar loads), a transect that only touches row 0 (always-zero south edges)"""
+    import torch
+    from nemoflux_b200 import _lib
+    d = 'cuda'
+    g = oracle.DataGen(nx=37, ny=19, nz=1, nt=2, dy=180. / 19)            # 703 cells: odd
+    P, arc = g.points(), oracle.arc_lengths(g.points())
+    u, v = g.uv('x + 2*y')
+    th = g.thickness()
+    args = [torch.from_numpy(x).to(d) for x in (u, v, th, arc[:, 1].copy(), arc[:, 2].copy())]
+    _, p = _build(gpu, P, 19, 37)
+    try:
+        for mode in (0, 2):
+            _lib.set_option(_lib.NFX_OPT_FAST_SERIES, mode)
+            p.computeWeights([])
+            assert tuple(p.fluxSeries(*args).shape) == (2, 0)
+            outside = [tr([(0, 100), (10, 120)]), tr([(5, 5)]), tr([(1, 1), (1, 1)])]
+            p.computeWeights(outside)
+            assert (p.fluxSeries(*args).cpu().numpy() == 0).all()
+            row0 = [tr([(-170, -89.5), (170, -89.5)]), tr([(-100, -60), (100, 40)])]
+            p.computeWeights(row0)
+            s = p.fluxSeries(*args).cpu().numpy()
+            ref = oracle.flux_series(P, row0, u, v, th, use_c=True)
+            assert numpy.abs(s - ref).max() <= 1e-12 * numpy.abs(ref).max()
+            empty = p.fluxSeries(args[0][:0], args[1][:0], *args[2:])
+            assert tuple(empty.shape) == (0, 2)
+            one = p.fluxSeries(args[0][1:], args[1][1:], *args[2:]).cpu().numpy()
+            assert numpy.array_equal(one[0], s[1])
+    finally:
+        _lib.set_option(_lib.NFX_OPT_FAST_SERIES, 1)
+    with pytest.raises(ValueError):
+        p.fluxSeries(args[0][:, :, :10], args[1][:, :, :10], *args[2:])         # wrong grid size
+    with pytest.raises(TypeError):
+        p.fluxSeries(args[0], args[1].cpu(), *args[2:])

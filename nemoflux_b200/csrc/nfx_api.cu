@@ -154,6 +154,7 @@ int nfx_set_option(int option, int value) {
                 break;
             case NFX_OPT_K2_UNROLL: g_k2opt.unroll = value; break;
             case NFX_OPT_K2_BLOCK: g_k2opt.block = value; break;
+            case NFX_OPT_K2_ALU_MASK: g_k2opt.alu_mask = value; break;
             case NFX_OPT_FAST_SERIES:
                 NFX_REQUIRE(value >= 0 && value <= 2, "NFX_OPT_FAST_SERIES must be 0, 1 or 2");
                 g_fast_series = value;
@@ -174,6 +175,7 @@ int nfx_get_option(int option, int* value) {
             case NFX_OPT_K2_VARIANT: *value = g_k2opt.variant; break;
             case NFX_OPT_K2_UNROLL: *value = g_k2opt.unroll; break;
             case NFX_OPT_K2_BLOCK: *value = g_k2opt.block; break;
+            case NFX_OPT_K2_ALU_MASK: *value = g_k2opt.alu_mask; break;
             case NFX_OPT_FAST_SERIES: *value = g_fast_series; break;
             case NFX_OPT_RING_SLOT_MB: *value = (int)(g_slot_bytes >> 20); break;
             default: throw Error(NFX_E_INVALID, "unknown option");

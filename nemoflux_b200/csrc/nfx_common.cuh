@@ -160,6 +160,7 @@ struct K2Options {
     int variant = NFX_K2_AUTO;
     int unroll = 0;   // 0 = default
     int block = 0;    // 0 = default
+    int alu_mask = -1;  // float32 storage: levels (of each batch of 5) converted on the ALU; -1 = built-in choice
 };
 void edgeflux_assemble(const void* u, const void* v, int dtype, const double* thickness, const double* arc1,
                        const double* arc2, int nt, int nz, int64_t ncell, int sverdrup, double fill, double* eflux,

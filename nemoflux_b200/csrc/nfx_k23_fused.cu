@@ -88,8 +88,18 @@ k23_fused(const FusedArgs a) {
     extern __shared__ double s_dz[];
     __shared__ int s_item;
     __shared__ int s_ok;
-    for (int k = threadIdx.x; k < a.nz; k += kFusedBlock) s_dz[k] = a.dz[k];
-    __syncthreads();
+    // float32 storage: levels go through clean_scaled() (nfx_stream_ops.cuh) with dz * 2^896 in s_dz[nz..2nz)
+    constexpr bool kScaled = sizeof(T) == 4;
+    int big = 0;
+    for (int k = threadIdx.x; k < a.nz; k += kFusedBlock) {
+        const double d = a.dz[k];
+        s_dz[k] = d;
+        if constexpr (kScaled) {
+            s_dz[a.nz + k] = d * kScaleUp;
+            big |= !(fabs(d) < kScaleLimit);
+        }
+    }
+    const bool redo_all = __syncthreads_or(big) != 0;
     using P = Pack<T, VEC>;
     using V = typename P::type;
     const T* __restrict__ u = reinterpret_cast<const T*>(a.u);
@@ -136,6 +146,7 @@ k23_fused(const FusedArgs a) {
                     su[e] = 0.0;
                     sv[e] = 0.0;
                 }
+                float amax = 0.f;
                 int k = 0;
                 for (; k + UNROLL <= a.nz; k += UNROLL) {
                     V ru[UNROLL], rv[UNROLL];
@@ -154,11 +165,16 @@ k23_fused(const FusedArgs a) {
                         T x[VEC], y[VEC];
                         P::unpack(ru[qq], x);
                         P::unpack(rv[qq], y);
-                        const double d = s_dz[k + qq];
+                        const double d = s_dz[(kScaled ? a.nz : 0) + k + qq];
 #pragma unroll
                         for (int e = 0; e < VEC; ++e) {
-                            su[e] = __dadd_rn(su[e], __dmul_rn(d, clean<T>(x[e], fill, a.has_fill)));
-                            sv[e] = __dadd_rn(sv[e], __dmul_rn(d, clean<T>(y[e], fill, a.has_fill)));
+                            if constexpr (kScaled) {
+                                su[e] = __dadd_rn(su[e], __dmul_rn(d, clean_scaled(x[e], fill, a.has_fill, amax)));
+                                sv[e] = __dadd_rn(sv[e], __dmul_rn(d, clean_scaled(y[e], fill, a.has_fill, amax)));
+                            } else {
+                                su[e] = __dadd_rn(su[e], __dmul_rn(d, clean<T>(x[e], fill, a.has_fill)));
+                                sv[e] = __dadd_rn(sv[e], __dmul_rn(d, clean<T>(y[e], fill, a.has_fill)));
+                            }
                         }
                     }
                 }
@@ -171,6 +187,24 @@ k23_fused(const FusedArgs a) {
                     for (int e = 0; e < VEC; ++e) {
                         su[e] = __dadd_rn(su[e], __dmul_rn(d, clean<T>(x[e], fill, a.has_fill)));
                         sv[e] = __dadd_rn(sv[e], __dmul_rn(d, clean<T>(y[e], fill, a.has_fill)));
+                    }
+                }
+                if constexpr (kScaled) {
+                    if (redo_all || !(amax <= 3.402823466e38f)) {   // rare: an infinity in this thread's columns
+#pragma unroll
+                        for (int e = 0; e < VEC; ++e) {
+                            su[e] = 0.0;
+                            sv[e] = 0.0;
+                        }
+#pragma unroll 1
+                        for (int kk = 0; kk < a.nz; ++kk) {
+                            const double d = s_dz[kk];
+#pragma unroll
+                            for (int e = 0; e < VEC; ++e) {
+                                su[e] = __dadd_rn(su[e], __dmul_rn(d, clean<T>(pu[(int64_t)kk * a.ld + e], fill, a.has_fill)));
+                                sv[e] = __dadd_rn(sv[e], __dmul_rn(d, clean<T>(pv[(int64_t)kk * a.ld + e], fill, a.has_fill)));
+                            }
+                        }
                     }
                 }
                 double* ou = a.ring + (int64_t)(b % a.ring_slots) * a.slot_elems + cl;
@@ -245,7 +279,7 @@ int fused_grid() {
         NFX_CUDA(cudaGetDevice(&dev));
         NFX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         NFX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k23_fused<T, VEC, 5>, kFusedBlock,
-                                                               sizeof(double) * 128));
+                                                               sizeof(double) * 256));
         grid = sms * std::max(per_sm, 1);
     }
     return grid;
@@ -253,7 +287,7 @@ int fused_grid() {
 
 template <typename T, int VEC>
 void launch_fused(const FusedArgs& a, cudaStream_t s) {
-    k23_fused<T, VEC, 5><<<fused_grid<T, VEC>(), kFusedBlock, sizeof(double) * a.nz, s>>>(a);
+    k23_fused<T, VEC, 5><<<fused_grid<T, VEC>(), kFusedBlock, sizeof(double) * a.nz * 2, s>>>(a);
 }
 
 int fused_grid_for(int dtype, int vec) {

@@ -31,18 +31,33 @@ using namespace dev;
 // One thread owns VEC adjacent columns of one time step; blockIdx.y = time step.
 // E3: per-column, per-level scale factors e3u/e3v (NEMO's vertical metric, partial cells / z*) replace the 1-D
 // layer thickness dz[k] of field.py:51 -- two more streamed arrays, same layout as u/v.
-template <typename T, int VEC, int UNROLL, int BLOCK, bool E3>
+// ALU_MASK (float32 storage): bit q set = level q of every batch of UNROLL levels goes through clean_scaled()
+// (bit shuffle on the ALU, dz scaled by 2^896) instead of an F2F on the XU pipe; same bits either way
+template <typename T, int VEC, int UNROLL, int BLOCK, bool E3, int ALU_MASK>
 __global__ void __launch_bounds__(BLOCK)
 k2_edgeflux_ldg(const T* __restrict__ u, const T* __restrict__ v, const double* __restrict__ dz,
                 const double* __restrict__ arc1, const double* __restrict__ arc2, double* __restrict__ eflux, int nz,
                 int64_t ncell, int64_t ld, double scale, int use_scale, T fill, int has_fill, int keep_l2,
                 const T* __restrict__ e3u, const T* __restrict__ e3v, int64_t e3_tstride) {
     // ncell = columns handled by this launch (a panel of the grid), ld = cells per level plane (row stride of u, v)
-    extern __shared__ double s_dz[];
+    extern __shared__ double s_dz[];   // [nz] dz, then (ALU_MASK != 0) [nz] dz * 2^896
+    bool redo = false;                 // ALU_MASK: recompute this thread's columns with clean() (saw an infinity)
     if constexpr (!E3) {
-        for (int k = threadIdx.x; k < nz; k += BLOCK) s_dz[k] = dz[k];
-        __syncthreads();
+        int big = 0;
+        for (int k = threadIdx.x; k < nz; k += BLOCK) {
+            const double d = dz[k];
+            s_dz[k] = d;
+            if constexpr (ALU_MASK != 0) {
+                s_dz[nz + k] = d * kScaleUp;
+                big |= !(fabs(d) < kScaleLimit);
+            }
+        }
+        if constexpr (ALU_MASK != 0)
+            redo = __syncthreads_or(big) != 0;   // absurd thickness: the scaled factors could overflow
+        else
+            __syncthreads();
     }
+    float amax = 0.f;
     using P = Pack<T, VEC>;
     using V = typename P::type;
     const int64_t t = blockIdx.y;
@@ -90,13 +105,19 @@ k2_edgeflux_ldg(const T* __restrict__ u, const T* __restrict__ v, const double* 
                 P::unpack(re[q], ea);
                 P::unpack(rf[q], eb);
             }
-            const double d = E3 ? 0.0 : s_dz[k + q];
+            const bool kScaled = (ALU_MASK >> q) & 1;   // compile-time after unrolling
+            const double d = E3 ? 0.0 : s_dz[(kScaled ? nz : 0) + k + q];
 #pragma unroll
             for (int e = 0; e < VEC; ++e) {
                 const double du = E3 ? clean<T>(ea[e], fill, has_fill) : d;
                 const double dv = E3 ? clean<T>(eb[e], fill, has_fill) : d;
-                su[e] = __dadd_rn(su[e], __dmul_rn(du, clean<T>(a[e], fill, has_fill)));
-                sv[e] = __dadd_rn(sv[e], __dmul_rn(dv, clean<T>(b[e], fill, has_fill)));
+                if (kScaled) {
+                    su[e] = __dadd_rn(su[e], __dmul_rn(du, clean_scaled(a[e], fill, has_fill, amax)));
+                    sv[e] = __dadd_rn(sv[e], __dmul_rn(dv, clean_scaled(b[e], fill, has_fill, amax)));
+                } else {
+                    su[e] = __dadd_rn(su[e], __dmul_rn(du, clean<T>(a[e], fill, has_fill)));
+                    sv[e] = __dadd_rn(sv[e], __dmul_rn(dv, clean<T>(b[e], fill, has_fill)));
+                }
             }
         }
     }
@@ -115,6 +136,25 @@ k2_edgeflux_ldg(const T* __restrict__ u, const T* __restrict__ v, const double* 
             const double dv = E3 ? clean<T>(eb[e], fill, has_fill) : d;
             su[e] = __dadd_rn(su[e], __dmul_rn(du, clean<T>(a[e], fill, has_fill)));
             sv[e] = __dadd_rn(sv[e], __dmul_rn(dv, clean<T>(b[e], fill, has_fill)));
+        }
+    }
+    if constexpr (ALU_MASK != 0) {
+        redo = redo || !(amax <= 3.402823466e38f);
+        if (redo) {                    // rare: an infinity in this thread's columns -- plain conversion, same order
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) {
+                su[e] = 0.0;
+                sv[e] = 0.0;
+            }
+#pragma unroll 1
+            for (int kk = 0; kk < nz; ++kk) {
+                const double d = s_dz[kk];
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) {
+                    su[e] = __dadd_rn(su[e], __dmul_rn(d, clean<T>(pu[(int64_t)kk * ld + e], fill, has_fill)));
+                    sv[e] = __dadd_rn(sv[e], __dmul_rn(d, clean<T>(pv[(int64_t)kk * ld + e], fill, has_fill)));
+                }
+            }
         }
     }
     double* ou = eflux + t * 2 * ncell + c0;
@@ -159,15 +199,33 @@ struct E3Args {
 template <typename T, int VEC, int UNROLL, int BLOCK>
 void launch_ldg(const T* u, const T* v, const double* dz, const double* arc1, const double* arc2, double* eflux, int nt,
                 int nz, int64_t ncell, int64_t ld, double scale, int use_scale, T fill, int has_fill, int keep_l2,
-                const E3Args& e3, cudaStream_t s) {
+                const E3Args& e3, int alu_mask, cudaStream_t s) {
     const int64_t nthreads = (ncell + VEC - 1) / VEC;
     dim3 grid((unsigned)((nthreads + BLOCK - 1) / BLOCK), (unsigned)nt);
+    // float32: every level through the bit-shuffle conversion (profiles/r1_f32_alu_sweep.md: 5.09 -> 6.37 TB/s)
+    constexpr int kAluMask = (sizeof(T) == 4) ? 0x1f : 0;
     if (e3.e3u)
-        k2_edgeflux_ldg<T, VEC, UNROLL, BLOCK, true><<<grid, BLOCK, sizeof(double) * nz, s>>>(
+        k2_edgeflux_ldg<T, VEC, UNROLL, BLOCK, true, 0><<<grid, BLOCK, sizeof(double) * nz, s>>>(
             u, v, dz, arc1, arc2, eflux, nz, ncell, ld, scale, use_scale, fill, has_fill, keep_l2, (const T*)e3.e3u,
             (const T*)e3.e3v, e3.tstride);
-    else
-        k2_edgeflux_ldg<T, VEC, UNROLL, BLOCK, false><<<grid, BLOCK, sizeof(double) * nz, s>>>(
+    else if (alu_mask >= 0 && sizeof(T) == 4 && UNROLL == 5) {
+        switch (alu_mask) {
+#define NFX_ALU_CASE(M)                                                                                             \
+    case M:                                                                                                         \
+        k2_edgeflux_ldg<T, VEC, UNROLL, BLOCK, false, (sizeof(T) == 4 && UNROLL == 5) ? M : 0>                      \
+            <<<grid, BLOCK, sizeof(double) * nz * 2, s>>>(u, v, dz, arc1, arc2, eflux, nz, ncell, ld, scale,      \
+                                                          use_scale, fill, has_fill, keep_l2, nullptr, nullptr, 0); \
+        break;
+            NFX_ALU_CASE(0)
+            NFX_ALU_CASE(0x01)
+            NFX_ALU_CASE(0x09)
+            NFX_ALU_CASE(0x15)
+            NFX_ALU_CASE(0x1f)
+#undef NFX_ALU_CASE
+            default: throw Error(NFX_E_INVALID, "edgeflux: unsupported ALU conversion mask");
+        }
+    } else
+        k2_edgeflux_ldg<T, VEC, UNROLL, BLOCK, false, kAluMask><<<grid, BLOCK, sizeof(double) * nz * 2, s>>>(
             u, v, dz, arc1, arc2, eflux, nz, ncell, ld, scale, use_scale, fill, has_fill, keep_l2, nullptr, nullptr, 0);
 }
 
@@ -180,7 +238,7 @@ void dispatch_ldg(const T* u, const T* v, const double* dz, const double* arc1, 
 #define NFX_K2_CASE(U, B)                                                                                          \
     if (unroll == U && block == B) {                                                                               \
         launch_ldg<T, VEC, U, B>(u, v, dz, arc1, arc2, eflux, nt, nz, ncell, ld, scale, use_scale, fill, has_fill,  \
-                                 keep_l2, e3, s);                                                                  \
+                                 keep_l2, e3, opt.alu_mask, s);                                                    \
         return;                                                                                                    \
     }
     NFX_K2_CASE(5, 256)

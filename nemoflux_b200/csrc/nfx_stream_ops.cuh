@@ -183,6 +183,37 @@ __device__ __forceinline__ double clean(T x, T fill, bool has_fill) {
     return bad ? 0.0 : (double)x;
 }
 
+// float32 storage: (double)x is an F2F.F64.F32 on the XU pipe, which saturates at ~5.2 TB/s of input (ncu:
+// profiles/r1_k2_f32_ncu.md).  clean_scaled() avoids the conversion: the float's bits, shifted into the double
+// layout WITHOUT re-biasing the exponent (sign | exponent | mantissa << 29), are exactly x * 2^-896 for every
+// finite float -- normals, denormals (they become double denormals with the same value) and +-0.  The caller
+// multiplies by dz[k] * 2^896 instead of dz[k]: both factors are scaled exactly, so the rounded product has the
+// same bits as dz[k] * (double)x.  NaN and the missing-value marker give 0 as in clean().  Infinities have no
+// image (exponent 255 would read as a finite number): they contribute 0 here and are recorded in `amax`, and a
+// thread that saw one recomputes its columns with clean() (see k2_edgeflux_ldg).  Three integer operations
+// replace the F2F.
+constexpr double kScaleUp = 0x1p896;      // dz[k] is multiplied by this
+constexpr double kScaleLimit = 0x1p100;   // |dz[k]| below this: dz[k] * 2^896 cannot overflow
+
+__device__ __forceinline__ double clean_scaled(float x, float fill, bool has_fill, float& amax) {
+    const float ax = fabsf(x);
+    amax = fmaxf(amax, ax);                                        // NaN is ignored by fmaxf, inf sticks
+    // without a marker the caller passes fill = NaN, and x != NaN holds for every x: no has_fill test needed.
+    // One chained predicate (FSETP ... AND P) and one select; the compiler's own code had two of each.
+    uint32_t b;
+    asm("{\n\t.reg .pred p;\n\t"
+        "setp.neu.f32 p, %1, %2;\n\t"
+        "setp.le.and.f32 p, %3, 0f7F7FFFFF, p;\n\t"
+        "selp.b32 %0, %1, 0, p;\n\t}"
+        : "=r"(b)
+        : "r"(__float_as_uint(x)), "r"(__float_as_uint(fill)), "r"(__float_as_uint(ax)));
+    const uint32_t hi = (uint32_t)((int32_t)b >> 3) & 0x8fffffffu;
+    const uint32_t lo = b << 29;
+    return __hiloint2double((int)hi, (int)lo);
+}
+__device__ __forceinline__ double clean_scaled(double x, double fill, bool has_fill, float&) {
+    return clean<double>(x, fill, has_fill);                       // never used: ALU_MASK is 0 for float64 storage
+}
 
 }  // namespace dev
 }  // namespace nfx

@@ -23,6 +23,8 @@ def main():
     ap.add_argument('--slots', default='8')
     ap.add_argument('--out', default='')
     ap.add_argument('--nx', type=int, default=0)
+    ap.add_argument('--dtype', default='f64', choices=['f64', 'f32'])
+    ap.add_argument('--pad', type=int, default=0)
     a = ap.parse_args()
     dev = torch.device('cuda', 0)
     syn = synth.make(a.workload, **({'nx': a.nx} if a.nx else {}))
@@ -33,11 +35,12 @@ def main():
     p = nemoflux_gpu.PolylineIntegral()
     p.build(g)
     p.computeWeights(syn.transects)
-    u, v = syn.fill_device(0, nt, dev)
+    tdt = torch.float32 if a.dtype == 'f32' else torch.float64
+    u, v = syn.fill_device(0, nt, dev, dtype=tdt, pad=a.pad)
     th, a1, a2 = (torch.from_numpy(x).to(dev) for x in (syn.thickness, syn.arc1, syn.arc2))
     eflux = torch.empty((nt, 2 * syn.ncell), dtype=torch.float64, device=dev)
     out = torch.empty((nt, syn.ntransects), dtype=torch.float64, device=dev)
-    nbytes = 16.0 * syn.units_per_step() * nt
+    nbytes = (8.0 if a.dtype == 'f32' else 16.0) * syn.units_per_step() * nt
     modes = [('classic', dict(eflux=eflux), {})]
     for mb in [int(x) for x in a.slots.split(',')]:
         modes.append((f'fused slot={mb}MB', {}, {_lib.NFX_OPT_RING_SLOT_MB: mb, _lib.NFX_OPT_FAST_SERIES: 2}))

@@ -179,6 +179,43 @@ def test_k2_bit_exact_vs_sequential_oracle(gpu, oracle, shape, dtype, sverdrup):
     assert gpu.edgeFluxAbsMax(ef) == numpy.abs(efh).max()
 
 
+@pytest.mark.parametrize('thick_max', [20., 2.0e31])
+@pytest.mark.parametrize('shape', [(2, 75, 16, 32), (2, 12, 9, 11)])
+def test_k2_f32_special_values(gpu, oracle, shape, thick_max):
+    """float32 storage takes the bit-shuffle conversion (clean_scaled): denormals, signed zeros, FLT_MAX, the
+    smallest normals and infinities must give the bits of the plain (double)x path; thickness >= 2^100 too"""
+    import torch
+    nt, nz, ny, nx = shape
+    rng = numpy.random.default_rng(99)
+    u, v = _rand_uv(rng, nt, nz, ny, nx, numpy.float32)
+    for a in (u, v):
+        r = rng.random(a.shape)
+        a[r < 0.02] = 0.0
+        a[(r >= 0.02) & (r < 0.04)] = -0.0
+        a[(r >= 0.04) & (r < 0.07)] = numpy.float32(1.0e-41)
+        a[(r >= 0.07) & (r < 0.09)] = numpy.float32(-1.4e-45)
+        a[(r >= 0.09) & (r < 0.11)] = numpy.finfo(numpy.float32).max
+        a[(r >= 0.11) & (r < 0.13)] = -numpy.finfo(numpy.float32).tiny
+        a[(r >= 0.13) & (r < 0.1305)] = numpy.inf
+        a[(r >= 0.1305) & (r < 0.131)] = -numpy.inf
+    th = rng.uniform(0.5, thick_max, nz)
+    arc1 = rng.uniform(1e-3, 2e-2, ny * nx)
+    arc2 = rng.uniform(1e-3, 2e-2, ny * nx)
+    d = 'cuda'
+    efh = gpu.edgeFluxAssemble(torch.from_numpy(u).to(d), torch.from_numpy(v).to(d), torch.from_numpy(th).to(d),
+                               torch.from_numpy(arc1).to(d), torch.from_numpy(arc2).to(d)).cpu().numpy()
+    ninf = 0
+    for t in range(nt):
+        with numpy.errstate(all='ignore'):
+            _, eU, eV = oracle.edgeflux_step_c(u[t], v[t], th, arc1, arc2, False, want_iV=False)
+        ref = numpy.concatenate([eU, eV])
+        nan = numpy.isnan(ref)
+        assert numpy.array_equal(nan, numpy.isnan(efh[t]))      # inf - inf: NaN on both sides (payload is not compared)
+        assert_bitwise(numpy.where(nan, 0., efh[t]), numpy.where(nan, 0., ref), f't={t}')
+        ninf += int(numpy.isinf(ref).sum() + nan.sum())
+    assert ninf > 0
+
+
 def test_k2_fill_value(gpu, oracle):
     import torch
     rng = numpy.random.default_rng(5)
@@ -402,6 +439,10 @@ def test_padded_level_planes(gpu, oracle, dtype):
     u, v = g.uv(SF_C2)
     u, v = u.astype(dtype), v.astype(dtype)
     u[:, :, 100:120, 50:90] = numpy.nan
+    if dtype == numpy.float32:                  # denormals and signed zeros through the bit-shuffle conversion
+        u[:, ::2, 10:14, 5:25] = numpy.float32(1.0e-41)
+        v[:, ::3, 30:34, 5:25] = numpy.float32(-0.0)
+        v[:, 1::3, 30:34, 5:25] = -numpy.finfo(numpy.float32).tiny
     ncell = nx * ny
     pad = 4 if dtype == numpy.float64 else 8
     ld = (ncell + pad - 1) // pad * pad

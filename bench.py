@@ -88,6 +88,15 @@ class ClockSampler(object):
                                          stdout=open(self.path, 'w'), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
+            return
+        t0 = time.time()            # nvidia-smi takes a few 100 ms to print its first sample: wait for it, so that a
+        while time.time() - t0 < 3.0:   # short timed region (float32 storage: 0.2 s) is not over before it starts
+            try:
+                if os.path.getsize(self.path) > 0:
+                    break
+            except OSError:
+                break
+            time.sleep(0.02)
 
     def stop(self, t_begin=None, t_end=None):
         """median SM clock / reasons of the samples taken between t_begin and t_end (time.time()); when the timed
@@ -376,8 +385,7 @@ def run_b200(args):
     if bal is not None:
         k2_bytes = 2.0 * esize * syn.units_per_step() * (bal['b1'] - bal['b0']) / bal['npanels']
     achieved = k2_bytes / (k2_ms * 1e-3) / 1e9
-    fused_used = (not args.classic) and args.dtype == 'f64' and (
-        syn.ncell * 16 <= (args.ring_slot_mb or 8) * (1 << 20) or padded or syn.ncell % 4 == 0)
+    fused_used = (not args.classic) and _lib.get_option(_lib.NFX_OPT_LAST_SERIES_PATH) == 1   # what the library did
     roofline = {'bound': 'hbm', 'kernel': 'k2_edgeflux_ldg' if args.classic else
                 ('k23_fused (persistent K2+K3, one launch per step; algorithmic bytes = the u/v stream)' if fused_used
                  else 'k2_edgeflux_ldg + k3_integrate (timed together, two launches)'),

@@ -16,6 +16,8 @@ NFX_ORDER_LIST, NFX_ORDER_MAP = 0, 1
 NFX_K2_AUTO, NFX_K2_LDG, NFX_K2_TMA, NFX_K2_LDG128 = 0, 1, 2, 3
 NFX_OPT_K2_VARIANT, NFX_OPT_K2_UNROLL, NFX_OPT_K2_BLOCK, NFX_OPT_FAST_SERIES, NFX_OPT_RING_SLOT_MB = 1, 2, 3, 4, 5
 NFX_OPT_K2_ALU_MASK = 6
+NFX_OPT_FUSED_F32_SHAPE = 7
+NFX_OPT_LAST_SERIES_PATH = 8
 
 c_i64 = ctypes.c_int64
 c_int = ctypes.c_int
@@ -122,3 +124,9 @@ def launch_count():
 
 def set_option(option, value):
     call('nfx_set_option', option, value)
+
+
+def get_option(option):
+    v = ctypes.c_int()
+    call('nfx_get_option', option, ctypes.byref(v))
+    return v.value

@@ -187,6 +187,7 @@ void flux_series_fused(PliDev& p, const PanelPlan& pl, const void* u, const void
                        int64_t batch_begin, int64_t batch_end, double* out, cudaStream_t s);
 int fused_tile_columns(int dtype, const void* u, const void* v, int64_t ncell, int64_t ld, int64_t panel);
 int fused_error_flag(PliDev& p, cudaStream_t s);
+extern int g_fused_f32_shape;
 int k3_group_for(int64_t nnz, int64_t nrows);
 
 }  // namespace nfx

@@ -26,6 +26,8 @@
 
 namespace nfx {
 
+int g_fused_f32_shape = 0;   // NFX_OPT_FUSED_F32_SHAPE (tuning knob)
+
 namespace {
 
 using namespace dev;
@@ -83,7 +85,7 @@ __device__ __forceinline__ bool cta_wait(const int* flag, int target, int* err, 
 }
 
 template <typename T, int VEC, int UNROLL>
-__global__ void __launch_bounds__(kFusedBlock)
+__global__ void __launch_bounds__(kFusedBlock, (sizeof(T) == 4 && VEC == 8 && UNROLL == 5) ? 3 : (sizeof(T) == 4 ? 4 : 1))
 k23_fused(const FusedArgs a) {
     extern __shared__ double s_dz[];
     __shared__ int s_item;
@@ -271,28 +273,30 @@ k23_fused(const FusedArgs a) {
     }
 }
 
-template <typename T, int VEC>
+template <typename T, int VEC, int UNROLL>
 int fused_grid() {
     static int grid = 0;
     if (grid == 0) {
         int dev = 0, sms = 0, per_sm = 0;
         NFX_CUDA(cudaGetDevice(&dev));
         NFX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        NFX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k23_fused<T, VEC, 5>, kFusedBlock,
+        NFX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k23_fused<T, VEC, UNROLL>, kFusedBlock,
                                                                sizeof(double) * 256));
         grid = sms * std::max(per_sm, 1);
     }
     return grid;
 }
 
-template <typename T, int VEC>
+template <typename T, int VEC, int UNROLL>
 void launch_fused(const FusedArgs& a, cudaStream_t s) {
-    k23_fused<T, VEC, 5><<<fused_grid<T, VEC>(), kFusedBlock, sizeof(double) * a.nz * 2, s>>>(a);
+    k23_fused<T, VEC, UNROLL><<<fused_grid<T, VEC, UNROLL>(), kFusedBlock, sizeof(double) * a.nz * 2, s>>>(a);
 }
 
-int fused_grid_for(int dtype, int vec) {
-    if (dtype == NFX_F64) return vec == 4 ? fused_grid<double, 4>() : vec == 2 ? fused_grid<double, 2>() : fused_grid<double, 1>();
-    return vec == 8 ? fused_grid<float, 8>() : vec == 4 ? fused_grid<float, 4>() : fused_grid<float, 1>();
+int fused_grid_for(int dtype, int vec, int unroll) {
+    if (dtype == NFX_F64)
+        return vec == 4 ? fused_grid<double, 4, 5>() : vec == 2 ? fused_grid<double, 2, 5>() : fused_grid<double, 1, 5>();
+    if (unroll == 3) return vec == 8 ? fused_grid<float, 8, 3>() : fused_grid<float, 4, 3>();
+    return vec == 8 ? fused_grid<float, 8, 5>() : vec == 4 ? fused_grid<float, 4, 5>() : fused_grid<float, 1, 5>();
 }
 
 }  // namespace
@@ -327,7 +331,15 @@ void flux_series_fused(PliDev& p, const PanelPlan& pl, const void* u, const void
                        int64_t batch_begin, int64_t batch_end, double* out, cudaStream_t s) {
     const int64_t ncell = p.grid->ncell;
     const int M = p.ntransects;
-    const int vec = fused_tile_columns(dtype, u, v, ncell, ld, pl.panel_cells);
+    int vec = fused_tile_columns(dtype, u, v, ncell, ld, pl.panel_cells);
+    int unroll = 5;
+    if (dtype != NFX_F64 && vec >= 4) {
+        // float32 storage: 128-bit loads x 5 levels at 64 registers (4 CTAs per SM) beat 256-bit loads at 80
+        // registers (3 CTAs per SM) by 20 % (profiles/r1_f32_alu_sweep.md); the option is a tuning knob
+        const int shape = g_fused_f32_shape > 0 ? g_fused_f32_shape : 45;   // 10 * vector width + unroll
+        vec = std::min(vec, shape / 10 >= 8 ? 8 : 4);
+        unroll = shape % 10 == 3 ? 3 : 5;
+    }
     FusedArgs a;
     a.u = u;
     a.v = v;
@@ -363,7 +375,7 @@ void flux_series_fused(PliDev& p, const PanelPlan& pl, const void* u, const void
     NFX_REQUIRE((int64_t)(a.nbatches + 1) * (a.ntiles + a.nk3) < 2000000000ll, "fused pass: too many work items");
     // enough slots that every resident CTA finds a K2 tile while the K3 of older batches drains (x2 margin),
     // but no more than ~64 MB of evict-last lines in the 126 MB L2
-    const int resident = fused_grid_for(dtype, vec);
+    const int resident = fused_grid_for(dtype, vec, unroll);
     int slots = (2 * resident + a.ntiles - 1) / a.ntiles + 1;
     const int64_t cap = std::max<int64_t>(3, ((int64_t)64 << 20) / (a.slot_elems * 8));
     slots = (int)std::min<int64_t>(std::max(slots, 3), cap);
@@ -392,13 +404,15 @@ void flux_series_fused(PliDev& p, const PanelPlan& pl, const void* u, const void
     a.sync = p.fused_sync.p;
     NFX_CUDA(cudaMemsetAsync(a.sync, 0, sizeof(int) * (2 + 2 * a.nbatches), s));
     if (dtype == NFX_F64) {
-        if (vec == 4) launch_fused<double, 4>(a, s);
-        else if (vec == 2) launch_fused<double, 2>(a, s);
-        else launch_fused<double, 1>(a, s);
+        if (vec == 4) launch_fused<double, 4, 5>(a, s);
+        else if (vec == 2) launch_fused<double, 2, 5>(a, s);
+        else launch_fused<double, 1, 5>(a, s);
     } else {
-        if (vec == 8) launch_fused<float, 8>(a, s);
-        else if (vec == 4) launch_fused<float, 4>(a, s);
-        else launch_fused<float, 1>(a, s);
+        if (unroll == 3 && vec == 8) launch_fused<float, 8, 3>(a, s);
+        else if (unroll == 3 && vec == 4) launch_fused<float, 4, 3>(a, s);
+        else if (vec == 8) launch_fused<float, 8, 5>(a, s);
+        else if (vec == 4) launch_fused<float, 4, 5>(a, s);
+        else launch_fused<float, 1, 5>(a, s);
     }
     count_launch();
     NFX_CUDA(cudaGetLastError());

@@ -25,6 +25,7 @@ def main():
     ap.add_argument('--nx', type=int, default=0)
     ap.add_argument('--dtype', default='f64', choices=['f64', 'f32'])
     ap.add_argument('--pad', type=int, default=0)
+    ap.add_argument('--f32-shapes', default='', help='fused float32 kernel shapes to compare, e.g. 85,45,83,43')
     a = ap.parse_args()
     dev = torch.device('cuda', 0)
     syn = synth.make(a.workload, **({'nx': a.nx} if a.nx else {}))
@@ -44,6 +45,9 @@ def main():
     modes = [('classic', dict(eflux=eflux), {})]
     for mb in [int(x) for x in a.slots.split(',')]:
         modes.append((f'fused slot={mb}MB', {}, {_lib.NFX_OPT_RING_SLOT_MB: mb, _lib.NFX_OPT_FAST_SERIES: 2}))
+    for shape in [int(x) for x in a.f32_shapes.split(',') if x]:
+        modes.append((f'fused f32 shape={shape}', {}, {_lib.NFX_OPT_RING_SLOT_MB: 8, _lib.NFX_OPT_FAST_SERIES: 2,
+                                                         _lib.NFX_OPT_FUSED_F32_SHAPE: shape}))
     times = {m[0]: [] for m in modes}
     ref = None
     for rnd in range(a.rounds):

@@ -18,6 +18,7 @@ NFX_OPT_K2_VARIANT, NFX_OPT_K2_UNROLL, NFX_OPT_K2_BLOCK, NFX_OPT_FAST_SERIES, NF
 NFX_OPT_K2_ALU_MASK = 6
 NFX_OPT_FUSED_F32_SHAPE = 7
 NFX_OPT_LAST_SERIES_PATH = 8
+NFX_OPT_FUSED_ORDER = 9
 
 c_i64 = ctypes.c_int64
 c_int = ctypes.c_int

@@ -125,6 +125,9 @@ struct PliDev {
     PanelPlan plan[2];            // per summation order
     DevBuf<double> ring, partial;  // L2-resident eflux ring and per-panel partial sums of the fused pass
     DevBuf<int> fused_sync;        // work counter, error flag, per-batch completion counters
+    DevBuf<int> batch_map;         // fused pass: order in which the (time step, panel) batches are visited
+    std::vector<int> h_batch_map;
+    int64_t batch_map_key[4] = {-1, -1, -1, -1};   // (batch_begin, batch_end, npanels, order) of the cached map
     std::vector<int64_t> h_sub_offsets, h_map_offsets;
     // scratch reused by the host-buffer entry points
     DevBuf<double> scratch_data, scratch_res;
@@ -188,6 +191,7 @@ void flux_series_fused(PliDev& p, const PanelPlan& pl, const void* u, const void
 int fused_tile_columns(int dtype, const void* u, const void* v, int64_t ncell, int64_t ld, int64_t panel);
 int fused_error_flag(PliDev& p, cudaStream_t s);
 extern int g_fused_f32_shape;
+extern int g_fused_order;
 int k3_group_for(int64_t nnz, int64_t nrows);
 
 }  // namespace nfx

@@ -27,6 +27,8 @@
 namespace nfx {
 
 int g_fused_f32_shape = 0;   // NFX_OPT_FUSED_F32_SHAPE (tuning knob)
+int g_fused_order = 3;       // NFX_OPT_FUSED_ORDER: bit 0 = visit the batches panel-major, bit 1 = K3 gathers unrolled x8
+                             // (same-box A/B, profiles/r1_fused_order_ab.md: -3 % and -1 % time on multi-panel grids)
 
 namespace {
 
@@ -52,7 +54,8 @@ struct FusedArgs {
     int* sync;              // [0] work counter, [1] error flag, [2 .. 2+nb) K2 tiles done, [2+nb .. 2+2nb) K3 items done
     int64_t ncell, ld, panel, slot_elems;   // ld = cells per level plane in memory (>= ncell)
     int nt, nz, ntransects, npanels, nbatches, ntiles, nk3, ring_slots;
-    int batch_begin;        // first (time step, panel) batch of this call: batch index = batch_begin + b
+    const int* batch_map;   // (nbatches) global batch index t * npanels + q of the b-th batch visited
+    int k3_unroll8;
     double scale, fill;
     int use_scale, has_fill;
 };
@@ -133,8 +136,9 @@ k23_fused(const FusedArgs a) {
             const int b = bb;
             if (b >= a.nbatches) continue;
             if (b >= a.ring_slots && !cta_wait(k3done + (b - a.ring_slots), a.nk3, err, &s_ok)) break;
-            const int64_t t = (a.batch_begin + b) / a.npanels;
-            const int q = (a.batch_begin + b) - (int)t * a.npanels;
+            const int gb = a.batch_map[b];
+            const int64_t t = gb / a.npanels;
+            const int q = gb - (int)t * a.npanels;
             const int64_t pc0 = (int64_t)q * a.panel;
             const int64_t pc = min(a.panel, a.ncell - pc0);
             const int64_t cl = ((int64_t)r * kFusedBlock + threadIdx.x) * VEC;   // column inside the panel
@@ -248,8 +252,9 @@ k23_fused(const FusedArgs a) {
             if (b < 0) continue;
             if (!cta_wait(k2done + b, a.ntiles, err, &s_ok)) break;
             __threadfence();
-            const int64_t t = (a.batch_begin + b) / a.npanels;
-            const int q = (a.batch_begin + b) - (int)t * a.npanels;
+            const int gb = a.batch_map[b];
+            const int64_t t = gb / a.npanels;
+            const int q = gb - (int)t * a.npanels;
             {
                 // one warp per sub-row (<= kSubRow entries): lane-strided partial sums, fixed shuffle tree
                 const int64_t sr = a.panel_sr[q] + (int64_t)(r - a.ntiles) * kWarps + wid;
@@ -257,8 +262,13 @@ k23_fused(const FusedArgs a) {
                     const int64_t r0 = a.sr_ptr[sr], r1 = a.sr_ptr[sr + 1];
                     const double* d = a.ring + (int64_t)(b % a.ring_slots) * a.slot_elems;
                     double acc = 0.0;
+                    if (a.k3_unroll8) {
+#pragma unroll 8
+                        for (int64_t n = r0 + lane; n < r1; n += 32) acc = fma(a.w[n], __ldcg(d + a.idx[n]), acc);
+                    } else {
 #pragma unroll 4
-                    for (int64_t n = r0 + lane; n < r1; n += 32) acc = fma(a.w[n], __ldcg(d + a.idx[n]), acc);
+                        for (int64_t n = r0 + lane; n < r1; n += 32) acc = fma(a.w[n], __ldcg(d + a.idx[n]), acc);
+                    }
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
                     if (lane == 0) a.out[t * a.nsr + sr] = acc;
@@ -356,8 +366,8 @@ void flux_series_fused(PliDev& p, const PanelPlan& pl, const void* u, const void
     a.npanels = pl.npanels;
     NFX_REQUIRE(batch_begin >= 0 && batch_begin <= batch_end && batch_end <= (int64_t)nt * pl.npanels,
                 "fused pass: bad batch range");
-    a.batch_begin = (int)batch_begin;
     a.nbatches = (int)(batch_end - batch_begin);
+    a.k3_unroll8 = (g_fused_order >> 1) & 1;
     const int64_t item_cols = (int64_t)kFusedBlock * vec;
     a.ntiles = (int)((std::min(pl.panel_cells, ncell) + item_cols - 1) / item_cols);
     a.nk3 = std::max(1, (pl.max_sr_per_panel + kWarps - 1) / kWarps);
@@ -399,6 +409,27 @@ void flux_series_fused(PliDev& p, const PanelPlan& pl, const void* u, const void
         zero_rows(batch_end, (int64_t)nt * pl.npanels);
     }
     if (a.nbatches == 0) return;
+    {
+        // visiting order of the batches.  Time-major: (t, q) as numbered.  Panel-major: all local time steps of
+        // panel 0, then of panel 1, ... -- the panel's slice of the CSR (weights, indices) and of the metric
+        // arrays is reused from L2 for every time step instead of being re-read from HBM once per step.
+        const int order = g_fused_order & 1;
+        const int64_t key[4] = {batch_begin, batch_end, pl.npanels, order};
+        if (!std::equal(key, key + 4, p.batch_map_key) || p.batch_map.p == nullptr) {
+            p.h_batch_map.resize((size_t)a.nbatches);
+            for (int b = 0; b < a.nbatches; ++b) p.h_batch_map[(size_t)b] = (int)(batch_begin + b);
+            if (order == 1 && pl.npanels > 1) {
+                const int np = pl.npanels;
+                std::stable_sort(p.h_batch_map.begin(), p.h_batch_map.end(),
+                                 [np](int x, int y) { return x % np < y % np; });
+            }
+            p.batch_map.ensure((size_t)a.nbatches);
+            NFX_CUDA(cudaMemcpyAsync(p.batch_map.p, p.h_batch_map.data(), sizeof(int) * (size_t)a.nbatches,
+                                     cudaMemcpyHostToDevice, s));
+            std::copy(key, key + 4, p.batch_map_key);
+        }
+        a.batch_map = p.batch_map.p;
+    }
     p.fused_sync.ensure((size_t)(2 + 2 * a.nbatches));
     a.ring = p.ring.p;
     a.sync = p.fused_sync.p;

@@ -467,12 +467,18 @@ def test_padded_level_planes(gpu, oracle, dtype):
             s_dense = p.fluxSeries(dense[0], dense[1], th, a1, a2).cpu().numpy()
             s_pad = p.fluxSeries(up, vp, th, a1, a2).cpu().numpy()
             assert numpy.array_equal(s_pad, s_dense)
+            if mode == 2:                           # the visiting order of the batches cannot change a bit
+                for order in (0, 1, 2):
+                    _lib.set_option(_lib.NFX_OPT_FUSED_ORDER, order)
+                    assert numpy.array_equal(p.fluxSeries(up, vp, th, a1, a2).cpu().numpy(), s_pad)
+                _lib.set_option(_lib.NFX_OPT_FUSED_ORDER, 3)
         ref = oracle.flux_series(P, transects, u.astype(numpy.float64), v.astype(numpy.float64), g.thickness(), use_c=True)
         scale = _l1_scale(oracle, P, transects, u.astype(numpy.float64), v.astype(numpy.float64), g.thickness(), arc, False)
         assert (numpy.abs(s_pad - ref) <= FLUX_RTOL * scale + 1e-300).all()
     finally:
         _lib.set_option(_lib.NFX_OPT_RING_SLOT_MB, 8)
         _lib.set_option(_lib.NFX_OPT_FAST_SERIES, 1)
+        _lib.set_option(_lib.NFX_OPT_FUSED_ORDER, 3)
     with pytest.raises(ValueError):
         gpu.edgeFluxAssemble(up.transpose(0, 1), vp.transpose(0, 1), th, a1, a2)
 

@@ -25,6 +25,8 @@ def main():
     ap.add_argument('--nx', type=int, default=0)
     ap.add_argument('--dtype', default='f64', choices=['f64', 'f32'])
     ap.add_argument('--pad', type=int, default=0)
+    ap.add_argument('--base-order', type=int, default=0, help='NFX_OPT_FUSED_ORDER of the modes that do not set it')
+    ap.add_argument('--orders', default='', help='fused batch visiting orders / K3 unroll to compare (NFX_OPT_FUSED_ORDER), e.g. 0,1,2,3')
     ap.add_argument('--f32-shapes', default='', help='fused float32 kernel shapes to compare, e.g. 85,45,83,43')
     a = ap.parse_args()
     dev = torch.device('cuda', 0)
@@ -48,11 +50,17 @@ def main():
     for shape in [int(x) for x in a.f32_shapes.split(',') if x]:
         modes.append((f'fused f32 shape={shape}', {}, {_lib.NFX_OPT_RING_SLOT_MB: 8, _lib.NFX_OPT_FAST_SERIES: 2,
                                                          _lib.NFX_OPT_FUSED_F32_SHAPE: shape}))
+    for o in [int(x) for x in a.orders.split(',') if x]:
+        modes.append((f'fused order={o}', {}, {_lib.NFX_OPT_RING_SLOT_MB: 8, _lib.NFX_OPT_FAST_SERIES: 2,
+                                               _lib.NFX_OPT_FUSED_ORDER: o}))
     times = {m[0]: [] for m in modes}
     ref = None
     for rnd in range(a.rounds):
         for name, kw, opts in modes:
-            for k, val in opts.items():
+            full = {_lib.NFX_OPT_RING_SLOT_MB: 8, _lib.NFX_OPT_FAST_SERIES: 2, _lib.NFX_OPT_FUSED_F32_SHAPE: 0,
+                    _lib.NFX_OPT_FUSED_ORDER: a.base_order}
+            full.update(opts)                       # every mode sets every knob: nothing leaks from the mode before
+            for k, val in full.items():
                 _lib.set_option(k, val)
             p.fluxSeries(u, v, th, a1, a2, out=out, **kw)
             torch.cuda.synchronize()

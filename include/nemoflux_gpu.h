@@ -37,6 +37,10 @@ extern "C" {
 /* storage type of uo/vo */
 #define NFX_F64 0   /* datagen.py:9 writes float64 */
 #define NFX_F32 1   /* real NEMO output            */
+/* OR into dtype for nfx_flux_series_host only: the host buffers hold BIG-ENDIAN values, i.e. the bytes of a
+ * NetCDF classic file as stored on disk (what scipy.io.netcdf_file memory-maps).  The raw bytes are uploaded and the
+ * byte order is swapped on the device, instead of a conversion pass over the data on the host CPU. */
+#define NFX_BIG_ENDIAN 0x100
 
 /* summation order of the transect integral */
 #define NFX_ORDER_LIST 0  /* emission order: sub-segment by sub-segment, edges 0..3          */

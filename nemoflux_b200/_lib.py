@@ -12,6 +12,7 @@ LIB_PATH = os.path.join(_HERE, 'libnemoflux_gpu.so')
 NFX_OK = 0
 NFX_CELL_BY_CELL_DATA = 0
 NFX_F64, NFX_F32 = 0, 1
+NFX_BIG_ENDIAN = 0x100
 NFX_ORDER_LIST, NFX_ORDER_MAP = 0, 1
 NFX_K2_AUTO, NFX_K2_LDG, NFX_K2_TMA, NFX_K2_LDG128 = 0, 1, 2, 3
 NFX_OPT_K2_VARIANT, NFX_OPT_K2_UNROLL, NFX_OPT_K2_BLOCK, NFX_OPT_FAST_SERIES, NFX_OPT_RING_SLOT_MB = 1, 2, 3, 4, 5

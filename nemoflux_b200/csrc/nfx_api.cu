@@ -675,14 +675,16 @@ int nfx_flux_series(nfx_pli** self, const void* u, const void* v, int dtype, con
 }
 
 // ---- everything from host buffers: double-buffered H2D staging, K2+K3 per chunk --------------------------
-int nfx_flux_series_host(nfx_pli** self, const void* u, const void* v, int dtype, const double* thickness,
+int nfx_flux_series_host(nfx_pli** self, const void* u, const void* v, int dtype_flags, const double* thickness,
                          const double* arc1, const double* arc2, int nt, int nz, int sverdrup, double fill, int order,
                          int chunk_steps, double* series) {
     return guarded([&] {
         NFX_REQUIRE(self && *self, "NULL handle");
         NFX_REQUIRE(u && v && thickness && arc1 && arc2 && series, "NULL pointer");
         NFX_REQUIRE(nt >= 0 && nz > 0, "bad sizes");
-        NFX_REQUIRE(dtype == NFX_F64 || dtype == NFX_F32, "dtype must be NFX_F64 or NFX_F32");
+        const bool big_endian = (dtype_flags & NFX_BIG_ENDIAN) != 0;
+        const int dtype = dtype_flags & ~NFX_BIG_ENDIAN;
+        NFX_REQUIRE(dtype == NFX_F64 || dtype == NFX_F32, "dtype must be NFX_F64 or NFX_F32 (optionally | NFX_BIG_ENDIAN)");
         PliDev& p = (*self)->d;
         NFX_REQUIRE(p.grid, "setGrid was not called");
         DeviceGuard g(p.grid->device);
@@ -728,6 +730,10 @@ int nfx_flux_series_host(nfx_pli** self, const void* u, const void* v, int dtype
             const unsigned char* hv = (const unsigned char*)v + (size_t)t0 * step_bytes;
             NFX_CUDA(cudaMemcpyAsync(p.stage_u[slot].p, hu, step_bytes * n, cudaMemcpyHostToDevice, cs));
             NFX_CUDA(cudaMemcpyAsync(p.stage_v[slot].p, hv, step_bytes * n, cudaMemcpyHostToDevice, cs));
+            if (big_endian) {   // file bytes as stored: swap on the device, behind the copy on the copy stream
+                bswap_inplace(p.stage_u[slot].p, step_bytes * n / esize, (int)esize, cs);
+                bswap_inplace(p.stage_v[slot].p, step_bytes * n / esize, (int)esize, cs);
+            }
             NFX_CUDA(cudaEventRecord(p.ev_ready[slot], cs));
             NFX_CUDA(cudaStreamWaitEvent(ks, p.ev_ready[slot], 0));
             if (fused) {

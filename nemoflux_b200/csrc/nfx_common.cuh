@@ -174,6 +174,7 @@ void edgeflux_assemble_panel(const void* u, const void* v, int dtype, const doub
                              const void* e3u = nullptr, const void* e3v = nullptr, int64_t e3_tstride = 0);
 void edgeflux_to_cell_by_cell(const double* eflux, int nt, int ny, int nx, double* iv, cudaStream_t s);
 void edgeflux_absmax(const double* eflux, int nt, int64_t ncell, double* result_host, cudaStream_t s);
+void bswap_inplace(void* p, size_t n, int esize, cudaStream_t s);   // big-endian file bytes -> native, on the device
 
 // K3 (nfx_k3_reduce.cu)
 void csr_integrate(const Csr& c, int ntransects, const double* data, int64_t stride_t, int nt, double* series,

@@ -472,7 +472,47 @@ __global__ void k_absmax(const double* __restrict__ x, int64_t n, unsigned long 
     if ((threadIdx.x & 31) == 0) atomicMax(out, (unsigned long long)__double_as_longlong(m));
 }
 
+// in-place byte-order swap of n elements of 4 or 8 bytes, 16 bytes per thread and iteration
+template <int ESIZE>
+__global__ void k_bswap(uint4* __restrict__ p, int64_t nvec, unsigned char* __restrict__ tail, int ntail_elems) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+        uint4 x = p[i];
+        x.x = __byte_perm(x.x, 0, 0x0123);
+        x.y = __byte_perm(x.y, 0, 0x0123);
+        x.z = __byte_perm(x.z, 0, 0x0123);
+        x.w = __byte_perm(x.w, 0, 0x0123);
+        if (ESIZE == 8) x = make_uint4(x.y, x.x, x.w, x.z);
+        p[i] = x;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < ntail_elems) {   // fewer than 16 bytes left over
+        unsigned char* q = tail + threadIdx.x * ESIZE;
+#pragma unroll
+        for (int b = 0; b < ESIZE / 2; ++b) {
+            const unsigned char c = q[b];
+            q[b] = q[ESIZE - 1 - b];
+            q[ESIZE - 1 - b] = c;
+        }
+    }
+}
+
 }  // namespace
+
+void bswap_inplace(void* p, size_t n, int esize, cudaStream_t s) {
+    NFX_REQUIRE(esize == 4 || esize == 8, "bswap: element size must be 4 or 8");
+    NFX_REQUIRE(((uintptr_t)p & 15) == 0, "bswap: buffer must be 16-byte aligned");
+    if (n == 0) return;
+    const size_t bytes = n * (size_t)esize;
+    const int64_t nvec = (int64_t)(bytes / 16);
+    unsigned char* tail = (unsigned char*)p + (size_t)nvec * 16;
+    const int ntail = (int)((bytes - (size_t)nvec * 16) / (size_t)esize);
+    const int grid = (int)std::min<int64_t>(148 * 8, std::max<int64_t>(1, (nvec + 255) / 256));
+    if (esize == 8)
+        k_bswap<8><<<grid, 256, 0, s>>>((uint4*)p, nvec, tail, ntail);
+    else
+        k_bswap<4><<<grid, 256, 0, s>>>((uint4*)p, nvec, tail, ntail);
+    count_launch();
+    NFX_CUDA(cudaGetLastError());
+}
 
 // One launch over `ncols` adjacent columns (a panel of the grid, pointers already offset to its first column)
 // and `nt` time steps; ld = cells per level plane.  eflux: (nt, 2*ncols).

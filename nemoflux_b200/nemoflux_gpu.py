@@ -255,8 +255,9 @@ class PolylineIntegral(object):
 
         u, v: (nt, nz, ny, nx) [or (nz, ny, nx)] float64/float32, either cuda tensors (device path: K2+K3 on
         the current stream, returns a cuda tensor) or host numpy arrays / CPU tensors (streams time chunks
-        through double-buffered device staging, returns a numpy array).  thickness (nz), arc1/arc2 (ncell)
-        on the same side as u, v.  Needs Grid.setCGridShape before computeWeights.
+        through double-buffered device staging, returns a numpy array; big-endian numpy arrays -- a NetCDF classic
+        file as memory-mapped -- are uploaded as stored and byte-swapped on the device).  thickness (nz),
+        arc1/arc2 (ncell) on the same side as u, v.  Needs Grid.setCGridShape before computeWeights.
 
         batch_range=(b0, b1) (device tensors only): run only the batches b = t*npanels + q in [b0, b1) and return
         PARTIAL sums -- the building block of the balanced multi-GPU sharding in nemoflux_b200.dist.
@@ -340,6 +341,9 @@ class PolylineIntegral(object):
             u, v = u[None], v[None]
         if u.ndim != 4 or u.shape != v.shape or u.dtype != v.dtype:
             raise ValueError("uo/vo shape does not match (t, z, y, x) or (z, y, x)")
+        code = _dtype_code(u.dtype.newbyteorder('=').name)
+        if not u.dtype.isnative:        # bytes as stored in a NetCDF classic file: swapped on the device
+            code |= _lib.NFX_BIG_ENDIAN
         if not (u.flags.c_contiguous and v.flags.c_contiguous):
             u, v = numpy.ascontiguousarray(u), numpy.ascontiguousarray(v)
         nt, nz, ny, nx = u.shape
@@ -351,7 +355,7 @@ class PolylineIntegral(object):
             raise ValueError('thickness/arc1/arc2 sizes do not match uo')
         m = self.getNumberOfTransects()
         out = numpy.zeros((nt, m), numpy.float64)
-        _lib.call('nfx_flux_series_host', ctypes.byref(self._h), _np_ptr(u), _np_ptr(v), _dtype_code(str(u.dtype)),
+        _lib.call('nfx_flux_series_host', ctypes.byref(self._h), _np_ptr(u), _np_ptr(v), code,
                   _np_ptr(th), _np_ptr(a1), _np_ptr(a2), nt, nz, int(bool(sverdrup)), float(fill), _ORDERS[order],
                   int(chunk_steps), _np_ptr(out))
         del keep

@@ -422,6 +422,15 @@ def test_fast_series_path_matches_classic(gpu, oracle, slot_mb, shape):
             assert_bitwise(ef[nt - 1].cpu().numpy(), numpy.concatenate([eU, eV]), 'eflux')
             host = p.fluxSeries(u, v, th, arc[:, 1].copy(), arc[:, 2].copy(), order=order, chunk_steps=4)
             assert numpy.array_equal(host, fast)
+            # big-endian host buffers (a NetCDF classic file as stored): swapped on the device, same bits
+            host_be = p.fluxSeries(u.astype('>f8'), v.astype('>f8'), th, arc[:, 1].copy(), arc[:, 2].copy(),
+                                   order=order, chunk_steps=4)
+            assert numpy.array_equal(host_be, host)
+            h32 = p.fluxSeries(u.astype('<f4'), v.astype('<f4'), th, arc[:, 1].copy(), arc[:, 2].copy(),
+                               order=order, chunk_steps=3)
+            h32_be = p.fluxSeries(u.astype('>f4'), v.astype('>f4'), th, arc[:, 1].copy(), arc[:, 2].copy(),
+                                  order=order, chunk_steps=3)
+            assert numpy.array_equal(h32_be, h32)
     finally:
         _lib.set_option(_lib.NFX_OPT_RING_SLOT_MB, 8)
         _lib.set_option(_lib.NFX_OPT_FAST_SERIES, 1)

@@ -42,6 +42,8 @@ def main():
     ap.add_argument('--nt', type=int, default=8)
     ap.add_argument('--dtype', default='float64')
     ap.add_argument('--dir', default='/tmp/nfx_e2e')
+    ap.add_argument('--chunk-steps', default='0', help='comma list; the first is the reported one (0 = default)')
+    ap.add_argument('--reps', type=int, default=5)
     ap.add_argument('--out', default='gpurun_out/file_e2e.json')
     a = ap.parse_args()
     syn = synth.make(a.workload)
@@ -58,10 +60,17 @@ def main():
     t0 = time.perf_counter()
     fld = Field(T, U, V, syn.transects, verbose=False)
     t_init = time.perf_counter() - t0
-    fld.fluxSeries()                                      # warm-up (page cache, allocations)
-    t0 = time.perf_counter()
-    s_gpu = fld.fluxSeries()
-    t_gpu = time.perf_counter() - t0
+    sweep = {}
+    for cs in [int(x) for x in a.chunk_steps.split(',')]:
+        fld.fluxSeries(chunk_steps=cs)                    # warm-up (page cache, allocations)
+        ts = []
+        for _ in range(a.reps):
+            t0 = time.perf_counter()
+            s_gpu = fld.fluxSeries(chunk_steps=cs)
+            ts.append(time.perf_counter() - t0)
+        sweep[cs] = dict(median_s=float(numpy.median(ts)), min_s=min(ts))
+        print('chunk_steps', cs, sweep[cs], flush=True)
+    t_gpu = sweep[int(a.chunk_steps.split(',')[0])]['median_s']
 
     # CPU: the reference's loop restated (oracle), reading the same files through the same reader
     from oracle import oracle as O
@@ -89,6 +98,7 @@ def main():
     err = float(numpy.abs(s_gpu - s_cpu).max() / numpy.abs(s_cpu).max())
     res = dict(workload=a.workload, nt=a.nt, dtype=a.dtype, transects=len(syn.transects),
                file_bytes=int(os.path.getsize(U) + os.path.getsize(V)), write_s=t_write,
+               chunk_sweep=sweep,
                gpu=dict(init_s=t_init, series_s=t_gpu, units_per_s=units / t_gpu,
                         file_gbs=(os.path.getsize(U) + os.path.getsize(V)) / t_gpu / 1e9),
                cpu=dict(init_s=t_cpu_init, series_s=t_cpu, units_per_s=units / t_cpu, cores=os.cpu_count()),

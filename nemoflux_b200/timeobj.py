@@ -1,24 +1,32 @@
-"""Time axis lookup -- mirror of nemoflux/timeobj.py (labels only, not on the compute path).
+"""Time axis labels (not on the compute path).
 
-The time variable is the one whose standard_name is 'time' or whose long_name is 'Time axis'
-(timeobj.py:8-13).  Mock data from datagen has none; unlike the reference (which then raises in
-getTimeAsString, timeobj.py:31-33) the index is used as the label.
+Interface of nemoflux/timeobj.py: TimeObj(nc) finds the variable whose standard_name is 'time' or whose long_name
+is 'Time axis' (timeobj.py:8-13); getValues / getSize / getTimeAsDate / getTimeAsString.  The reference gets
+calendar objects from xarray; here the raw numbers are decoded from the CF units ('<unit> since Y-M-D').  Mock
+data from datagen has no time axis: the reference raises in getTimeAsString (timeobj.py:31-33), this class labels
+the step with its index instead.
 """
-from datetime import datetime, timedelta
+import datetime
 import re
+
+_SECONDS = {'seconds': 1.0, 'minutes': 60.0, 'hours': 3600.0, 'days': 86400.0}
+_SINCE = re.compile(r'\s*(seconds|minutes|hours|days)\s+since\s+(\d+)-(\d+)-(\d+)')
+
+
+def _is_time_axis(var):
+    return getattr(var, 'standard_name', '') == 'time' or getattr(var, 'long_name', '') == 'Time axis'
 
 
 class TimeObj(object):
 
     def __init__(self, nc):
-        self.timeVarName = ''
-        self.timeVar = []
-        self.units = ''
-        for vName, var in nc.items():
-            if getattr(var, 'standard_name', '') == 'time' or getattr(var, 'long_name', '') == 'Time axis':
-                self.timeVarName = vName
-                self.timeVar = var[:]
-                self.units = getattr(var, 'units', '')
+        self.timeVarName, self.timeVar, self.units = '', [], ''
+        for name, var in nc.items():
+            if _is_time_axis(var):          # the last match wins, as in the reference
+                self.timeVarName, self.timeVar, self.units = name, var[:], str(getattr(var, 'units', ''))
+        since = _SINCE.match(self.units)
+        self._origin = datetime.datetime(*(int(since.group(k)) for k in (2, 3, 4))) if since else None
+        self._unit_s = _SECONDS[since.group(1)] if since else None
 
     def getValues(self):
         return self.timeVar[:]
@@ -27,18 +35,14 @@ class TimeObj(object):
         return len(self.timeVar)
 
     def getTimeAsDate(self, timeIndex):
-        """CF 'seconds|hours|days since YYYY-MM-DD ...' -> date; the index itself when there is no time axis"""
-        if len(self.timeVar) == 0:
+        """calendar date of the step, or the index itself when the file has no (decodable) time axis"""
+        if self._origin is None or len(self.timeVar) == 0:
             return timeIndex
-        m = re.match(r'\s*(seconds|minutes|hours|days)\s+since\s+(\d+)-(\d+)-(\d+)', str(self.units))
-        if not m:
-            return timeIndex
-        scale = dict(seconds=1., minutes=60., hours=3600., days=86400.)[m.group(1)]
-        t0 = datetime(int(m.group(2)), int(m.group(3)), int(m.group(4)))
-        return (t0 + timedelta(seconds=float(self.timeVar[timeIndex]) * scale)).date()
+        offset = datetime.timedelta(seconds=float(self.timeVar[timeIndex]) * self._unit_s)
+        return (self._origin + offset).date()
 
     def getTimeAsString(self, timeIndex):
-        d = self.getTimeAsDate(timeIndex)
-        if isinstance(d, int):
-            return f'time index {d}'
-        return f'{d.year}-{d.month}-{d.day}'
+        when = self.getTimeAsDate(timeIndex)
+        if isinstance(when, datetime.date):
+            return f'{when.year}-{when.month}-{when.day}'
+        return f'time index {when}'

@@ -631,6 +631,15 @@ def test_series_edge_cases(gpu, oracle):
             assert tuple(empty.shape) == (0, 2)
             one = p.fluxSeries(args[0][1:], args[1][1:], *args[2:]).cpu().numpy()
             assert numpy.array_equal(one[0], s[1])
+            # host buffers, big-endian, 703 values per chunk: the device byte swap has a tail of < 16 bytes
+            for dt in ('f8', 'f4'):
+                h_le = p.fluxSeries(u.astype('<' + dt), v.astype('<' + dt), th, arc[:, 1].copy(), arc[:, 2].copy(),
+                                    chunk_steps=1)
+                h_be = p.fluxSeries(u.astype('>' + dt), v.astype('>' + dt), th, arc[:, 1].copy(), arc[:, 2].copy(),
+                                    chunk_steps=1)
+                assert numpy.array_equal(h_le, h_be)
+                if dt == 'f8':
+                    assert numpy.array_equal(h_le, s)
     finally:
         _lib.set_option(_lib.NFX_OPT_FAST_SERIES, 1)
     with pytest.raises(ValueError):

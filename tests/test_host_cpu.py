@@ -88,6 +88,40 @@ def test_latlonreader_matches_reference_outputs(tmp_path):
     assert LatLonReader(str(p)).getLonLats().tolist() == [[-10.0, 63.0], [164.0, -46.0]]
 
 
+def test_subsetnemo_cuts_the_index_window(tmp_path):
+    """subsetNEMO.py:6-93: x/y dimensions shrunk, bounds and uo/vo cut, everything else and all attributes kept"""
+    from nemoflux_b200 import datagen, ncio, subsetnemo
+    src, dst = str(tmp_path) + '/', str(tmp_path / 'sub')
+    datagen.cli(['-s', '(1+z)*(t+1)*x*y', '--nx=24', '--ny=12', '--nz=3', '--nt=2', '--deltaDeg=20,30', '-p', src])
+    w = ncio.Writer(src + 'U2.nc')                  # a U file with a time axis, as real NEMO output has
+    with ncio.open_dataset(src + 'U.nc') as nc:
+        for name, n in (('t', 2), ('z', 3), ('y', 12), ('x', 24)):
+            w.createDimension(name, n)
+        w.createVariable('time_counter', 'float64', ('t',), attrs={'standard_name': 'time', 'units': 'days since 2000-01-01'},
+                         data=numpy.array([10., 11.]))
+        w.createVariable('uo', 'float32', ('t', 'z', 'y', 'x'), fill_value=1.e20, attrs={'units': 'm/s'},
+                         data=nc['uo'].raw().astype(numpy.float32))
+        w.setAttr('earthRadius', nc.attrs['earthRadius'])
+    w.close()
+    subsetnemo.main(['-t', src + 'T.nc', '-u', src + 'U2.nc', '-v', src + 'V.nc', '-o', dst,
+                     '--jmin=2', '--jmax=9', '--imin=5', '--imax=20'])
+    with ncio.open_dataset(src + 'T.nc') as a, ncio.open_dataset(dst + '/T.nc') as b:
+        assert b['bounds_lon'].shape == (7, 15, 4) and b['bounds_lon'].dimensions == ('y', 'x', 'nvertex')
+        assert numpy.array_equal(b['bounds_lon'][:], a['bounds_lon'][:][2:9, 5:20])
+        assert numpy.array_equal(b['bounds_lat'][:], a['bounds_lat'][:][2:9, 5:20])
+        assert numpy.array_equal(b['deptht_bounds'][:], a['deptht_bounds'][:]) and 'deptht' not in b
+    with ncio.open_dataset(src + 'U2.nc') as a, ncio.open_dataset(dst + '/U.nc') as b:
+        assert b['uo'].shape == (2, 3, 7, 15) and b['uo'].dtype.itemsize == 4 and b['uo'].units == 'm/s'
+        assert float(b['uo'].attrs['_FillValue']) == float(numpy.float32(1.e20))
+        assert numpy.array_equal(b['uo'].raw(), a['uo'].raw()[:, :, 2:9, 5:20])
+        assert numpy.array_equal(b['time_counter'][:], [10., 11.]) and b['time_counter'].standard_name == 'time'
+        assert 'timestamp' in b.attrs and 'earth radius' in b.attrs['earthRadius']
+    with ncio.open_dataset(src + 'V.nc') as a, ncio.open_dataset(dst + '/V.nc') as b:
+        assert numpy.array_equal(b['vo'].raw(), a['vo'].raw()[:, :, 2:9, 5:20])
+    with pytest.raises(ValueError):
+        subsetnemo.subset(tfile=src + 'T.nc', outputdir=dst, jmin=0, jmax=13, imin=0, imax=4, verbose=False)
+
+
 def test_datagen_cli_writes_nemo_conventions(tmp_path):
     from nemoflux_b200 import datagen, ncio
     prefix = str(tmp_path) + '/'

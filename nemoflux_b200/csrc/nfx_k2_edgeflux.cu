@@ -109,6 +109,16 @@ k2_edgeflux_ldg(const T* __restrict__ u, const T* __restrict__ v, const double* 
             const double d = E3 ? 0.0 : s_dz[(kScaled ? nz : 0) + k + q];
 #pragma unroll
             for (int e = 0; e < VEC; ++e) {
+                if (kScaled && E3) {
+                    // both factors come from float32: undo the 2^-896 of each bit shuffle with an exact multiply
+                    const double du = __dmul_rn(clean_scaled(ea[e], fill, has_fill, amax), kScaleUp);
+                    const double dv = __dmul_rn(clean_scaled(eb[e], fill, has_fill, amax), kScaleUp);
+                    const double xu = __dmul_rn(clean_scaled(a[e], fill, has_fill, amax), kScaleUp);
+                    const double xv = __dmul_rn(clean_scaled(b[e], fill, has_fill, amax), kScaleUp);
+                    su[e] = __dadd_rn(su[e], __dmul_rn(du, xu));
+                    sv[e] = __dadd_rn(sv[e], __dmul_rn(dv, xv));
+                    continue;
+                }
                 const double du = E3 ? clean<T>(ea[e], fill, has_fill) : d;
                 const double dv = E3 ? clean<T>(eb[e], fill, has_fill) : d;
                 if (kScaled) {
@@ -148,11 +158,13 @@ k2_edgeflux_ldg(const T* __restrict__ u, const T* __restrict__ v, const double* 
             }
 #pragma unroll 1
             for (int kk = 0; kk < nz; ++kk) {
-                const double d = s_dz[kk];
+                const double d = E3 ? 0.0 : s_dz[kk];
 #pragma unroll
                 for (int e = 0; e < VEC; ++e) {
-                    su[e] = __dadd_rn(su[e], __dmul_rn(d, clean<T>(pu[(int64_t)kk * ld + e], fill, has_fill)));
-                    sv[e] = __dadd_rn(sv[e], __dmul_rn(d, clean<T>(pv[(int64_t)kk * ld + e], fill, has_fill)));
+                    const double du = E3 ? clean<T>(pe[(int64_t)kk * ld + e], fill, has_fill) : d;
+                    const double dv = E3 ? clean<T>(pf[(int64_t)kk * ld + e], fill, has_fill) : d;
+                    su[e] = __dadd_rn(su[e], __dmul_rn(du, clean<T>(pu[(int64_t)kk * ld + e], fill, has_fill)));
+                    sv[e] = __dadd_rn(sv[e], __dmul_rn(dv, clean<T>(pv[(int64_t)kk * ld + e], fill, has_fill)));
                 }
             }
         }
@@ -204,8 +216,8 @@ void launch_ldg(const T* u, const T* v, const double* dz, const double* arc1, co
     dim3 grid((unsigned)((nthreads + BLOCK - 1) / BLOCK), (unsigned)nt);
     // float32: every level through the bit-shuffle conversion (profiles/r1_f32_alu_sweep.md: 5.09 -> 6.37 TB/s)
     constexpr int kAluMask = (sizeof(T) == 4) ? 0x1f : 0;
-    if (e3.e3u)
-        k2_edgeflux_ldg<T, VEC, UNROLL, BLOCK, true, 0><<<grid, BLOCK, sizeof(double) * nz, s>>>(
+    if (e3.e3u)   // float32: every level through the bit shuffle (restored exactly by one multiply per value)
+        k2_edgeflux_ldg<T, VEC, UNROLL, BLOCK, true, (sizeof(T) == 4 ? (1 << UNROLL) - 1 : 0)><<<grid, BLOCK, sizeof(double) * nz, s>>>(
             u, v, dz, arc1, arc2, eflux, nz, ncell, ld, scale, use_scale, fill, has_fill, keep_l2, (const T*)e3.e3u,
             (const T*)e3.e3v, e3.tstride);
     else if (alu_mask >= 0 && sizeof(T) == 4 && UNROLL == 5) {
@@ -578,7 +590,10 @@ void edgeflux_assemble_panel(const void* u, const void* v, int dtype, const doub
     } else {
         const float* pu = (const float*)u;
         const float* pv = (const float*)v;
-        if (aligned32 && ld % 8 == 0 && (ncols % 8 == 0 || ld >= (ncols + 7) / 8 * 8))
+        // float32: 128-bit loads (72 registers, 3 CTAs per SM) stream 15 % faster than 256-bit loads (2 CTAs per SM)
+        // -- profiles/r1_f32_alu_sweep.md; the 256-bit shape stays selectable with NFX_K2_LDG
+        const bool wide = opt.variant == NFX_K2_LDG;
+        if (wide && aligned32 && ld % 8 == 0 && (ncols % 8 == 0 || ld >= (ncols + 7) / 8 * 8))
             dispatch_ldg<float, 8>(pu, pv, thickness, arc1, arc2, eflux, nt, nz, ncols, ld, scale, sverdrup,
                                    (float)fill, has_fill, keep_l2, e3, opt, s);
         else if (aligned16 && ld % 4 == 0 && (ncols % 4 == 0 || ld >= (ncols + 3) / 4 * 4))

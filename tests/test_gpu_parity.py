@@ -202,8 +202,15 @@ def test_k2_f32_special_values(gpu, oracle, shape, thick_max):
     arc1 = rng.uniform(1e-3, 2e-2, ny * nx)
     arc2 = rng.uniform(1e-3, 2e-2, ny * nx)
     d = 'cuda'
-    efh = gpu.edgeFluxAssemble(torch.from_numpy(u).to(d), torch.from_numpy(v).to(d), torch.from_numpy(th).to(d),
-                               torch.from_numpy(arc1).to(d), torch.from_numpy(arc2).to(d)).cpu().numpy()
+    from nemoflux_b200 import _lib
+    dev_args = [torch.from_numpy(x).to(d) for x in (u, v, th, arc1, arc2)]
+    efh = gpu.edgeFluxAssemble(*dev_args).cpu().numpy()                    # 128-bit loads (the float32 default)
+    try:
+        _lib.set_option(_lib.NFX_OPT_K2_VARIANT, _lib.NFX_K2_LDG)         # widest loads: float x 8
+        assert_bitwise_nan = gpu.edgeFluxAssemble(*dev_args).cpu().numpy()
+    finally:
+        _lib.set_option(_lib.NFX_OPT_K2_VARIANT, _lib.NFX_K2_AUTO)
+    assert numpy.array_equal(assert_bitwise_nan, efh, equal_nan=True)
     ninf = 0
     for t in range(nt):
         with numpy.errstate(all='ignore'):

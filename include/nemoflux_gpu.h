@@ -60,6 +60,7 @@ extern "C" {
 #define NFX_OPT_RING_SLOT_MB 5
 #define NFX_OPT_LAST_SERIES_PATH 8 /* read only: 1 = the last nfx_flux_series* call took the fused pass, 0 = two launches, -1 = none yet */
 #define NFX_OPT_FUSED_ORDER 9      /* fused pass: bit 0 = visit (time step, panel) batches panel-major, bit 1 = K3 gathers unrolled x8; default 3 */
+#define NFX_OPT_FUSED_F64_CTAS 10  /* fused pass, float64 storage, 256-bit loads: register budget for 2 or 4 CTAs per SM (0 = default 3) */
 #define NFX_OPT_FUSED_F32_SHAPE 7  /* fused pass, float32 storage: 10 * vector width + unroll (85, 45, 83, 43); 0 default */ /* size of one eflux ring slot of that path in MB (default 8)                */
 
 typedef struct nfx_grid nfx_grid;

@@ -27,6 +27,7 @@
 namespace nfx {
 
 int g_fused_f32_shape = 0;   // NFX_OPT_FUSED_F32_SHAPE (tuning knob)
+int g_fused_f64_ctas = 0;    // NFX_OPT_FUSED_F64_CTAS (tuning knob): 2 or 4 resident CTAs per SM instead of 3
 int g_fused_order = 3;       // NFX_OPT_FUSED_ORDER: bit 0 = visit the batches panel-major, bit 1 = K3 gathers unrolled x8
                              // (same-box A/B, profiles/r1_fused_order_ab.md: -3 % and -1 % time on multi-panel grids)
 
@@ -35,6 +36,8 @@ namespace {
 using namespace dev;
 
 constexpr int kFusedBlock = 256;
+constexpr int kFusedF64Ctas = 3;   // float64 storage: 80 registers; -2.5 % time against 4 CTAs x 64 registers,
+                                   // -6 % against 2 CTAs x 114 registers (profiles/r1_fused_ctas_ab.md)
 constexpr int kWarps = kFusedBlock / 32;
 constexpr unsigned kSpinLimit = 1u << 27;
 
@@ -87,8 +90,16 @@ __device__ __forceinline__ bool cta_wait(const int* flag, int target, int* err, 
     return ok;
 }
 
+// resident CTAs per SM the register allocation is bounded for (0 = the default of the shape)
 template <typename T, int VEC, int UNROLL>
-__global__ void __launch_bounds__(kFusedBlock, (sizeof(T) == 4 && VEC == 8 && UNROLL == 5) ? 3 : (sizeof(T) == 4 ? 4 : 1))
+constexpr int fused_min_ctas(int wanted) {
+    if (wanted > 0) return wanted;
+    if (sizeof(T) == 4) return (VEC == 8 && UNROLL == 5) ? 3 : 4;
+    return kFusedF64Ctas;
+}
+
+template <typename T, int VEC, int UNROLL, int CTAS = 0>
+__global__ void __launch_bounds__(kFusedBlock, fused_min_ctas<T, VEC, UNROLL>(CTAS))
 k23_fused(const FusedArgs a) {
     extern __shared__ double s_dz[];
     __shared__ int s_item;
@@ -283,29 +294,32 @@ k23_fused(const FusedArgs a) {
     }
 }
 
-template <typename T, int VEC, int UNROLL>
+template <typename T, int VEC, int UNROLL, int CTAS = 0>
 int fused_grid() {
     static int grid = 0;
     if (grid == 0) {
         int dev = 0, sms = 0, per_sm = 0;
         NFX_CUDA(cudaGetDevice(&dev));
         NFX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        NFX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k23_fused<T, VEC, UNROLL>, kFusedBlock,
+        NFX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k23_fused<T, VEC, UNROLL, CTAS>, kFusedBlock,
                                                                sizeof(double) * 256));
         grid = sms * std::max(per_sm, 1);
     }
     return grid;
 }
 
-template <typename T, int VEC, int UNROLL>
+template <typename T, int VEC, int UNROLL, int CTAS = 0>
 void launch_fused(const FusedArgs& a, cudaStream_t s) {
-    k23_fused<T, VEC, UNROLL><<<fused_grid<T, VEC, UNROLL>(), kFusedBlock, sizeof(double) * a.nz * 2, s>>>(a);
+    k23_fused<T, VEC, UNROLL, CTAS><<<fused_grid<T, VEC, UNROLL, CTAS>(), kFusedBlock, sizeof(double) * a.nz * 2, s>>>(a);
 }
 
-int fused_grid_for(int dtype, int vec, int unroll) {
-    if (dtype == NFX_F64)
-        return vec == 4 ? fused_grid<double, 4, 5>() : vec == 2 ? fused_grid<double, 2, 5>() : fused_grid<double, 1, 5>();
+int fused_grid_for(int dtype, int vec, int unroll, int ctas) {
+    if (dtype == NFX_F64) {
+        if (vec == 4) return ctas == 2 ? fused_grid<double, 4, 5, 2>() : ctas == 4 ? fused_grid<double, 4, 5, 4>() : fused_grid<double, 4, 5>();
+        return vec == 2 ? fused_grid<double, 2, 5>() : fused_grid<double, 1, 5>();
+    }
     if (unroll == 3) return vec == 8 ? fused_grid<float, 8, 3>() : fused_grid<float, 4, 3>();
+    if (vec == 4 && ctas == 3) return fused_grid<float, 4, 5, 3>();
     return vec == 8 ? fused_grid<float, 8, 5>() : vec == 4 ? fused_grid<float, 4, 5>() : fused_grid<float, 1, 5>();
 }
 
@@ -385,7 +399,10 @@ void flux_series_fused(PliDev& p, const PanelPlan& pl, const void* u, const void
     NFX_REQUIRE((int64_t)(a.nbatches + 1) * (a.ntiles + a.nk3) < 2000000000ll, "fused pass: too many work items");
     // enough slots that every resident CTA finds a K2 tile while the K3 of older batches drains (x2 margin),
     // but no more than ~64 MB of evict-last lines in the 126 MB L2
-    const int resident = fused_grid_for(dtype, vec, unroll);
+    int ctas = 0;   // 0 = the default register budget of the shape
+    if (dtype == NFX_F64 && vec == 4 && (g_fused_f64_ctas == 2 || g_fused_f64_ctas == 4)) ctas = g_fused_f64_ctas;
+    if (dtype != NFX_F64 && vec == 4 && unroll == 5 && g_fused_f64_ctas == 3) ctas = 3;
+    const int resident = fused_grid_for(dtype, vec, unroll, ctas);
     int slots = (2 * resident + a.ntiles - 1) / a.ntiles + 1;
     const int64_t cap = std::max<int64_t>(3, ((int64_t)64 << 20) / (a.slot_elems * 8));
     slots = (int)std::min<int64_t>(std::max(slots, 3), cap);
@@ -435,13 +452,16 @@ void flux_series_fused(PliDev& p, const PanelPlan& pl, const void* u, const void
     a.sync = p.fused_sync.p;
     NFX_CUDA(cudaMemsetAsync(a.sync, 0, sizeof(int) * (2 + 2 * a.nbatches), s));
     if (dtype == NFX_F64) {
-        if (vec == 4) launch_fused<double, 4, 5>(a, s);
+        if (vec == 4 && ctas == 2) launch_fused<double, 4, 5, 2>(a, s);
+        else if (vec == 4 && ctas == 4) launch_fused<double, 4, 5, 4>(a, s);
+        else if (vec == 4) launch_fused<double, 4, 5>(a, s);
         else if (vec == 2) launch_fused<double, 2, 5>(a, s);
         else launch_fused<double, 1, 5>(a, s);
     } else {
         if (unroll == 3 && vec == 8) launch_fused<float, 8, 3>(a, s);
         else if (unroll == 3 && vec == 4) launch_fused<float, 4, 3>(a, s);
         else if (vec == 8) launch_fused<float, 8, 5>(a, s);
+        else if (vec == 4 && ctas == 3) launch_fused<float, 4, 5, 3>(a, s);
         else if (vec == 4) launch_fused<float, 4, 5>(a, s);
         else launch_fused<float, 1, 5>(a, s);
     }

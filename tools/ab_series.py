@@ -25,6 +25,7 @@ def main():
     ap.add_argument('--nx', type=int, default=0)
     ap.add_argument('--dtype', default='f64', choices=['f64', 'f32'])
     ap.add_argument('--pad', type=int, default=0)
+    ap.add_argument('--f64-ctas', default='', help='fused float64 kernel: register budgets (CTAs per SM) to compare, e.g. 2,3')
     ap.add_argument('--base-order', type=int, default=0, help='NFX_OPT_FUSED_ORDER of the modes that do not set it')
     ap.add_argument('--orders', default='', help='fused batch visiting orders / K3 unroll to compare (NFX_OPT_FUSED_ORDER), e.g. 0,1,2,3')
     ap.add_argument('--f32-shapes', default='', help='fused float32 kernel shapes to compare, e.g. 85,45,83,43')
@@ -53,12 +54,14 @@ def main():
     for o in [int(x) for x in a.orders.split(',') if x]:
         modes.append((f'fused order={o}', {}, {_lib.NFX_OPT_RING_SLOT_MB: 8, _lib.NFX_OPT_FAST_SERIES: 2,
                                                _lib.NFX_OPT_FUSED_ORDER: o}))
+    for c in [int(x) for x in a.f64_ctas.split(',') if x]:
+        modes.append((f'fused f64 ctas/SM={c}', {}, {_lib.NFX_OPT_FUSED_F64_CTAS: c}))
     times = {m[0]: [] for m in modes}
     ref = None
     for rnd in range(a.rounds):
         for name, kw, opts in modes:
             full = {_lib.NFX_OPT_RING_SLOT_MB: 8, _lib.NFX_OPT_FAST_SERIES: 2, _lib.NFX_OPT_FUSED_F32_SHAPE: 0,
-                    _lib.NFX_OPT_FUSED_ORDER: a.base_order}
+                    _lib.NFX_OPT_FUSED_ORDER: a.base_order, _lib.NFX_OPT_FUSED_F64_CTAS: 0}
             full.update(opts)                       # every mode sets every knob: nothing leaks from the mode before
             for k, val in full.items():
                 _lib.set_option(k, val)

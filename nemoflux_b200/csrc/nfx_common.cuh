@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <algorithm>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -57,6 +58,27 @@ struct DevBuf {
     }
     void ensure(size_t count) {
         if (count > n) alloc(count);
+    }
+};
+
+// Bump allocator over one persistent device buffer: the temporaries of computeWeights (tens of bytes per
+// sub-segment, 0.8 GB on an ORCA12 grid with 1024 transects) cost more in cudaMalloc/cudaFree than their kernels.
+// Everything taken from an Arena is used on ONE stream, so rewinding (`used = mark`) is safe in stream order.
+template <typename T>
+struct View {
+    T* p = nullptr;
+};
+struct Arena {
+    unsigned char* base = nullptr;
+    size_t cap = 0, used = 0;
+    template <typename T>
+    View<T> take(size_t count) {
+        const size_t bytes = (std::max<size_t>(count, 1) * sizeof(T) + 255) & ~(size_t)255;
+        if (used + bytes > cap) throw Error(NFX_E_INTERNAL, "scratch arena overflow");
+        View<T> v;
+        v.p = reinterpret_cast<T*>(base + used);
+        used += bytes;
+        return v;
     }
 };
 
@@ -125,6 +147,8 @@ struct PliDev {
     PanelPlan plan[2];            // per summation order
     DevBuf<double> ring, partial;  // L2-resident eflux ring and per-panel partial sums of the fused pass
     DevBuf<int> fused_sync;        // work counter, error flag, per-batch completion counters
+    DevBuf<unsigned char> scratch; // computeWeights temporaries (Arena), kept between calls
+    DevBuf<int64_t> scan_tmp;
     DevBuf<int> batch_map;         // fused pass: order in which the (time step, panel) batches are visited
     std::vector<int> h_batch_map;
     int64_t batch_map_key[4] = {-1, -1, -1, -1};   // (batch_begin, batch_end, npanels, order) of the cached map

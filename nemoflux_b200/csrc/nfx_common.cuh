@@ -92,8 +92,8 @@ struct GridDev {
     DevBuf<double2> verts;       // (ncell*4) lon,lat
     // locator (built by nfx_pli_build_locator, cached on the grid so every pli shares it)
     bool locator_built = false;
-    int64_t nl1 = 0, nl2 = 0;
-    DevBuf<double4> box1, box2;  // xmin, xmax, ymin, ymax
+    int64_t nl1 = 0, nl2 = 0, nl3 = 0;
+    DevBuf<double4> box1, box2, box3;  // xmin, xmax, ymin, ymax; level k groups 32 boxes of level k-1
 };
 
 // CSR of (flux index, weight) per transect

@@ -200,77 +200,96 @@ __global__ void k_build_box2(const double4* __restrict__ box1, int64_t nl1, doub
     if (lane == 0) box2[node] = b;
 }
 
-// ---- traversal: one warp per (segment, image) -------------------------------------------------------
+// ---- traversal: one warp per (segment, image, piece) ------------------------------------------------
+// A long segment (an ORCA12 diagonal crosses ~7 000 cells) would keep one warp busy for 16 ms while the rest of the
+// GPU idles, so every (segment, image) is cut into kPieces parameter ranges [k/P, (k+1)/P]: the warp of a piece
+// walks the box hierarchy with the piece's own end points (a filter only), runs the exact routine on the FULL
+// segment -- same arithmetic, same ta/tb as before -- and keeps a cell iff its ta falls into the piece's range.
+// The point p(ta) lies on the cell and on that piece, so the piece always sees the cell as a candidate (margin
+// 1e-7 deg against 1e-13 of rounding), and exactly one piece keeps it.  The order inside a segment is restored by
+// the sort that follows, as before.
+constexpr int kPieces = 8;
+
 struct SegIn {
     double p0x, p0y, p1x, p1y;
 };
 
+// ballot of "box first+lane may be crossed by the segment (qa, qb)"
+__device__ __forceinline__ unsigned box_hits(const double4* __restrict__ boxes, int64_t nbox, int64_t first, int lane,
+                                             double qax, double qay, double qbx, double qby) {
+    const int64_t k = first + lane;
+    bool hit = false;
+    if (k < nbox) {
+        const double4 b = boxes[k];
+        hit = !seg_box_reject(qax, qay, qbx, qby, b.x, b.y, b.z, b.w);
+    }
+    return __ballot_sync(0xffffffffu, hit);
+}
+
+__device__ __forceinline__ int piece_of(double ta) {
+    const int k = (int)floor(ta * (double)kPieces);
+    return k < 0 ? 0 : (k >= kPieces ? kPieces - 1 : k);
+}
+
 template <bool FILL>
 __global__ void __launch_bounds__(128)
 k1_traverse(const double2* __restrict__ verts, int64_t ncell, const double4* __restrict__ box1, int64_t nl1,
-            const double4* __restrict__ box2, int64_t nl2, const SegIn* __restrict__ segs, int nseg, int nimg,
+            const double4* __restrict__ box2, int64_t nl2, const double4* __restrict__ box3, int64_t nl3,
+            const SegIn* __restrict__ segs, int nseg, int nimg,
             double period_x, int64_t* __restrict__ counts, const int64_t* __restrict__ offsets,
             int32_t* __restrict__ o_cell, int32_t* __restrict__ o_img, double* __restrict__ o_ta,
             double* __restrict__ o_tb) {
     const int lane = threadIdx.x & 31;
     const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (w >= (int64_t)nseg * nimg) return;
-    const int seg = (int)(w / nimg);
-    const int img = (int)(w % nimg) - (nimg == 3 ? 1 : 0);
+    if (w >= (int64_t)nseg * nimg * kPieces) return;
+    const int piece = (int)(w % kPieces);
+    const int64_t wi = w / kPieces;
+    const int seg = (int)(wi / nimg);
+    const int img = (int)(wi % nimg) - (nimg == 3 ? 1 : 0);
     const SegIn sg = segs[seg];
     int64_t count = 0;
     if (!(sg.p0x == sg.p1x && sg.p0y == sg.p1y)) {
         const double shift = dmul((double)img, period_x);
         const double ax = dadd(sg.p0x, shift), bx = dadd(sg.p1x, shift);
         const double ay = sg.p0y, by = sg.p1y;
+        // end points of this piece: candidate filter only
+        const double l0 = (double)piece / kPieces, l1 = (double)(piece + 1) / kPieces;
+        const double qax = ax + (bx - ax) * l0, qay = ay + (by - ay) * l0;
+        const double qbx = ax + (bx - ax) * l1, qby = ay + (by - ay) * l1;
         const int64_t base = FILL ? offsets[w] : 0;
-        for (int64_t n2b = 0; n2b < nl2; n2b += 32) {
-            const int64_t n2 = n2b + lane;
-            bool hit2 = false;
-            if (n2 < nl2) {
-                const double4 b = box2[n2];
-                hit2 = !seg_box_reject(ax, ay, bx, by, b.x, b.y, b.z, b.w);
-            }
-            unsigned mask2 = __ballot_sync(0xffffffffu, hit2);
-            while (mask2) {
-                const int b2 = __ffs(mask2) - 1;
-                mask2 &= mask2 - 1;
-                const int64_t node2 = n2b + b2;
-                const int64_t n1 = node2 * kFan + lane;
-                bool hit1 = false;
-                if (n1 < nl1) {
-                    const double4 b = box1[n1];
-                    hit1 = !seg_box_reject(ax, ay, bx, by, b.x, b.y, b.z, b.w);
-                }
-                unsigned mask1 = __ballot_sync(0xffffffffu, hit1);
-                while (mask1) {
-                    const int b1 = __ffs(mask1) - 1;
-                    mask1 &= mask1 - 1;
-                    const int64_t c = (node2 * kFan + b1) * kFan + lane;
-                    bool accept = false;
-                    double ta = 0.0, tb = 0.0;
-                    if (c < ncell) {
-                        double2 v[4];
+        // three levels of boxes, 32 children each: the warp tests 32 boxes at a time, descends into every hit
+        for (int64_t n3b = 0; n3b < nl3; n3b += 32) {
+            for (unsigned m3 = box_hits(box3, nl3, n3b, lane, qax, qay, qbx, qby); m3; m3 &= m3 - 1) {
+                const int64_t node3 = n3b + (__ffs(m3) - 1);
+                for (unsigned m2 = box_hits(box2, nl2, node3 * kFan, lane, qax, qay, qbx, qby); m2; m2 &= m2 - 1) {
+                    const int64_t node2 = node3 * kFan + (__ffs(m2) - 1);
+                    for (unsigned m1 = box_hits(box1, nl1, node2 * kFan, lane, qax, qay, qbx, qby); m1; m1 &= m1 - 1) {
+                        const int64_t c = (node2 * kFan + (__ffs(m1) - 1)) * kFan + lane;   // one cell per lane
+                        bool accept = false;
+                        double ta = 0.0, tb = 0.0;
+                        if (c < ncell) {
+                            double2 v[4];
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) v[k] = verts[c * 4 + k];
-                        const double xmin = fmin(fmin(v[0].x, v[1].x), fmin(v[2].x, v[3].x));
-                        const double xmax = fmax(fmax(v[0].x, v[1].x), fmax(v[2].x, v[3].x));
-                        const double ymin = fmin(fmin(v[0].y, v[1].y), fmin(v[2].y, v[3].y));
-                        const double ymax = fmax(fmax(v[0].y, v[1].y), fmax(v[2].y, v[3].y));
-                        if (!seg_box_reject(ax, ay, bx, by, xmin, xmax, ymin, ymax)) {
-                            const int n = collect_lambdas(v, ax, ay, bx, by, ta, tb);
-                            accept = (n >= 2) && (fabs(dsub(tb, ta)) > kEps100);
+                            for (int k = 0; k < 4; ++k) v[k] = verts[c * 4 + k];
+                            const double xmin = fmin(fmin(v[0].x, v[1].x), fmin(v[2].x, v[3].x));
+                            const double xmax = fmax(fmax(v[0].x, v[1].x), fmax(v[2].x, v[3].x));
+                            const double ymin = fmin(fmin(v[0].y, v[1].y), fmin(v[2].y, v[3].y));
+                            const double ymax = fmax(fmax(v[0].y, v[1].y), fmax(v[2].y, v[3].y));
+                            if (!seg_box_reject(qax, qay, qbx, qby, xmin, xmax, ymin, ymax)) {
+                                const int n = collect_lambdas(v, ax, ay, bx, by, ta, tb);
+                                accept = (n >= 2) && (fabs(dsub(tb, ta)) > kEps100) && piece_of(ta) == piece;
+                            }
                         }
+                        const unsigned macc = __ballot_sync(0xffffffffu, accept);
+                        if (FILL && accept) {
+                            const int64_t pos = base + count + __popc(macc & ((1u << lane) - 1u));
+                            o_cell[pos] = (int32_t)c;
+                            o_img[pos] = img;
+                            o_ta[pos] = ta;
+                            o_tb[pos] = tb;
+                        }
+                        count += __popc(macc);
                     }
-                    const unsigned macc = __ballot_sync(0xffffffffu, accept);
-                    if (FILL && accept) {
-                        const int64_t pos = base + count + __popc(macc & ((1u << lane) - 1u));
-                        o_cell[pos] = (int32_t)c;
-                        o_img[pos] = img;
-                        o_ta[pos] = ta;
-                        o_tb[pos] = tb;
-                    }
-                    count += __popc(macc);
                 }
             }
         }
@@ -817,11 +836,14 @@ void grid_build_locator(GridDev& g, cudaStream_t s) {
     NFX_REQUIRE(g.ncell > 0, "buildLocator: the grid has no points");
     g.nl1 = (g.ncell + kFan - 1) / kFan;
     g.nl2 = (g.nl1 + kFan - 1) / kFan;
+    g.nl3 = (g.nl2 + kFan - 1) / kFan;
     g.box1.alloc((size_t)g.nl1);
     g.box2.alloc((size_t)g.nl2);
+    g.box3.alloc((size_t)g.nl3);
     k_build_box1<<<nblk(g.nl1 * 32, 256), 256, 0, s>>>(g.verts.p, g.ncell, g.box1.p, g.nl1);
     k_build_box2<<<nblk(g.nl2 * 32, 256), 256, 0, s>>>(g.box1.p, g.nl1, g.box2.p, g.nl2);
-    count_launch(2);
+    k_build_box2<<<nblk(g.nl3 * 32, 256), 256, 0, s>>>(g.box2.p, g.nl2, g.box3.p, g.nl3);   // same reduction, one level up
+    count_launch(3);
     NFX_CUDA(cudaGetLastError());
     g.locator_built = true;
 }
@@ -850,7 +872,7 @@ void pli_compute_weights(PliDev& p, int ntransects, const int* offsets, const do
         tr_seg_off[m + 1] = (int64_t)segs.size();
     }
     const int nseg = (int)segs.size();
-    const int64_t nw = (int64_t)nseg * nimg;
+    const int64_t nw = (int64_t)nseg * nimg * kPieces;   // warps of the traversal: (segment, image, piece)
 
     p.ntransects = ntransects;
     p.nsub = 0;
@@ -891,7 +913,7 @@ void pli_compute_weights(PliDev& p, int ntransects, const int* offsets, const do
 
     // count
     const unsigned tb = nblk(nw * 32, 128);
-    k1_traverse<false><<<tb, 128, 0, s>>>(g.verts.p, g.ncell, g.box1.p, g.nl1, g.box2.p, g.nl2, d_segs.p, nseg, nimg,
+    k1_traverse<false><<<tb, 128, 0, s>>>(g.verts.p, g.ncell, g.box1.p, g.nl1, g.box2.p, g.nl2, g.box3.p, g.nl3, d_segs.p, nseg, nimg,
                                          p.period_x, d_counts.p, nullptr, nullptr, nullptr, nullptr, nullptr);
     count_launch();
     NFX_CUDA(cudaGetLastError());
@@ -905,7 +927,7 @@ void pli_compute_weights(PliDev& p, int ntransects, const int* offsets, const do
     // per-segment / per-transect offsets
     std::vector<int64_t> h_seg_off(nseg + 1);
     int64_t max_seg = 0;
-    for (int q = 0; q <= nseg; ++q) h_seg_off[q] = h_off[(size_t)q * nimg];
+    for (int q = 0; q <= nseg; ++q) h_seg_off[q] = h_off[(size_t)q * nimg * kPieces];
     for (int q = 0; q < nseg; ++q) max_seg = std::max(max_seg, h_seg_off[q + 1] - h_seg_off[q]);
     int64_t max_tr = 0;
     for (int m = 0; m <= ntransects; ++m) p.h_sub_offsets[m] = h_seg_off[tr_seg_off[m]];
@@ -952,7 +974,7 @@ void pli_compute_weights(PliDev& p, int ntransects, const int* offsets, const do
         auto r_tb = ar.take<double>(ns);
         auto kb = ar.take<int64_t>(ns);
         auto perm = ar.take<int64_t>(ns);
-        k1_traverse<true><<<tb, 128, 0, s>>>(g.verts.p, g.ncell, g.box1.p, g.nl1, g.box2.p, g.nl2, d_segs.p, nseg, nimg,
+        k1_traverse<true><<<tb, 128, 0, s>>>(g.verts.p, g.ncell, g.box1.p, g.nl1, g.box2.p, g.nl2, g.box3.p, g.nl3, d_segs.p, nseg, nimg,
                                             p.period_x, nullptr, d_off.p, r_cell.p, r_img.p, r_ta.p, r_tb.p);
         // sort inside each segment by (ta, cell, image)
         k_make_sort1_key<<<nblk(nsub, 256), 256, 0, s>>>(r_cell.p, r_img.p, nsub, kb.p);

@@ -5,7 +5,7 @@ import numpy
 import pytest
 
 from conftest import GOLDEN
-from helpers import README_C1, README_C2, README_SINGULAR, SF_C2, tr
+from helpers import README_C1, README_SINGULAR, SF_C2, tr
 
 pytestmark = pytest.mark.gpu
 

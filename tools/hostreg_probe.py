@@ -1,6 +1,5 @@
 """probe: can a read-only memory-mapped file be page-locked in place (cudaHostRegister ... ReadOnly) and copied to the
 device at PCIe rate without a host-side memcpy?  Prints GB/s for: registered mmap, plain mmap (pageable), pinned copy."""
-import ctypes
 import mmap
 import os
 import sys

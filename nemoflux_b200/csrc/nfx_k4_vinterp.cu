@@ -67,7 +67,8 @@ __device__ __forceinline__ bool box_has(const double4& b, double px, double py) 
 
 __global__ void __launch_bounds__(128)
 k4_find_points(const double2* __restrict__ verts, int64_t ncell, const double4* __restrict__ box1, int64_t nl1,
-               const double4* __restrict__ box2, int64_t nl2, const double* __restrict__ xyz, int64_t npts,
+               const double4* __restrict__ box2, int64_t nl2, const double4* __restrict__ box3, int64_t nl3,
+               const double* __restrict__ xyz, int64_t npts,
                double period_x, double tol, int32_t* __restrict__ cell, double* __restrict__ xi) {
     const int lane = threadIdx.x & 31;
     const int64_t n = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -80,36 +81,34 @@ k4_find_points(const double2* __restrict__ verts, int64_t ncell, const double4* 
         const double shift = im == 0 ? 0.0 : (im == 1 ? -period_x : period_x);
         const double px = dadd(xyz[3 * n], shift);
         int64_t best = INT64_MAX;
-        for (int64_t n2b = 0; n2b < nl2; n2b += 32) {
-            const int64_t n2 = n2b + lane;
-            unsigned mask2 = __ballot_sync(0xffffffffu, n2 < nl2 && box_has(box2[n2 < nl2 ? n2 : 0], px, py));
-            while (mask2) {
-                const int b2 = __ffs(mask2) - 1;
-                mask2 &= mask2 - 1;
-                const int64_t node2 = n2b + b2;
-                if (node2 * kFan * kFan >= best) { mask2 = 0; break; }   // cells of later nodes have larger ids
-                const int64_t n1 = node2 * kFan + lane;
-                unsigned mask1 = __ballot_sync(0xffffffffu, n1 < nl1 && box_has(box1[n1 < nl1 ? n1 : 0], px, py));
-                while (mask1) {
-                    const int b1 = __ffs(mask1) - 1;
-                    mask1 &= mask1 - 1;
-                    const int64_t c = (node2 * kFan + b1) * kFan + lane;
-                    bool in = false;
-                    if (c < ncell) {
-                        double2 v[4];
+        // descend the three box levels; cell ids grow with the node index at every level, so the first hit in
+        // traversal order is the lowest containing cell id and everything after it can be skipped
+        for (int64_t n3b = 0; n3b < nl3 && best == INT64_MAX; n3b += 32) {
+            const int64_t n3 = n3b + lane;
+            unsigned mask3 = __ballot_sync(0xffffffffu, n3 < nl3 && box_has(box3[n3 < nl3 ? n3 : 0], px, py));
+            for (; mask3 && best == INT64_MAX; mask3 &= mask3 - 1) {
+                const int64_t node3 = n3b + (__ffs(mask3) - 1);
+                const int64_t n2 = node3 * kFan + lane;
+                unsigned mask2 = __ballot_sync(0xffffffffu, n2 < nl2 && box_has(box2[n2 < nl2 ? n2 : 0], px, py));
+                for (; mask2 && best == INT64_MAX; mask2 &= mask2 - 1) {
+                    const int64_t node2 = node3 * kFan + (__ffs(mask2) - 1);
+                    const int64_t n1 = node2 * kFan + lane;
+                    unsigned mask1 = __ballot_sync(0xffffffffu, n1 < nl1 && box_has(box1[n1 < nl1 ? n1 : 0], px, py));
+                    for (; mask1 && best == INT64_MAX; mask1 &= mask1 - 1) {
+                        const int64_t first = (node2 * kFan + (__ffs(mask1) - 1)) * kFan;
+                        const int64_t c = first + lane;
+                        bool in = false;
+                        if (c < ncell) {
+                            double2 v[4];
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) v[k] = verts[c * 4 + k];
-                        in = contains_point(v, px, py, tol);
-                    }
-                    const unsigned m = __ballot_sync(0xffffffffu, in);
-                    if (m) {
-                        const int64_t cand = (node2 * kFan + b1) * kFan + (__ffs(m) - 1);
-                        if (cand < best) best = cand;
-                        mask1 = 0;   // later level-1 nodes of this level-2 node only hold larger ids
+                            for (int k = 0; k < 4; ++k) v[k] = verts[c * 4 + k];
+                            in = contains_point(v, px, py, tol);
+                        }
+                        const unsigned m = __ballot_sync(0xffffffffu, in);
+                        if (m) best = first + (__ffs(m) - 1);
                     }
                 }
             }
-            if (best != INT64_MAX) break;   // later level-2 blocks only hold larger ids
         }
         if (best != INT64_MAX) {
             found = best;
@@ -173,7 +172,7 @@ void vinterp_find_points(VInterpDev& vi, int64_t npts, const double* xyz_host, d
     d_xyz.alloc((size_t)3 * npts);
     NFX_CUDA(cudaMemcpyAsync(d_xyz.p, xyz_host, sizeof(double) * 3 * npts, cudaMemcpyHostToDevice, s));
     const double tol = tol2 > kEps ? tol2 : kEps;
-    k4_find_points<<<(unsigned)((npts * 32 + 127) / 128), 128, 0, s>>>(g.verts.p, g.ncell, g.box1.p, g.nl1, g.box2.p, g.nl2,
+    k4_find_points<<<(unsigned)((npts * 32 + 127) / 128), 128, 0, s>>>(g.verts.p, g.ncell, g.box1.p, g.nl1, g.box2.p, g.nl2, g.box3.p, g.nl3,
                                                                        d_xyz.p, npts, vi.period_x, tol, vi.cell.p, vi.xi.p);
     count_launch();
     NFX_CUDA(cudaGetLastError());

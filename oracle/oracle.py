@@ -288,7 +288,10 @@ class Grid(object):
 
     def __del__(self):
         if getattr(self, 'h', None):
-            lib().orc_grid_del(self.h)
+            try:
+                lib().orc_grid_del(self.h)
+            except TypeError:       # interpreter shutdown: the module globals are already gone
+                pass
             self.h = None
 
     def getNumberOfCells(self):

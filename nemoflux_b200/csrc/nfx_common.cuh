@@ -94,6 +94,7 @@ struct GridDev {
     bool locator_built = false;
     int64_t nl1 = 0, nl2 = 0, nl3 = 0;
     DevBuf<double4> box1, box2, box3;  // xmin, xmax, ymin, ymax; level k groups 32 boxes of level k-1
+    double mean_cell = 0.0;      // sqrt(bounding-box area / ncell): scale for the sub-segment count estimate of K1
 };
 
 // CSR of (flux index, weight) per transect
@@ -147,7 +148,9 @@ struct PliDev {
     PanelPlan plan[2];            // per summation order
     DevBuf<double> ring, partial;  // L2-resident eflux ring and per-panel partial sums of the fused pass
     DevBuf<int> fused_sync;        // work counter, error flag, per-batch completion counters
-    DevBuf<unsigned char> scratch; // computeWeights temporaries (Arena), kept between calls
+    DevBuf<unsigned char> scratch; // computeWeights temporaries (Arena), kept between calls when small
+    int64_t nsub_hint = 0;         // sub-segments of the previous computeWeights: sizes the record list of the next
+    size_t scratch_hint = 0;       // bytes the arena ended with
     DevBuf<int64_t> scan_tmp;
     DevBuf<int> batch_map;         // fused pass: order in which the (time step, panel) batches are visited
     std::vector<int> h_batch_map;

@@ -19,6 +19,7 @@
 #include <math_constants.h>
 
 #include <algorithm>
+#include <cmath>
 
 #include "nfx_common.cuh"
 
@@ -231,6 +232,21 @@ __device__ __forceinline__ int piece_of(double ta) {
     return k < 0 ? 0 : (k >= kPieces ? kPieces - 1 : k);
 }
 
+// Speculative record of the count pass: every accepted cell is also appended to a list (warp id, index inside the
+// warp's output, cell, ta, tb) in chunks of kRecChunk slots that a warp takes with one atomic.  When the list was
+// large enough (host estimate of the number of sub-segments), the fill pass is a plain scatter of the records
+// (k_scatter_records) instead of a second traversal; when it overflowed, the fill traversal runs as before.
+constexpr int kRecChunk = 32;
+struct RecList {
+    unsigned long long* nchunks;   // chunks handed out (may exceed cap_chunks: overflow)
+    int64_t cap_chunks;
+    int32_t* w;                    // -1 = unused slot
+    int32_t* idx;
+    int32_t* cell;
+    double* ta;
+    double* tb;
+};
+
 template <bool FILL>
 __global__ void __launch_bounds__(128)
 k1_traverse(const double2* __restrict__ verts, int64_t ncell, const double4* __restrict__ box1, int64_t nl1,
@@ -238,10 +254,12 @@ k1_traverse(const double2* __restrict__ verts, int64_t ncell, const double4* __r
             const SegIn* __restrict__ segs, int nseg, int nimg,
             double period_x, int64_t* __restrict__ counts, const int64_t* __restrict__ offsets,
             int32_t* __restrict__ o_cell, int32_t* __restrict__ o_img, double* __restrict__ o_ta,
-            double* __restrict__ o_tb) {
+            double* __restrict__ o_tb, const RecList rec) {
     const int lane = threadIdx.x & 31;
     const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (w >= (int64_t)nseg * nimg * kPieces) return;
+    int64_t chunk_base = -1;       // record list: first slot of the warp's current chunk
+    int chunk_used = kRecChunk;
     const int piece = (int)(w % kPieces);
     const int64_t wi = w / kPieces;
     const int seg = (int)(wi / nimg);
@@ -288,13 +306,52 @@ k1_traverse(const double2* __restrict__ verts, int64_t ncell, const double4* __r
                             o_ta[pos] = ta;
                             o_tb[pos] = tb;
                         }
+                        if (!FILL && rec.cap_chunks > 0 && macc) {
+                            const int nacc = __popc(macc);
+                            if (chunk_used + nacc > kRecChunk) {   // the hits of one ballot stay in one chunk
+                                if (chunk_base >= 0 && chunk_base / kRecChunk < rec.cap_chunks)
+                                    for (int i = chunk_used + lane; i < kRecChunk; i += 32) rec.w[chunk_base + i] = -1;
+                                unsigned long long b = 0;
+                                if (lane == 0) b = atomicAdd(rec.nchunks, 1ull);
+                                b = __shfl_sync(0xffffffffu, b, 0);
+                                chunk_base = (int64_t)b * kRecChunk;
+                                chunk_used = 0;
+                            }
+                            if (accept && chunk_base / kRecChunk < rec.cap_chunks) {
+                                const int rk = __popc(macc & ((1u << lane) - 1u));
+                                const int64_t r = chunk_base + chunk_used + rk;
+                                rec.w[r] = (int32_t)w;
+                                rec.idx[r] = (int32_t)(count + rk);
+                                rec.cell[r] = (int32_t)c;
+                                rec.ta[r] = ta;
+                                rec.tb[r] = tb;
+                            }
+                            chunk_used += nacc;
+                        }
                         count += __popc(macc);
                     }
                 }
             }
         }
     }
+    if (!FILL && rec.cap_chunks > 0 && chunk_base >= 0 && chunk_base / kRecChunk < rec.cap_chunks)
+        for (int i = chunk_used + lane; i < kRecChunk; i += 32) rec.w[chunk_base + i] = -1;
     if (!FILL && lane == 0) counts[w] = count;
+}
+
+// fill pass from the record list: slot r of warp w goes to offsets[w] + idx -- the layout of k1_traverse<true>
+__global__ void k_scatter_records(const RecList rec, int64_t nslots, const int64_t* __restrict__ offsets, int nimg,
+                                  int32_t* __restrict__ o_cell, int32_t* __restrict__ o_img, double* __restrict__ o_ta,
+                                  double* __restrict__ o_tb) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nslots) return;
+    const int32_t w = rec.w[r];
+    if (w < 0) return;
+    const int64_t pos = offsets[w] + rec.idx[r];
+    o_cell[pos] = rec.cell[r];
+    o_img[pos] = (int32_t)((w / kPieces) % nimg) - (nimg == 3 ? 1 : 0);
+    o_ta[pos] = rec.ta[r];
+    o_tb[pos] = rec.tb[r];
 }
 
 // ---- exclusive scan (int64), 3 passes ---------------------------------------------------------------
@@ -845,6 +902,20 @@ void grid_build_locator(GridDev& g, cudaStream_t s) {
     k_build_box2<<<nblk(g.nl3 * 32, 256), 256, 0, s>>>(g.box2.p, g.nl2, g.box3.p, g.nl3);   // same reduction, one level up
     count_launch(3);
     NFX_CUDA(cudaGetLastError());
+    {   // bounding box of the grid from the top level -> mean cell size (K1's estimate of the sub-segment count)
+        std::vector<double4> top((size_t)g.nl3);
+        NFX_CUDA(cudaMemcpyAsync(top.data(), g.box3.p, sizeof(double4) * g.nl3, cudaMemcpyDeviceToHost, s));
+        NFX_CUDA(cudaStreamSynchronize(s));
+        double x0 = 1.0e300, x1 = -1.0e300, y0 = 1.0e300, y1 = -1.0e300;
+        for (const double4& b : top) {
+            x0 = std::min(x0, b.x);
+            x1 = std::max(x1, b.y);
+            y0 = std::min(y0, b.z);
+            y1 = std::max(y1, b.w);
+        }
+        const double area = (x1 - x0) * (y1 - y0);
+        g.mean_cell = area > 0.0 ? std::sqrt(area / (double)g.ncell) : 0.0;
+    }
     g.locator_built = true;
 }
 
@@ -900,29 +971,55 @@ void pli_compute_weights(PliDev& p, int ntransects, const int* offsets, const do
     // temporaries come from the handle's scratch arena: (1) the per-segment arrays, sized now; (2) after the count
     // pass the arena is grown once for the per-sub-segment arrays (76 bytes each) and the small arrays are re-taken
     DevBuf<int64_t>& d_tmp = p.scan_tmp;
-    const size_t small_bytes = 256 * 8 + sizeof(SegIn) * nseg + sizeof(int32_t) * 2 * (size_t)nseg +
-                               sizeof(int64_t) * (2 * (size_t)nw + (size_t)nseg + 2);
-    p.scratch.ensure(small_bytes);
+    // record list of the count pass (see RecList): sized from the previous call on this handle, else from the
+    // lengths of the segments over the mean cell size; too small = the fill pass traverses again, nothing else
+    int64_t rec_slots = 0;
+    {
+        double est = 0.0;
+        if (p.nsub_hint > 0) {
+            est = 1.25 * (double)p.nsub_hint;
+        } else if (g.mean_cell > 0.0) {
+            for (const SegIn& sg : segs)
+                est += 1.2 * (std::fabs(sg.p1x - sg.p0x) + std::fabs(sg.p1y - sg.p0y)) / g.mean_cell + 2.0;
+        }
+        est += (double)kRecChunk * (double)(nw / 2 + 1);          // partly filled chunks
+        if (est * 28.0 <= 1.0e9) rec_slots = ((int64_t)est + kRecChunk - 1) / kRecChunk * kRecChunk;
+    }
+    const size_t small_bytes = 256 * 16 + sizeof(SegIn) * nseg + sizeof(int32_t) * 2 * (size_t)nseg +
+                               sizeof(int64_t) * (2 * (size_t)nw + (size_t)nseg + 2) + 28 * (size_t)rec_slots + 8;
+    p.scratch.ensure(std::max(small_bytes, p.scratch_hint));   // the size the previous call ended with: no regrowth
     Arena ar{p.scratch.p, p.scratch.n, 0};
     auto d_segs = ar.take<SegIn>(nseg);
     auto d_seg_local = ar.take<int32_t>(nseg);
     auto d_counts = ar.take<int64_t>((size_t)nw);
     auto d_off = ar.take<int64_t>((size_t)nw + 1);
+    auto rec_n = ar.take<unsigned long long>(1);
+    auto rec_w = ar.take<int32_t>((size_t)rec_slots);
+    auto rec_i = ar.take<int32_t>((size_t)rec_slots);
+    auto rec_c = ar.take<int32_t>((size_t)rec_slots);
+    auto rec_ta = ar.take<double>((size_t)rec_slots);
+    auto rec_tb = ar.take<double>((size_t)rec_slots);
     NFX_CUDA(cudaMemcpyAsync(d_segs.p, segs.data(), sizeof(SegIn) * nseg, cudaMemcpyHostToDevice, s));
     NFX_CUDA(cudaMemcpyAsync(d_seg_local.p, seg_local.data(), sizeof(int32_t) * nseg, cudaMemcpyHostToDevice, s));
+    NFX_CUDA(cudaMemsetAsync(rec_n.p, 0, sizeof(unsigned long long), s));
+    RecList rec{rec_n.p, rec_slots / kRecChunk, rec_w.p, rec_i.p, rec_c.p, rec_ta.p, rec_tb.p};
 
-    // count
+    // count (and record)
     const unsigned tb = nblk(nw * 32, 128);
     k1_traverse<false><<<tb, 128, 0, s>>>(g.verts.p, g.ncell, g.box1.p, g.nl1, g.box2.p, g.nl2, g.box3.p, g.nl3, d_segs.p, nseg, nimg,
-                                         p.period_x, d_counts.p, nullptr, nullptr, nullptr, nullptr, nullptr);
+                                         p.period_x, d_counts.p, nullptr, nullptr, nullptr, nullptr, nullptr, rec);
     count_launch();
     NFX_CUDA(cudaGetLastError());
     exclusive_scan(d_counts.p, d_off.p, nw, d_tmp, s);
     std::vector<int64_t> h_off((size_t)nw + 1);
+    unsigned long long h_chunks = 0;
     NFX_CUDA(cudaMemcpyAsync(h_off.data(), d_off.p, sizeof(int64_t) * (nw + 1), cudaMemcpyDeviceToHost, s));
+    NFX_CUDA(cudaMemcpyAsync(&h_chunks, rec_n.p, sizeof h_chunks, cudaMemcpyDeviceToHost, s));
     NFX_CUDA(cudaStreamSynchronize(s));
     const int64_t nsub = h_off[nw];
     p.nsub = nsub;
+    p.nsub_hint = nsub;
+    const bool rec_ok = rec.cap_chunks > 0 && (int64_t)h_chunks <= rec.cap_chunks;
 
     // per-segment / per-transect offsets
     std::vector<int64_t> h_seg_off(nseg + 1);
@@ -956,10 +1053,21 @@ void pli_compute_weights(PliDev& p, int ntransects, const int* offsets, const do
         std::swap(bigger.n, p.scratch.n);
         const size_t used = ar.used;
         ar = Arena{p.scratch.p, p.scratch.n, used};
-        d_segs.p = reinterpret_cast<SegIn*>(p.scratch.p + ((unsigned char*)d_segs.p - bigger.p));
-        d_seg_local.p = reinterpret_cast<int32_t*>(p.scratch.p + ((unsigned char*)d_seg_local.p - bigger.p));
-        d_counts.p = reinterpret_cast<int64_t*>(p.scratch.p + ((unsigned char*)d_counts.p - bigger.p));
-        d_off.p = reinterpret_cast<int64_t*>(p.scratch.p + ((unsigned char*)d_off.p - bigger.p));
+        auto rebase = [&](auto& view) {   // same offset in the new buffer (bigger.p is the old one after the swap)
+            using PT = decltype(view.p);
+            view.p = reinterpret_cast<PT>(p.scratch.p + ((unsigned char*)view.p - bigger.p));
+        };
+        rebase(d_segs);
+        rebase(d_seg_local);
+        rebase(d_counts);
+        rebase(d_off);
+        rebase(rec_n);
+        rebase(rec_w);
+        rebase(rec_i);
+        rebase(rec_c);
+        rebase(rec_ta);
+        rebase(rec_tb);
+        rec = RecList{rec_n.p, rec.cap_chunks, rec_w.p, rec_i.p, rec_c.p, rec_ta.p, rec_tb.p};
     }
     auto d_seg_off = ar.take<int64_t>(nseg + 1);
     NFX_CUDA(cudaMemcpyAsync(d_seg_off.p, h_seg_off.data(), sizeof(int64_t) * (nseg + 1), cudaMemcpyHostToDevice, s));
@@ -974,8 +1082,17 @@ void pli_compute_weights(PliDev& p, int ntransects, const int* offsets, const do
         auto r_tb = ar.take<double>(ns);
         auto kb = ar.take<int64_t>(ns);
         auto perm = ar.take<int64_t>(ns);
-        k1_traverse<true><<<tb, 128, 0, s>>>(g.verts.p, g.ncell, g.box1.p, g.nl1, g.box2.p, g.nl2, g.box3.p, g.nl3, d_segs.p, nseg, nimg,
-                                            p.period_x, nullptr, d_off.p, r_cell.p, r_img.p, r_ta.p, r_tb.p);
+        if (rec_ok) {   // the count pass recorded every hit: scatter instead of a second traversal
+            const int64_t nslots = (int64_t)h_chunks * kRecChunk;
+            if (nslots > 0)
+                k_scatter_records<<<nblk(nslots, 256), 256, 0, s>>>(rec, nslots, d_off.p, nimg, r_cell.p, r_img.p, r_ta.p,
+                                                                   r_tb.p);
+        } else {
+            k1_traverse<true><<<tb, 128, 0, s>>>(g.verts.p, g.ncell, g.box1.p, g.nl1, g.box2.p, g.nl2, g.box3.p, g.nl3,
+                                                d_segs.p, nseg, nimg, p.period_x, nullptr, d_off.p, r_cell.p, r_img.p,
+                                                r_ta.p, r_tb.p, RecList{nullptr, 0, nullptr, nullptr, nullptr, nullptr,
+                                                                        nullptr});
+        }
         // sort inside each segment by (ta, cell, image)
         k_make_sort1_key<<<nblk(nsub, 256), 256, 0, s>>>(r_cell.p, r_img.p, nsub, kb.p);
         auto ska = ar.take<double>(ns);
@@ -1058,6 +1175,12 @@ void pli_compute_weights(PliDev& p, int ntransects, const int* offsets, const do
                 NFX_CUDA(cudaMemsetAsync(p.csr[o][l].rowptr.p, 0, sizeof(int64_t) * (ntransects + 1), s));
             }
         NFX_CUDA(cudaStreamSynchronize(s));
+    }
+    // the arena is kept for the next call unless it is large (ORCA12 with 1024 transects: 1.2 GB)
+    p.scratch_hint = p.scratch.n;
+    if (p.scratch.n > ((size_t)256 << 20)) {
+        NFX_CUDA(cudaStreamSynchronize(s));
+        p.scratch.release();
     }
 }
 

@@ -88,6 +88,29 @@ def test_k1_random_transects_bit_exact(gpu, oracle, delta):
     assert n > 1000
 
 
+def test_k1_record_list_and_fallback_agree(gpu, oracle):
+    """the count pass records its hits so that the fill pass is a scatter; when the record list (sized from the
+    previous call on the handle) is too small the fill pass traverses again -- same lists either way"""
+    g = oracle.DataGen(nx=720, ny=360)
+    P = g.points()
+    long_tr = [tr([(-179.3, -80.2), (178.9, 79.7)]), tr([(-100, 60), (120, -70), (150, 10)])]
+    _, p1 = _build(gpu, P, g.ny, g.nx)
+    p1.computeWeights(long_tr)                                  # first call: list sized from the geometry
+    a = p1.getSubsegments()
+    _, p2 = _build(gpu, P, g.ny, g.nx)
+    p2.computeWeights([tr([(10.2, 10.1), (10.9, 10.4)])])       # a handful of sub-segments -> a tiny hint
+    p2.computeWeights(long_tr)                                  # list overflows -> second traversal
+    b = p2.getSubsegments()
+    assert len(a['cell']) > 1500
+    for key in ('offsets', 'cell', 'seg', 'ta', 'tb', 'coeff', 'w'):
+        assert numpy.array_equal(a[key], b[key]), key
+    p2.computeWeights(long_tr)                                  # now the hint fits: record path again
+    c = p2.getSubsegments()
+    for key in ('cell', 'ta', 'w'):
+        assert numpy.array_equal(a[key], c[key]), key
+    _check_lists(oracle, p1, oracle.Grid(P), long_tr)
+
+
 def test_k1_counterclock_and_no_period(gpu, oracle):
     g = oracle.DataGen(nx=36, ny=18)
     P = g.points()
@@ -211,6 +234,16 @@ def test_k2_f32_special_values(gpu, oracle, shape, thick_max):
     finally:
         _lib.set_option(_lib.NFX_OPT_K2_VARIANT, _lib.NFX_K2_AUTO)
     assert numpy.array_equal(assert_bitwise_nan, efh, equal_nan=True)
+    if thick_max < 1.e30:
+        # the same special values through the e3u/e3v path (both factors float32, bit shuffle + exact rescale):
+        # e3 == dz[k] must reproduce the 1-D thickness result bit for bit
+        th32 = th.astype(numpy.float32)
+        e3 = torch.from_numpy(numpy.ascontiguousarray(numpy.broadcast_to(th32[None, :, None], (1, nz, ny * nx)))).to(d)
+        ref_1d = gpu.edgeFluxAssemble(dev_args[0], dev_args[1], torch.from_numpy(th32.astype(numpy.float64)).to(d),
+                                      dev_args[3], dev_args[4]).cpu().numpy()
+        got_e3 = gpu.edgeFluxAssemble(dev_args[0].reshape(nt, nz, -1), dev_args[1].reshape(nt, nz, -1), None,
+                                      dev_args[3], dev_args[4], e3u=e3, e3v=e3).cpu().numpy()
+        assert numpy.array_equal(got_e3, ref_1d, equal_nan=True)
     ninf = 0
     for t in range(nt):
         with numpy.errstate(all='ignore'):

@@ -4,12 +4,13 @@
 // /root/reference/nemoflux/field.py:44-49: periodX=360, counterclock=False, enableFolding=False).
 //
 // Pipeline (all on the device, one-off per set of transects):
-//   locator : 2-level bounding-box hierarchy with fan-out 32 (one warp reduces one node)
-//   count   : ONE WARP PER (TARGET SEGMENT, x-period image): lanes test 32 boxes / 32 cells at a time,
-//             ballot-compact the accepted cells
+//   locator : 3-level bounding-box hierarchy with fan-out 32 (one warp reduces one node)
+//   count   : ONE WARP PER (TARGET SEGMENT, x-period image, piece of the segment): lanes test 32 boxes / 32 cells
+//             at a time, ballot-compact the accepted cells; the hits are also appended to a record list
 //   scan    : exclusive scan of the per-warp counts
-//   fill    : same traversal, writes (cell, image, ta, tb)
-//   sort    : per segment by (ta, cell, image)  (rank sort, tiles of keys in shared memory)
+//   fill    : scatter of the record list into (cell, image, ta, tb); the same traversal again when the list
+//             (sized from an estimate) was too small
+//   sort    : per segment by (ta, cell, image): chunks of 4096 keys sorted in shared memory, then merge rank
 //   weights : duplicity coefficient, inverse bilinear map (Newton, fixed operation order), 4 edge
 //             weights per sub-segment with mint's edge order 0=S 1=E 2=N 3=W and sign convention
 //   map     : mint's std::map<(cell,edge),weight> view and the CSR lists consumed by K3

@@ -11,8 +11,9 @@
 //     ... | K2 tiles of batch b (ntiles items) | K3 items of batch b-1 (nk3 items) | K2 tiles of b+1 | ...
 // K2 item: z-sum + metric factors for 256*VEC columns (field.py:145-163, 195-196, 225-228), written to ring
 //          slot b % R; waits (b >= R) until K3 of batch b-R has finished reading that slot.
-// K3 item: 8 transects x batch b: one warp per transect gathers from the slot (L2) and writes
-//          partial[(t, q), m]; waits until all K2 tiles of batch b are done.
+// K3 item: 8 sub-rows (<= 4096 CSR entries of one transect inside panel q) x batch b: one warp per sub-row gathers
+//          from the slot (L2) and writes its partial sum; waits until all K2 tiles of batch b are done.
+// The batches are visited panel-major (batch_map), so a panel's slice of the CSR stays in L2 across time steps.
 // Every wait is on items with a SMALLER id, i.e. items already taken by a running CTA -> no deadlock, whatever
 // the number of resident CTAs.  Spins are bounded; on overflow an error flag is raised instead of hanging.
 //

@@ -189,6 +189,12 @@ def run_reference(args):
     from nemoflux_b200 import synth
     from oracle import oracle as O
     O.lib()
+    cores = os.cpu_count()
+    try:        # torchrun exports OMP_NUM_THREADS=1: give the BLAS behind numpy.tensordot all host threads back
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=cores)
+    except Exception:
+        pass
     syn = synth.make(args.workload)
     nt_local = args.nt_local or syn.nt
     g, plis = build_oracle_plis(O, syn)
@@ -203,7 +209,6 @@ def run_reference(args):
     dt = float(numpy.mean(times))
     units = syn.units_per_step() * sample
     value = units / dt
-    cores = os.cpu_count()
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': 1e3 * dt, 'higher_is_better': True, 'scaling': 'weak',
@@ -490,6 +495,11 @@ def run_b200(args):
         nc = max(1, min(nc, int(8e9 // step_bytes_uv)))
         steps = list(range(nc))
         fields = [syn.uv_host(t) for t in steps]
+        try:    # under torchrun OMP_NUM_THREADS=1 would throttle the BLAS behind numpy.tensordot
+            from threadpoolctl import threadpool_limits
+            threadpool_limits(limits=os.cpu_count())
+        except Exception:
+            pass
         cpu_reference_pass(O, syn, oplis, fields[:1], args.order)          # warm-up
         dt_np, ser_np = cpu_reference_pass(O, syn, oplis, fields, args.order)
         # flux error relative to sum |w f|

@@ -46,22 +46,28 @@ extern "C" {
 #define NFX_ORDER_LIST 0  /* emission order: sub-segment by sub-segment, edges 0..3          */
 #define NFX_ORDER_MAP 1   /* mint's std::map<(cellId,edgeIndex),weight> order (default)     */
 
-/* edge-flux kernel variants (nfx_set_option NFX_OPT_K2_VARIANT) */
-#define NFX_K2_AUTO 0
-#define NFX_K2_LDG 1      /* direct vectorised global loads, widest legal (256-bit on sm_100a) */
-#define NFX_K2_TMA 2      /* TMA (cp.async.bulk.tensor) staged level tiles                    */
-#define NFX_K2_LDG128 3   /* direct loads capped at 128 bits                                  */
-#define NFX_OPT_K2_VARIANT 1
-#define NFX_OPT_K2_UNROLL 2   /* levels in flight per thread (0 = default) */
-#define NFX_OPT_K2_BLOCK 3    /* threads per CTA (0 = default)             */
-#define NFX_OPT_FAST_SERIES 4 /* nfx_flux_series with eflux == NULL: 1 (default) fused L2-resident pass when one time
-                                 step of edge fluxes fits a ring slot, 2 always fused, 0 never (two launches)      */
-#define NFX_OPT_K2_ALU_MASK 6  /* float32 storage: which of every 5 levels are converted on the ALU (-1 default) */
-#define NFX_OPT_RING_SLOT_MB 5
-#define NFX_OPT_LAST_SERIES_PATH 8 /* read only: 1 = the last nfx_flux_series* call took the fused pass, 0 = two launches, -1 = none yet */
-#define NFX_OPT_FUSED_ORDER 9      /* fused pass: bit 0 = visit (time step, panel) batches panel-major, bit 1 = K3 gathers unrolled x8; default 3 */
-#define NFX_OPT_FUSED_F64_CTAS 10  /* fused pass, float64 storage, 256-bit loads: register budget for 2 or 4 CTAs per SM (0 = default 3) */
-#define NFX_OPT_FUSED_F32_SHAPE 7  /* fused pass, float32 storage: 10 * vector width + unroll (85, 45, 83, 43); 0 default */ /* size of one eflux ring slot of that path in MB (default 8)                */
+/* ---- tuning options (nfx_set_option / nfx_get_option) ----------------------------------------------------------
+ * Process-wide, not thread safe: set them before the calls they affect.  Every value changes speed only, never a
+ * result bit (the parity tests sweep them).  The defaults are the measured optimum on B200 (profiles/). */
+#define NFX_OPT_K2_VARIANT 1       /* edge-flux kernel of the two-launch path: */
+#define NFX_K2_AUTO 0              /*   direct loads, 256-bit for float64 storage, 128-bit for float32 */
+#define NFX_K2_LDG 1               /*   direct vectorised global loads, widest legal (256-bit on sm_100a) */
+#define NFX_K2_TMA 2               /*   1-D bulk copies (cp.async.bulk + mbarrier) into shared-memory stages */
+#define NFX_K2_LDG128 3            /*   direct loads capped at 128 bits */
+#define NFX_OPT_K2_UNROLL 2        /* levels in flight per thread (0 = default 5); TMA: tile configuration id */
+#define NFX_OPT_K2_BLOCK 3         /* threads per CTA (0 = default 256) */
+#define NFX_OPT_FAST_SERIES 4      /* nfx_flux_series with eflux == NULL: 1 (default) fused L2-resident pass where it
+                                      is the faster one, 2 always fused, 0 never (two launches) */
+#define NFX_OPT_RING_SLOT_MB 5     /* size of one edge-flux ring slot of the fused pass in MB (default 8) */
+#define NFX_OPT_K2_ALU_MASK 6      /* float32 storage, two-launch K2: which of every 5 levels take the bit-shuffle
+                                      conversion instead of F2F (-1 = default, all; 0 = none) */
+#define NFX_OPT_FUSED_F32_SHAPE 7  /* fused pass, float32 storage: 10 * vector width + unroll (85, 45, 83, 43; 0 = 45) */
+#define NFX_OPT_LAST_SERIES_PATH 8 /* READ ONLY: 1 = the last nfx_flux_series* call took the fused pass, 0 = two
+                                      launches, -1 = none yet */
+#define NFX_OPT_FUSED_ORDER 9      /* fused pass: bit 0 = visit the (time step, panel) batches panel-major, bit 1 = K3
+                                      gathers unrolled x8 (default 3) */
+#define NFX_OPT_FUSED_F64_CTAS 10  /* fused pass, float64 storage, 256-bit loads: register budget for 2 or 4 CTAs per
+                                      SM (0 = default 3) */
 
 typedef struct nfx_grid nfx_grid;
 typedef struct nfx_pli nfx_pli;

@@ -297,16 +297,18 @@ k23_fused(const FusedArgs a) {
 
 template <typename T, int VEC, int UNROLL, int CTAS = 0>
 int fused_grid() {
-    static int grid = 0;
-    if (grid == 0) {
-        int dev = 0, sms = 0, per_sm = 0;
-        NFX_CUDA(cudaGetDevice(&dev));
+    static int grid[64] = {0};   // per device ordinal
+    int dev = 0;
+    NFX_CUDA(cudaGetDevice(&dev));
+    int& g = grid[dev & 63];
+    if (g == 0) {
+        int sms = 0, per_sm = 0;
         NFX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         NFX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k23_fused<T, VEC, UNROLL, CTAS>, kFusedBlock,
                                                                sizeof(double) * 256));
-        grid = sms * std::max(per_sm, 1);
+        g = sms * std::max(per_sm, 1);
     }
-    return grid;
+    return g;
 }
 
 template <typename T, int VEC, int UNROLL, int CTAS = 0>

@@ -437,19 +437,12 @@ k2_edgeflux_tma(const T* __restrict__ u, const T* __restrict__ v, const double* 
 template <typename T, int TC, int KL, int STAGES, int CT>
 void launch_tma(const T* u, const T* v, const double* dz, const double* arc1, const double* arc2, double* eflux, int nt,
                 int nz, int64_t ncell, double scale, int use_scale, T fill, int has_fill, cudaStream_t s) {
-    static int num_sms = 0;
-    if (num_sms == 0) {
-        int dev = 0;
-        NFX_CUDA(cudaGetDevice(&dev));
-        NFX_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-    }
+    int dev = 0, num_sms = 0;   // queried per call: a few hundred ns, right for every device of the process
+    NFX_CUDA(cudaGetDevice(&dev));
+    NFX_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
     const size_t smem = 2 * sizeof(T) * (size_t)STAGES * KL * TC + sizeof(uint64_t) * 2 * STAGES + sizeof(double) * nz;
     auto kern = k2_edgeflux_tma<T, TC, KL, STAGES, CT>;
-    static bool configured = false;
-    if (!configured) {
-        NFX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        configured = true;
-    }
+    NFX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));   // per device
     NFX_REQUIRE(smem <= 227 * 1024, "edgeflux (TMA): too many levels for the shared-memory ring");
     const int ntiles = (int)((ncell + TC - 1) / TC);
     const int64_t nitems = (int64_t)nt * ntiles;

@@ -83,7 +83,8 @@ static int64_t fused_panel_cells(int64_t ncell) {
 static void flux_series_fast(PliDev& p, const void* u, const void* v, int dtype, const double* thickness,
                              const double* arc1, const double* arc2, int nt, int nz, int64_t ld, int sverdrup,
                              double fill, int order, double* series, cudaStream_t stream, int64_t batch_begin = 0,
-                             int64_t batch_end = -1) {
+                             int64_t batch_end = -1, const void* e3u = nullptr, const void* e3v = nullptr,
+                             int64_t e3_tstride = 0) {
     NFX_REQUIRE(order == NFX_ORDER_LIST || order == NFX_ORDER_MAP, "order must be NFX_ORDER_LIST or NFX_ORDER_MAP");
     NFX_REQUIRE(p.csr[order][0].rowptr.p != nullptr, "computeWeights was not called");
     NFX_REQUIRE(p.has_compact, "nfx_grid_set_cgrid_shape must be called before computeWeights for the flux path");
@@ -96,7 +97,7 @@ static void flux_series_fast(PliDev& p, const void* u, const void* v, int dtype,
     p.partial.ensure((size_t)nt * std::max<int64_t>(pl.nsr, 1));
     if (batch_end < 0) batch_end = (int64_t)nt * pl.npanels;
     flux_series_fused(p, pl, u, v, dtype, thickness, arc1, arc2, nt, nz, ld, sverdrup, fill, batch_begin, batch_end,
-                      p.partial.p, stream);
+                      p.partial.p, stream, e3u, e3v, e3_tstride);
     reduce_subrows(p.partial.p, nt, pl.nsr, pl.tr_ptr.p, pl.tr_sr.p, M, series, stream);
 }
 
@@ -113,6 +114,18 @@ static bool use_fused(const PliDev& p, int dtype, const void* u, const void* v, 
     if (ncell * 16 <= g_slot_bytes) return true;
     // several panels: only with 256-bit loads (32-byte aligned rows), where the same-box A/B shows -8 % time
     return vec == 4;
+}
+
+// the same decision with per-column scale factors (four streams; the fused kernels use 128-bit loads there):
+// float64 when one panel holds a time step of edge fluxes, float32 as above
+static bool use_fused_e3(const PliDev& p, int dtype, const void* u, const void* v, const void* e3u, const void* e3v,
+                         int64_t e3_tstride, int64_t ld) {
+    if (g_fast_series == 2) return true;
+    if (g_fast_series == 0 || !p.grid) return false;
+    const int64_t ncell = p.grid->ncell;
+    if (dtype == NFX_F64) return ncell * 16 <= g_slot_bytes;
+    const uintptr_t more = (uintptr_t)e3u | (uintptr_t)e3v | (uintptr_t)(e3_tstride * 4);
+    return fused_tile_columns(dtype, u, v, ncell, ld, fused_panel_cells(ncell), more) >= 4;
 }
 
 static const Csr& pick_csr(PliDev& p, int order, int layout) {
@@ -571,13 +584,21 @@ int nfx_flux_series_e3(nfx_pli** self, const void* u, const void* v, const void*
         const int64_t ncell = p.grid->ncell;
         NFX_REQUIRE(ld >= ncell, "ld must be >= the number of cells");
         NFX_REQUIRE(e3_nt == 1 || e3_nt == nt, "e3u/e3v must hold 1 (time-invariant) or nt time steps");
+        const int64_t e3_tstride = e3_nt == 1 ? 0 : (int64_t)nz * ld;
+        g_last_series_fused = 0;
+        if (eflux == nullptr && use_fused_e3(p, dtype, u, v, e3u, e3v, e3_tstride, ld)) {
+            g_last_series_fused = 1;
+            flux_series_fast(p, u, v, dtype, nullptr, arc1, arc2, nt, nz, ld, sverdrup, fill, order, series,
+                             (cudaStream_t)stream, 0, -1, e3u, e3v, e3_tstride);
+            return;
+        }
         const Csr& c = pick_csr(p, order, 1);
         if (eflux == nullptr) {
             p.stage_eflux[0].ensure((size_t)nt * 2 * ncell);
             eflux = p.stage_eflux[0].p;
         }
         edgeflux_assemble_panel(u, v, dtype, nullptr, arc1, arc2, nt, nz, ncell, ld, sverdrup, fill, eflux, 0, g_k2opt,
-                                (cudaStream_t)stream, e3u, e3v, e3_nt == 1 ? 0 : (int64_t)nz * ld);
+                                (cudaStream_t)stream, e3u, e3v, e3_tstride);
         csr_integrate(c, p.ntransects, eflux, ncell * 2, nt, series, (cudaStream_t)stream);
     });
 }

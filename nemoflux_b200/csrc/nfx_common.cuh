@@ -215,8 +215,10 @@ void build_panel_plan(PliDev& p, int order, int64_t panel_cells, cudaStream_t s)
 // K2+K3 fused persistent pass (nfx_k23_fused.cu)
 void flux_series_fused(PliDev& p, const PanelPlan& pl, const void* u, const void* v, int dtype, const double* thickness,
                        const double* arc1, const double* arc2, int nt, int nz, int64_t ld, int sverdrup, double fill,
-                       int64_t batch_begin, int64_t batch_end, double* out, cudaStream_t s);
-int fused_tile_columns(int dtype, const void* u, const void* v, int64_t ncell, int64_t ld, int64_t panel);
+                       int64_t batch_begin, int64_t batch_end, double* out, cudaStream_t s, const void* e3u = nullptr,
+                       const void* e3v = nullptr, int64_t e3_tstride = 0);
+int fused_tile_columns(int dtype, const void* u, const void* v, int64_t ncell, int64_t ld, int64_t panel,
+                       uintptr_t more_bits = 0);
 int fused_error_flag(PliDev& p, cudaStream_t s);
 extern int g_fused_f32_shape;
 extern int g_fused_order;

@@ -45,6 +45,9 @@ constexpr unsigned kSpinLimit = 1u << 27;
 struct FusedArgs {
     const void* u;
     const void* v;
+    const void* e3u;        // E3 kernels: per-column, per-level scale factors (dtype and plane layout of u, v) ...
+    const void* e3v;
+    int64_t e3_tstride;     // ... elements per time step of e3u/e3v, 0 = time-invariant
     const double* dz;
     const double* arc1;
     const double* arc2;
@@ -92,15 +95,18 @@ __device__ __forceinline__ bool cta_wait(const int* flag, int target, int* err, 
 }
 
 // resident CTAs per SM the register allocation is bounded for (0 = the default of the shape)
-template <typename T, int VEC, int UNROLL>
+template <typename T, int VEC, int UNROLL, bool E3 = false>
 constexpr int fused_min_ctas(int wanted) {
     if (wanted > 0) return wanted;
+    if (E3) return 3;   // four streams: 80 registers hold the loads of a batch without spilling
     if (sizeof(T) == 4) return (VEC == 8 && UNROLL == 5) ? 3 : 4;
     return kFusedF64Ctas;
 }
 
-template <typename T, int VEC, int UNROLL, int CTAS = 0>
-__global__ void __launch_bounds__(kFusedBlock, fused_min_ctas<T, VEC, UNROLL>(CTAS))
+// E3: e3u[t,k,c] / e3v[t,k,c] replace the 1-D thickness dz[k], the arithmetic of
+// k2_edgeflux_ldg<..., E3 = true> (nfx_k2_edgeflux.cu) operation for operation -> the same edge fluxes bit for bit
+template <typename T, int VEC, int UNROLL, int CTAS = 0, bool E3 = false>
+__global__ void __launch_bounds__(kFusedBlock, fused_min_ctas<T, VEC, UNROLL, E3>(CTAS))
 k23_fused(const FusedArgs a) {
     extern __shared__ double s_dz[];
     __shared__ int s_item;
@@ -108,12 +114,14 @@ k23_fused(const FusedArgs a) {
     // float32 storage: levels go through clean_scaled() (nfx_stream_ops.cuh) with dz * 2^896 in s_dz[nz..2nz)
     constexpr bool kScaled = sizeof(T) == 4;
     int big = 0;
-    for (int k = threadIdx.x; k < a.nz; k += kFusedBlock) {
-        const double d = a.dz[k];
-        s_dz[k] = d;
-        if constexpr (kScaled) {
-            s_dz[a.nz + k] = d * kScaleUp;
-            big |= !(fabs(d) < kScaleLimit);
+    if constexpr (!E3) {
+        for (int k = threadIdx.x; k < a.nz; k += kFusedBlock) {
+            const double d = a.dz[k];
+            s_dz[k] = d;
+            if constexpr (kScaled) {
+                s_dz[a.nz + k] = d * kScaleUp;
+                big |= !(fabs(d) < kScaleLimit);
+            }
         }
     }
     const bool redo_all = __syncthreads_or(big) != 0;
@@ -121,6 +129,8 @@ k23_fused(const FusedArgs a) {
     using V = typename P::type;
     const T* __restrict__ u = reinterpret_cast<const T*>(a.u);
     const T* __restrict__ v = reinterpret_cast<const T*>(a.v);
+    const T* __restrict__ e3u = reinterpret_cast<const T*>(a.e3u);
+    const T* __restrict__ e3v = reinterpret_cast<const T*>(a.e3v);
     int* counter = a.sync;
     int* err = a.sync + 1;
     int* k2done = a.sync + 2;
@@ -158,6 +168,8 @@ k23_fused(const FusedArgs a) {
                 const int64_t c = pc0 + cl;
                 const T* pu = u + t * a.nz * a.ld + c;
                 const T* pv = v + t * a.nz * a.ld + c;
+                const T* pe = E3 ? e3u + t * a.e3_tstride + c : nullptr;
+                const T* pf = E3 ? e3v + t * a.e3_tstride + c : nullptr;
                 double su[VEC], sv[VEC];
 #pragma unroll
                 for (int e = 0; e < VEC; ++e) {
@@ -167,44 +179,72 @@ k23_fused(const FusedArgs a) {
                 float amax = 0.f;
                 int k = 0;
                 for (; k + UNROLL <= a.nz; k += UNROLL) {
-                    V ru[UNROLL], rv[UNROLL];
+                    V ru[UNROLL], rv[UNROLL], re[E3 ? UNROLL : 1], rf[E3 ? UNROLL : 1];
 #pragma unroll
                     for (int qq = 0; qq < UNROLL; ++qq) {
                         ru[qq] = ld_stream(reinterpret_cast<const V*>(pu + (int64_t)(k + qq) * a.ld), pol_ef);
                         rv[qq] = ld_stream(reinterpret_cast<const V*>(pv + (int64_t)(k + qq) * a.ld), pol_ef);
+                        if constexpr (E3) {
+                            re[qq] = ld_stream(reinterpret_cast<const V*>(pe + (int64_t)(k + qq) * a.ld), pol_ef);
+                            rf[qq] = ld_stream(reinterpret_cast<const V*>(pf + (int64_t)(k + qq) * a.ld), pol_ef);
+                        }
                     }
 #pragma unroll
                     for (int qq = 0; qq < UNROLL; ++qq) {
                         pin(ru[qq]);
                         pin(rv[qq]);
+                        if constexpr (E3) {
+                            pin(re[qq]);
+                            pin(rf[qq]);
+                        }
                     }
 #pragma unroll
                     for (int qq = 0; qq < UNROLL; ++qq) {
-                        T x[VEC], y[VEC];
+                        T x[VEC], y[VEC], ex[VEC], ey[VEC];
                         P::unpack(ru[qq], x);
                         P::unpack(rv[qq], y);
-                        const double d = s_dz[(kScaled ? a.nz : 0) + k + qq];
+                        if constexpr (E3) {
+                            P::unpack(re[qq], ex);
+                            P::unpack(rf[qq], ey);
+                        }
+                        const double d = E3 ? 0.0 : s_dz[(kScaled ? a.nz : 0) + k + qq];
 #pragma unroll
                         for (int e = 0; e < VEC; ++e) {
-                            if constexpr (kScaled) {
+                            if constexpr (kScaled && E3) {
+                                // both factors come from float32: undo the 2^-896 of each bit shuffle exactly
+                                const double du = __dmul_rn(clean_scaled(ex[e], fill, a.has_fill, amax), kScaleUp);
+                                const double dv = __dmul_rn(clean_scaled(ey[e], fill, a.has_fill, amax), kScaleUp);
+                                const double xu = __dmul_rn(clean_scaled(x[e], fill, a.has_fill, amax), kScaleUp);
+                                const double xv = __dmul_rn(clean_scaled(y[e], fill, a.has_fill, amax), kScaleUp);
+                                su[e] = __dadd_rn(su[e], __dmul_rn(du, xu));
+                                sv[e] = __dadd_rn(sv[e], __dmul_rn(dv, xv));
+                            } else if constexpr (kScaled) {
                                 su[e] = __dadd_rn(su[e], __dmul_rn(d, clean_scaled(x[e], fill, a.has_fill, amax)));
                                 sv[e] = __dadd_rn(sv[e], __dmul_rn(d, clean_scaled(y[e], fill, a.has_fill, amax)));
                             } else {
-                                su[e] = __dadd_rn(su[e], __dmul_rn(d, clean<T>(x[e], fill, a.has_fill)));
-                                sv[e] = __dadd_rn(sv[e], __dmul_rn(d, clean<T>(y[e], fill, a.has_fill)));
+                                const double du = E3 ? clean<T>(ex[e], fill, a.has_fill) : d;
+                                const double dv = E3 ? clean<T>(ey[e], fill, a.has_fill) : d;
+                                su[e] = __dadd_rn(su[e], __dmul_rn(du, clean<T>(x[e], fill, a.has_fill)));
+                                sv[e] = __dadd_rn(sv[e], __dmul_rn(dv, clean<T>(y[e], fill, a.has_fill)));
                             }
                         }
                     }
                 }
                 for (; k < a.nz; ++k) {
-                    T x[VEC], y[VEC];
+                    T x[VEC], y[VEC], ex[VEC], ey[VEC];
                     P::unpack(ld_stream(reinterpret_cast<const V*>(pu + (int64_t)k * a.ld), pol_ef), x);
                     P::unpack(ld_stream(reinterpret_cast<const V*>(pv + (int64_t)k * a.ld), pol_ef), y);
-                    const double d = s_dz[k];
+                    if constexpr (E3) {
+                        P::unpack(ld_stream(reinterpret_cast<const V*>(pe + (int64_t)k * a.ld), pol_ef), ex);
+                        P::unpack(ld_stream(reinterpret_cast<const V*>(pf + (int64_t)k * a.ld), pol_ef), ey);
+                    }
+                    const double d = E3 ? 0.0 : s_dz[k];
 #pragma unroll
                     for (int e = 0; e < VEC; ++e) {
-                        su[e] = __dadd_rn(su[e], __dmul_rn(d, clean<T>(x[e], fill, a.has_fill)));
-                        sv[e] = __dadd_rn(sv[e], __dmul_rn(d, clean<T>(y[e], fill, a.has_fill)));
+                        const double du = E3 ? clean<T>(ex[e], fill, a.has_fill) : d;
+                        const double dv = E3 ? clean<T>(ey[e], fill, a.has_fill) : d;
+                        su[e] = __dadd_rn(su[e], __dmul_rn(du, clean<T>(x[e], fill, a.has_fill)));
+                        sv[e] = __dadd_rn(sv[e], __dmul_rn(dv, clean<T>(y[e], fill, a.has_fill)));
                     }
                 }
                 if constexpr (kScaled) {
@@ -216,11 +256,13 @@ k23_fused(const FusedArgs a) {
                         }
 #pragma unroll 1
                         for (int kk = 0; kk < a.nz; ++kk) {
-                            const double d = s_dz[kk];
+                            const double d = E3 ? 0.0 : s_dz[kk];
 #pragma unroll
                             for (int e = 0; e < VEC; ++e) {
-                                su[e] = __dadd_rn(su[e], __dmul_rn(d, clean<T>(pu[(int64_t)kk * a.ld + e], fill, a.has_fill)));
-                                sv[e] = __dadd_rn(sv[e], __dmul_rn(d, clean<T>(pv[(int64_t)kk * a.ld + e], fill, a.has_fill)));
+                                const double du = E3 ? clean<T>(pe[(int64_t)kk * a.ld + e], fill, a.has_fill) : d;
+                                const double dv = E3 ? clean<T>(pf[(int64_t)kk * a.ld + e], fill, a.has_fill) : d;
+                                su[e] = __dadd_rn(su[e], __dmul_rn(du, clean<T>(pu[(int64_t)kk * a.ld + e], fill, a.has_fill)));
+                                sv[e] = __dadd_rn(sv[e], __dmul_rn(dv, clean<T>(pv[(int64_t)kk * a.ld + e], fill, a.has_fill)));
                             }
                         }
                     }
@@ -295,7 +337,7 @@ k23_fused(const FusedArgs a) {
     }
 }
 
-template <typename T, int VEC, int UNROLL, int CTAS = 0>
+template <typename T, int VEC, int UNROLL, int CTAS = 0, bool E3 = false>
 int fused_grid() {
     static int grid[64] = {0};   // per device ordinal
     int dev = 0;
@@ -304,16 +346,24 @@ int fused_grid() {
     if (g == 0) {
         int sms = 0, per_sm = 0;
         NFX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        NFX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k23_fused<T, VEC, UNROLL, CTAS>, kFusedBlock,
+        NFX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k23_fused<T, VEC, UNROLL, CTAS, E3>, kFusedBlock,
                                                                sizeof(double) * 256));
         g = sms * std::max(per_sm, 1);
     }
     return g;
 }
 
-template <typename T, int VEC, int UNROLL, int CTAS = 0>
+template <typename T, int VEC, int UNROLL, int CTAS = 0, bool E3 = false>
 void launch_fused(const FusedArgs& a, cudaStream_t s) {
-    k23_fused<T, VEC, UNROLL, CTAS><<<fused_grid<T, VEC, UNROLL, CTAS>(), kFusedBlock, sizeof(double) * a.nz * 2, s>>>(a);
+    k23_fused<T, VEC, UNROLL, CTAS, E3>
+        <<<fused_grid<T, VEC, UNROLL, CTAS, E3>(), kFusedBlock, sizeof(double) * a.nz * 2, s>>>(a);
+}
+
+// e3u/e3v kernels: four streamed arrays, so half the columns per thread of the thickness kernels keep the same
+// number of loads in flight at the same register budget (float64: 2 columns x 5 levels, float32: 4 x 3)
+int fused_grid_e3(int dtype, int vec) {
+    if (dtype == NFX_F64) return vec == 2 ? fused_grid<double, 2, 5, 0, true>() : fused_grid<double, 1, 5, 0, true>();
+    return vec == 4 ? fused_grid<float, 4, 3, 0, true>() : fused_grid<float, 1, 5, 0, true>();
 }
 
 int fused_grid_for(int dtype, int vec, int unroll, int ctas) {
@@ -334,9 +384,10 @@ int k3_group_for(int64_t nnz, int64_t nrows) {
     return avg >= 4096 ? 8 : avg >= 1024 ? 4 : avg >= 256 ? 2 : 1;
 }
 
-int fused_tile_columns(int dtype, const void* u, const void* v, int64_t ncell, int64_t ld, int64_t panel) {
-    // widest vector the alignment of every level row and panel start allows
-    const uintptr_t bits = ((uintptr_t)u) | ((uintptr_t)v);
+int fused_tile_columns(int dtype, const void* u, const void* v, int64_t ncell, int64_t ld, int64_t panel,
+                       uintptr_t more_bits) {
+    // widest vector the alignment of every level row and panel start allows (more_bits: further base addresses)
+    const uintptr_t bits = ((uintptr_t)u) | ((uintptr_t)v) | more_bits;
     const bool a16 = (bits & 15) == 0, a32 = (bits & 31) == 0;
     // rows start at multiples of ld, panels at multiples of `panel`; the last panel ends at ncell
     // (a vector may hang over the end of the last panel when the plane is padded: ld >= ncell rounded up)
@@ -355,12 +406,20 @@ int fused_tile_columns(int dtype, const void* u, const void* v, int64_t ncell, i
 
 void flux_series_fused(PliDev& p, const PanelPlan& pl, const void* u, const void* v, int dtype, const double* thickness,
                        const double* arc1, const double* arc2, int nt, int nz, int64_t ld, int sverdrup, double fill,
-                       int64_t batch_begin, int64_t batch_end, double* out, cudaStream_t s) {
+                       int64_t batch_begin, int64_t batch_end, double* out, cudaStream_t s, const void* e3u,
+                       const void* e3v, int64_t e3_tstride) {
     const int64_t ncell = p.grid->ncell;
     const int M = p.ntransects;
-    int vec = fused_tile_columns(dtype, u, v, ncell, ld, pl.panel_cells);
+    const bool e3 = e3u != nullptr;
+    NFX_REQUIRE((e3u == nullptr) == (e3v == nullptr), "fused pass: e3u and e3v go together");
+    NFX_REQUIRE(thickness || e3, "fused pass: needs the layer thickness or e3u/e3v");
+    int vec = fused_tile_columns(dtype, u, v, ncell, ld, pl.panel_cells,
+                                 (uintptr_t)e3u | (uintptr_t)e3v | (uintptr_t)(e3_tstride * (dtype == NFX_F64 ? 8 : 4)));
     int unroll = 5;
-    if (dtype != NFX_F64 && vec >= 4) {
+    if (e3) {
+        vec = dtype == NFX_F64 ? std::min(vec, 2) : (vec >= 4 ? 4 : 1);
+        unroll = (dtype != NFX_F64 && vec == 4) ? 3 : 5;
+    } else if (dtype != NFX_F64 && vec >= 4) {
         // float32 storage: 128-bit loads x 5 levels at 64 registers (4 CTAs per SM) beat 256-bit loads at 80
         // registers (3 CTAs per SM) by 20 % (profiles/r1_f32_alu_sweep.md); the option is a tuning knob
         const int shape = g_fused_f32_shape > 0 ? g_fused_f32_shape : 45;   // 10 * vector width + unroll
@@ -370,6 +429,9 @@ void flux_series_fused(PliDev& p, const PanelPlan& pl, const void* u, const void
     FusedArgs a;
     a.u = u;
     a.v = v;
+    a.e3u = e3u;
+    a.e3v = e3v;
+    a.e3_tstride = e3_tstride;
     a.dz = thickness;
     a.arc1 = arc1;
     a.arc2 = arc2;
@@ -405,7 +467,7 @@ void flux_series_fused(PliDev& p, const PanelPlan& pl, const void* u, const void
     int ctas = 0;   // 0 = the default register budget of the shape
     if (dtype == NFX_F64 && vec == 4 && (g_fused_f64_ctas == 2 || g_fused_f64_ctas == 4)) ctas = g_fused_f64_ctas;
     if (dtype != NFX_F64 && vec == 4 && unroll == 5 && g_fused_f64_ctas == 3) ctas = 3;
-    const int resident = fused_grid_for(dtype, vec, unroll, ctas);
+    const int resident = e3 ? fused_grid_e3(dtype, vec) : fused_grid_for(dtype, vec, unroll, ctas);
     int slots = (2 * resident + a.ntiles - 1) / a.ntiles + 1;
     const int64_t cap = std::max<int64_t>(3, ((int64_t)64 << 20) / (a.slot_elems * 8));
     slots = (int)std::min<int64_t>(std::max(slots, 3), cap);
@@ -454,7 +516,15 @@ void flux_series_fused(PliDev& p, const PanelPlan& pl, const void* u, const void
     a.ring = p.ring.p;
     a.sync = p.fused_sync.p;
     NFX_CUDA(cudaMemsetAsync(a.sync, 0, sizeof(int) * (2 + 2 * a.nbatches), s));
-    if (dtype == NFX_F64) {
+    if (e3) {
+        if (dtype == NFX_F64) {
+            if (vec == 2) launch_fused<double, 2, 5, 0, true>(a, s);
+            else launch_fused<double, 1, 5, 0, true>(a, s);
+        } else {
+            if (vec == 4) launch_fused<float, 4, 3, 0, true>(a, s);
+            else launch_fused<float, 1, 5, 0, true>(a, s);
+        }
+    } else if (dtype == NFX_F64) {
         if (vec == 4 && ctas == 2) launch_fused<double, 4, 5, 2>(a, s);
         else if (vec == 4 && ctas == 4) launch_fused<double, 4, 5, 4>(a, s);
         else if (vec == 4) launch_fused<double, 4, 5>(a, s);

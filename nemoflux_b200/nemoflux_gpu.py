@@ -263,7 +263,8 @@ class PolylineIntegral(object):
         PARTIAL sums -- the building block of the balanced multi-GPU sharding in nemoflux_b200.dist.
 
         e3u, e3v (device tensors only): per-column vertical scale factors, (1 or nt, nz, cells) with the dtype and
-        plane layout of uo/vo; they replace the 1-D thickness (two-launch path)."""
+        plane layout of uo/vo; they replace the 1-D thickness (fused pass with eflux=None when the
+        policy of nfx_flux_series_e3 allows, else two launches)."""
         torch = _torch()
         if isinstance(u, torch.Tensor) and u.is_cuda:
             return self._flux_series_device(u, v, thickness, arc1, arc2, sverdrup, fill, order, eflux, out, batch_range,

@@ -610,12 +610,115 @@ def test_k2_per_column_scale_factors(gpu, oracle, dtype, e3_nt):
     g = oracle.DataGen(nx=nx, ny=ny)
     _, p = _build(gpu, g.points(), ny, nx)
     p.computeWeights([tr([(-150, -50), (-20, 35), (60, -40)])])
-    s_e3 = p.fluxSeries(args[0], args[1], None, a1d, a2d, e3u=torch.from_numpy(e3c).to(d), e3v=torch.from_numpy(e3c).to(d))
+    e3d = torch.from_numpy(e3c).to(d)
     ef2 = torch.empty((nt, 2 * ny * nx), dtype=torch.float64, device=d)
+    ef3 = torch.empty_like(ef2)
+    s_e3 = p.fluxSeries(args[0], args[1], None, a1d, a2d, e3u=e3d, e3v=e3d, eflux=ef3)      # two launches
     s_th = p.fluxSeries(args[0], args[1], torch.from_numpy(th).to(d), a1d, a2d, eflux=ef2)
-    assert torch.equal(s_e3, s_th)
+    assert torch.equal(s_e3, s_th) and torch.equal(ef3, ef2)
+    f_e3 = p.fluxSeries(args[0], args[1], None, a1d, a2d, e3u=e3d, e3v=e3d)                 # fused pass
+    assert _lib_last_path() == 1
+    f_th = p.fluxSeries(args[0], args[1], torch.from_numpy(th).to(d), a1d, a2d)
+    assert torch.equal(f_e3, f_th)
     with pytest.raises(ValueError):
         gpu.edgeFluxAssemble(args[0], args[1], None, a1d, a2d, e3u=torch.from_numpy(e3c).to(d))
+
+
+def _lib_last_path():
+    from nemoflux_b200 import _lib
+    return _lib.get_option(_lib.NFX_OPT_LAST_SERIES_PATH)
+
+
+@pytest.mark.parametrize('dtype', [numpy.float64, numpy.float32])
+@pytest.mark.parametrize('e3_nt', [1, 5])
+@pytest.mark.parametrize('padded', [False, True])
+def test_fused_series_with_scale_factors(gpu, oracle, dtype, e3_nt, padded):
+    """e3u/e3v through the fused persistent pass (several tiles, several panels forced by a 1 MB ring slot, dense
+    and padded planes): identical run to run, equal to the two-launch e3 path to rounding, and to the oracle's
+    series built from the oracle's e3 edge fluxes; special float32 values take the same route as in K2"""
+    import torch
+    from nemoflux_b200 import _lib
+    nx, ny, nz, nt = 301, 251, 7, 5                 # ncell = 75551, odd; nz = 7 exercises the level tail (5 + 2, 3 + 3 + 1)
+    g = oracle.DataGen(nx=nx, ny=ny, nz=nz, nt=nt, deltaDeg=(20., 30.))
+    P, arc = g.points(), oracle.arc_lengths(g.points())
+    ncell = nx * ny
+    rng = numpy.random.default_rng(77)
+    u, v = g.uv(SF_C2)
+    u, v = u.astype(dtype), v.astype(dtype)
+    u[:, :, 100:120, 50:90] = numpy.nan
+    e3u = rng.uniform(0.5, 30., (e3_nt, nz, ny, nx)).astype(dtype)
+    e3v = rng.uniform(0.5, 30., (e3_nt, nz, ny, nx)).astype(dtype)
+    e3v[:, 2:, 40:44, 60:70] = numpy.nan            # missing scale factor below a synthetic bathymetry: counts as 0
+    if dtype == numpy.float32:
+        u[:, ::2, 10:14, 5:25] = numpy.float32(1.0e-41)
+        v[:, 1::3, 30:34, 5:25] = -numpy.finfo(numpy.float32).tiny
+        v[1, 3, 200, 100] = numpy.inf                # an infinity: the thread recomputes its columns with clean()
+        e3u[0, 1, 20, 30] = numpy.float32(2.0e-42)
+    d = 'cuda'
+    tdt = torch.float64 if dtype == numpy.float64 else torch.float32
+    pad = (4 if dtype == numpy.float64 else 8) if padded else 1
+    ld = (ncell + pad - 1) // pad * pad
+
+    def dev(x):
+        t = torch.full((x.shape[0], nz, ld), 7.0, dtype=tdt, device=d)[:, :, :ncell]
+        t.copy_(torch.from_numpy(x.reshape(x.shape[0], nz, ncell)))
+        return t
+    ud, vd, eu, ev = dev(u), dev(v), dev(e3u), dev(e3v)
+    a1, a2 = (torch.from_numpy(x).to(d) for x in (arc[:, 1].copy(), arc[:, 2].copy()))
+    transects = random_transects(numpy.random.default_rng(5), 6) + [tr(README_C2), tr(README_LOOP)]
+    _, p = _build(gpu, P, ny, nx)
+    p.computeWeights(transects)
+    try:
+        ef = torch.empty((nt, 2 * ncell), dtype=torch.float64, device=d)
+        classic = p.fluxSeries(ud, vd, None, a1, a2, e3u=eu, e3v=ev, eflux=ef).cpu().numpy()
+        assert _lib_last_path() == 0
+        # the oracle: its e3 edge fluxes (bit for bit), scattered as field.py:209-223 does, summed over its own map
+        og = oracle.Grid(P)
+        maps = []
+        for xyz in transects:
+            op = oracle.PolylineIntegral(og)
+            op.computeWeights(xyz)
+            maps.append(op.merged_map())
+        ref = numpy.zeros((nt, len(transects)))
+        scale = numpy.zeros((nt, len(transects)))
+        efh = ef.cpu().numpy()
+        for t in range(nt):
+            te = 0 if e3_nt == 1 else t
+            with numpy.errstate(all='ignore'):
+                eU, eV = oracle.edgeflux_step_c_e3(u[t].astype(numpy.float64), v[t].astype(numpy.float64),
+                                                   e3u[te].astype(numpy.float64), e3v[te].astype(numpy.float64),
+                                                   arc[:, 1].copy(), arc[:, 2].copy(), False)
+            assert_bitwise(efh[t, :ncell], eU, 'eU (e3)')
+            assert_bitwise(efh[t, ncell:], eV, 'eV (e3)')
+            iV = numpy.zeros((ny, nx, 4))
+            eU2, eV2 = eU.reshape(ny, nx), eV.reshape(ny, nx)
+            iV[:, :, 1], iV[:, :, 2] = eU2, eV2
+            iV[1:, :, 0] = eV2[:-1, :]
+            iV[:, 1:, 3] = eU2[:, :-1]
+            iV[:, 0, 3] = eU2[:, -1]
+            f = iV.reshape(-1)
+            with numpy.errstate(all='ignore'):
+                for m, (keys, ws) in enumerate(maps):
+                    ref[t, m] = (ws * f[keys]).sum()
+                    scale[t, m] = numpy.abs(ws * f[keys]).sum()
+        fin = numpy.isfinite(ref)
+        assert numpy.array_equal(numpy.isfinite(classic), fin)
+        assert fin.sum() >= fin.size - nt * 2           # at most the transects through the one infinite column
+        assert (numpy.abs(classic[fin] - ref[fin]) <= FLUX_RTOL * scale[fin] + 1e-300).all()
+        for slot_mb in (8, 1):
+            _lib.set_option(_lib.NFX_OPT_RING_SLOT_MB, slot_mb)
+            _lib.set_option(_lib.NFX_OPT_FAST_SERIES, 2)
+            fused = p.fluxSeries(ud, vd, None, a1, a2, e3u=eu, e3v=ev).cpu().numpy()
+            assert _lib_last_path() == 1
+            assert p.getNumberOfPanels()[0] == (1 if slot_mb == 8 else 2)
+            again = p.fluxSeries(ud, vd, None, a1, a2, e3u=eu, e3v=ev).cpu().numpy()
+            assert numpy.array_equal(fused, again, equal_nan=True)                       # deterministic
+            assert numpy.array_equal(numpy.isfinite(fused), fin)
+            assert (numpy.abs(fused[fin] - classic[fin]) <= 1e-13 * scale[fin] + 1e-300).all()
+            assert (numpy.abs(fused[fin] - ref[fin]) <= FLUX_RTOL * scale[fin] + 1e-300).all()
+    finally:
+        _lib.set_option(_lib.NFX_OPT_RING_SLOT_MB, 8)
+        _lib.set_option(_lib.NFX_OPT_FAST_SERIES, 1)
 
 
 def test_device_arc_lengths(gpu, oracle):

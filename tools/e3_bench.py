@@ -44,6 +44,7 @@ for dname, tdt in (('f64', torch.float64), ('f32', torch.float32)):
         nbytes = 4.0 * esize * syn.nz * syn.ncell * a.nt
         for name, fn in (('K2 e3 (edgeFluxAssemble)', lambda: nemoflux_gpu.edgeFluxAssemble(u, v, None, a1, a2, out=ef, e3u=e3u, e3v=e3v)),
                          ('series e3 (fluxSeries)', lambda: p.fluxSeries(u, v, None, a1, a2, out=out, e3u=e3u, e3v=e3v)),
+                         ('series e3, two launches (fluxSeries eflux=)', lambda: p.fluxSeries(u, v, None, a1, a2, out=out, eflux=ef, e3u=e3u, e3v=e3v)),
                          ('K2 1-D thickness (edgeFluxAssemble)', lambda: nemoflux_gpu.edgeFluxAssemble(u, v, th, a1, a2, out=ef)),
                          ('series 1-D thickness (fluxSeries)', lambda: p.fluxSeries(u, v, th, a1, a2, out=out))):
             for _ in range(3):
@@ -57,7 +58,8 @@ for dname, tdt in (('f64', torch.float64), ('f32', torch.float32)):
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / a.reps
             b = nbytes if 'e3' in name else nbytes / 2
-            rows.append(dict(dtype=dname, e3_time_steps=e3_nt, call=name, ms=round(ms, 4), GBps=round(b / ms / 1e6, 1),
+            fused = _lib.get_option(_lib.NFX_OPT_LAST_SERIES_PATH) if 'series' in name else None
+            rows.append(dict(dtype=dname, e3_time_steps=e3_nt, call=name, fused_pass=fused, ms=round(ms, 4), GBps=round(b / ms / 1e6, 1),
                              units_per_s=float(syn.nz * syn.ncell * a.nt / ms * 1e3)))
             print(json.dumps(rows[-1]), flush=True)
     del u, v, e3u, e3v

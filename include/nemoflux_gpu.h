@@ -199,6 +199,13 @@ int nfx_flux_series_range(nfx_pli** self, const void* u, const void* v, int dtyp
 int nfx_flux_series_host(nfx_pli** self, const void* u, const void* v, int dtype, const double* thickness,
                          const double* arc1, const double* arc2, int nt, int nz, int sverdrup, double fill,
                          int order, int chunk_steps, double* series);
+/* the same with per-column scale factors instead of thickness (what a NEMO mesh_mask or a
+ * variable-volume run provides): e3u, e3v of the dtype (and byte order) of u, v.  e3_on_device != 0: borrowed
+ * DEVICE arrays (e3_nt, nz, ncell) the caller uploaded once (the time-invariant e3u_0/e3v_0 of a mesh_mask);
+ * else HOST arrays: e3_nt == 1 is uploaded once per call, e3_nt == nt is streamed in the chunks next to u, v. */
+int nfx_flux_series_host_e3(nfx_pli** self, const void* u, const void* v, const void* e3u, const void* e3v, int dtype,
+                            int e3_nt, int e3_on_device, const double* arc1, const double* arc2, int nt, int nz,
+                            int sverdrup, double fill, int order, int chunk_steps, double* series);
 
 #ifdef __cplusplus
 }

@@ -81,6 +81,8 @@ SIGNATURES = {
                               c_i64, c_i64, c_vp, c_vp],
     'nfx_flux_series_host': [P(c_vp), c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_dbl, c_int, c_int,
                              c_vp],
+    'nfx_flux_series_host_e3': [P(c_vp), c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_vp, c_vp, c_int, c_int, c_int,
+                                c_dbl, c_int, c_int, c_vp],
 }
 
 _LIB = None

@@ -698,84 +698,151 @@ int nfx_flux_series(nfx_pli** self, const void* u, const void* v, int dtype, con
 }
 
 // ---- everything from host buffers: double-buffered H2D staging, K2+K3 per chunk --------------------------
+// e3u/e3v (optional): per-column scale factors instead of `thickness`.  e3_on_device: borrowed device arrays
+// (e3_nt, nz, ncell) of the dtype of u, v; else host arrays -- e3_nt == 1 is uploaded once per call, e3_nt == nt
+// travels in the chunks next to u and v (same byte order as u, v).
+static void flux_series_host_impl(nfx_pli** self, const void* u, const void* v, int dtype_flags, const double* thickness,
+                                  const void* e3u, const void* e3v, int e3_nt, int e3_on_device, const double* arc1,
+                                  const double* arc2, int nt, int nz, int sverdrup, double fill, int order,
+                                  int chunk_steps, double* series) {
+    NFX_REQUIRE(self && *self, "NULL handle");
+    const bool e3 = e3u != nullptr || e3v != nullptr;
+    NFX_REQUIRE(u && v && arc1 && arc2 && series, "NULL pointer");
+    NFX_REQUIRE(e3 ? (e3u && e3v) : thickness != nullptr, "needs the layer thickness or both of e3u, e3v");
+    NFX_REQUIRE(nt >= 0 && nz > 0, "bad sizes");
+    NFX_REQUIRE(!e3 || e3_nt == 1 || e3_nt == nt, "e3u/e3v must hold 1 (time-invariant) or nt time steps");
+    const bool big_endian = (dtype_flags & NFX_BIG_ENDIAN) != 0;
+    const int dtype = dtype_flags & ~NFX_BIG_ENDIAN;
+    NFX_REQUIRE(dtype == NFX_F64 || dtype == NFX_F32, "dtype must be NFX_F64 or NFX_F32 (optionally | NFX_BIG_ENDIAN)");
+    PliDev& p = (*self)->d;
+    NFX_REQUIRE(p.grid, "setGrid was not called");
+    DeviceGuard g(p.grid->device);
+    const Csr& c = pick_csr(p, order, 1);
+    const int64_t ncell = p.grid->ncell;
+    const int M = p.ntransects;
+    if (nt == 0 || M == 0) return;
+    const size_t esize = dtype == NFX_F64 ? 8 : 4;
+    const size_t step_bytes = esize * (size_t)nz * (size_t)ncell;
+    const bool e3_streamed = e3 && !e3_on_device && e3_nt == nt && nt > 1;
+    if (chunk_steps <= 0) {
+        const size_t target = (size_t)256 << 20;  // per variable and slot
+        chunk_steps = (int)std::max<size_t>(1, target / step_bytes);
+    }
+    chunk_steps = std::min(chunk_steps, nt);
+    if (!p.copy_stream) {
+        NFX_CUDA(cudaStreamCreateWithFlags(&p.copy_stream, cudaStreamNonBlocking));
+        NFX_CUDA(cudaStreamCreateWithFlags(&p.compute_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            NFX_CUDA(cudaEventCreateWithFlags(&p.ev_ready[i], cudaEventDisableTiming));
+            NFX_CUDA(cudaEventCreateWithFlags(&p.ev_done[i], cudaEventDisableTiming));
+        }
+    }
+    for (int i = 0; i < 2; ++i) {
+        p.stage_u[i].ensure(step_bytes * chunk_steps);
+        p.stage_v[i].ensure(step_bytes * chunk_steps);
+        if (e3_streamed) {
+            p.stage_e3u[i].ensure(step_bytes * chunk_steps);
+            p.stage_e3v[i].ensure(step_bytes * chunk_steps);
+        }
+    }
+    p.stage_series.ensure((size_t)nt * M);
+    p.stage_arc1.ensure(ncell);
+    p.stage_arc2.ensure(ncell);
+    cudaStream_t cs = p.copy_stream, ks = p.compute_stream;
+    if (!e3) {
+        p.stage_thick.ensure(nz);
+        NFX_CUDA(cudaMemcpyAsync(p.stage_thick.p, thickness, sizeof(double) * nz, cudaMemcpyHostToDevice, ks));
+    }
+    NFX_CUDA(cudaMemcpyAsync(p.stage_arc1.p, arc1, sizeof(double) * ncell, cudaMemcpyHostToDevice, ks));
+    NFX_CUDA(cudaMemcpyAsync(p.stage_arc2.p, arc2, sizeof(double) * ncell, cudaMemcpyHostToDevice, ks));
+    const void* d_e3u = e3u;   // device addresses of the scale factors of the first time step of a chunk
+    const void* d_e3v = e3v;
+    if (e3 && !e3_on_device && !e3_streamed) {   // host, time-invariant (or a single step): once per call
+        p.stage_e3u[0].ensure(step_bytes);
+        p.stage_e3v[0].ensure(step_bytes);
+        NFX_CUDA(cudaMemcpyAsync(p.stage_e3u[0].p, e3u, step_bytes, cudaMemcpyHostToDevice, ks));
+        NFX_CUDA(cudaMemcpyAsync(p.stage_e3v[0].p, e3v, step_bytes, cudaMemcpyHostToDevice, ks));
+        if (big_endian) {
+            bswap_inplace(p.stage_e3u[0].p, step_bytes / esize, (int)esize, ks);
+            bswap_inplace(p.stage_e3v[0].p, step_bytes / esize, (int)esize, ks);
+        }
+        d_e3u = p.stage_e3u[0].p;
+        d_e3v = p.stage_e3v[0].p;
+    }
+    const bool fused = e3 ? use_fused_e3(p, dtype, nullptr, nullptr, nullptr, nullptr, 0, ncell)
+                          : use_fused(p, dtype, nullptr, nullptr, ncell);
+    if (!fused)
+        for (int i = 0; i < 2; ++i) p.stage_eflux[i].ensure((size_t)chunk_steps * 2 * ncell);
+    int slot = 0;
+    bool used[2] = {false, false};
+    for (int t0 = 0; t0 < nt; t0 += chunk_steps, slot ^= 1) {
+        const int n = std::min(chunk_steps, nt - t0);
+        if (used[slot]) NFX_CUDA(cudaStreamWaitEvent(cs, p.ev_done[slot], 0));
+        const size_t off = (size_t)t0 * step_bytes;
+        const void* src[4] = {(const unsigned char*)u + off, (const unsigned char*)v + off,
+                              e3_streamed ? (const unsigned char*)e3u + off : nullptr,
+                              e3_streamed ? (const unsigned char*)e3v + off : nullptr};
+        unsigned char* dst[4] = {p.stage_u[slot].p, p.stage_v[slot].p, e3_streamed ? p.stage_e3u[slot].p : nullptr,
+                                 e3_streamed ? p.stage_e3v[slot].p : nullptr};
+        for (int q = 0; q < 4; ++q) {
+            if (!src[q]) continue;
+            NFX_CUDA(cudaMemcpyAsync(dst[q], src[q], step_bytes * n, cudaMemcpyHostToDevice, cs));
+            if (big_endian)   // file bytes as stored: swap on the device, behind the copy on the copy stream
+                bswap_inplace(dst[q], step_bytes * n / esize, (int)esize, cs);
+        }
+        NFX_CUDA(cudaEventRecord(p.ev_ready[slot], cs));
+        NFX_CUDA(cudaStreamWaitEvent(ks, p.ev_ready[slot], 0));
+        const void* ce3u = nullptr;
+        const void* ce3v = nullptr;
+        int64_t e3_tstride = 0;
+        if (e3_streamed) {
+            ce3u = dst[2];
+            ce3v = dst[3];
+            e3_tstride = (int64_t)nz * ncell;
+        } else if (e3) {
+            const bool per_step = e3_on_device && e3_nt == nt && nt > 1;
+            e3_tstride = per_step ? (int64_t)nz * ncell : 0;
+            ce3u = (const unsigned char*)d_e3u + (per_step ? off : 0);
+            ce3v = (const unsigned char*)d_e3v + (per_step ? off : 0);
+        }
+        double* out = p.stage_series.p + (size_t)t0 * M;
+        if (fused) {
+            flux_series_fast(p, dst[0], dst[1], dtype, e3 ? nullptr : p.stage_thick.p, p.stage_arc1.p, p.stage_arc2.p, n,
+                             nz, ncell, sverdrup, fill, order, out, ks, 0, -1, ce3u, ce3v, e3_tstride);
+        } else {
+            edgeflux_assemble_panel(dst[0], dst[1], dtype, e3 ? nullptr : p.stage_thick.p, p.stage_arc1.p,
+                                    p.stage_arc2.p, n, nz, ncell, ncell, sverdrup, fill, p.stage_eflux[slot].p, 0, g_k2opt,
+                                    ks, ce3u, ce3v, e3_tstride);
+            csr_integrate(c, M, p.stage_eflux[slot].p, ncell * 2, n, out, ks);
+        }
+        NFX_CUDA(cudaEventRecord(p.ev_done[slot], ks));
+        used[slot] = true;
+    }
+    NFX_CUDA(cudaMemcpyAsync(series, p.stage_series.p, sizeof(double) * (size_t)nt * M, cudaMemcpyDeviceToHost, ks));
+    NFX_CUDA(cudaStreamSynchronize(ks));
+    NFX_CUDA(cudaStreamSynchronize(cs));
+    g_last_series_fused = fused ? 1 : 0;
+    if (fused && fused_error_flag(p, ks) != 0)
+        throw Error(NFX_E_INTERNAL, "fused K2+K3 pass aborted (a bounded wait overflowed)");
+}
+
 int nfx_flux_series_host(nfx_pli** self, const void* u, const void* v, int dtype_flags, const double* thickness,
                          const double* arc1, const double* arc2, int nt, int nz, int sverdrup, double fill, int order,
                          int chunk_steps, double* series) {
     return guarded([&] {
-        NFX_REQUIRE(self && *self, "NULL handle");
-        NFX_REQUIRE(u && v && thickness && arc1 && arc2 && series, "NULL pointer");
-        NFX_REQUIRE(nt >= 0 && nz > 0, "bad sizes");
-        const bool big_endian = (dtype_flags & NFX_BIG_ENDIAN) != 0;
-        const int dtype = dtype_flags & ~NFX_BIG_ENDIAN;
-        NFX_REQUIRE(dtype == NFX_F64 || dtype == NFX_F32, "dtype must be NFX_F64 or NFX_F32 (optionally | NFX_BIG_ENDIAN)");
-        PliDev& p = (*self)->d;
-        NFX_REQUIRE(p.grid, "setGrid was not called");
-        DeviceGuard g(p.grid->device);
-        const Csr& c = pick_csr(p, order, 1);
-        const int64_t ncell = p.grid->ncell;
-        const int M = p.ntransects;
-        if (nt == 0 || M == 0) return;
-        const size_t esize = dtype == NFX_F64 ? 8 : 4;
-        const size_t step_bytes = esize * (size_t)nz * (size_t)ncell;
-        const bool fused = use_fused(p, dtype, nullptr, nullptr, ncell);
-        if (chunk_steps <= 0) {
-            const size_t target = (size_t)256 << 20;  // per variable and slot
-            chunk_steps = (int)std::max<size_t>(1, target / step_bytes);
-        }
-        chunk_steps = std::min(chunk_steps, nt);
-        if (!p.copy_stream) {
-            NFX_CUDA(cudaStreamCreateWithFlags(&p.copy_stream, cudaStreamNonBlocking));
-            NFX_CUDA(cudaStreamCreateWithFlags(&p.compute_stream, cudaStreamNonBlocking));
-            for (int i = 0; i < 2; ++i) {
-                NFX_CUDA(cudaEventCreateWithFlags(&p.ev_ready[i], cudaEventDisableTiming));
-                NFX_CUDA(cudaEventCreateWithFlags(&p.ev_done[i], cudaEventDisableTiming));
-            }
-        }
-        for (int i = 0; i < 2; ++i) {
-            p.stage_u[i].ensure(step_bytes * chunk_steps);
-            p.stage_v[i].ensure(step_bytes * chunk_steps);
-            if (!fused) p.stage_eflux[i].ensure((size_t)chunk_steps * 2 * ncell);
-        }
-        p.stage_series.ensure((size_t)nt * M);
-        p.stage_thick.ensure(nz);
-        p.stage_arc1.ensure(ncell);
-        p.stage_arc2.ensure(ncell);
-        cudaStream_t cs = p.copy_stream, ks = p.compute_stream;
-        NFX_CUDA(cudaMemcpyAsync(p.stage_thick.p, thickness, sizeof(double) * nz, cudaMemcpyHostToDevice, ks));
-        NFX_CUDA(cudaMemcpyAsync(p.stage_arc1.p, arc1, sizeof(double) * ncell, cudaMemcpyHostToDevice, ks));
-        NFX_CUDA(cudaMemcpyAsync(p.stage_arc2.p, arc2, sizeof(double) * ncell, cudaMemcpyHostToDevice, ks));
-        int slot = 0;
-        bool used[2] = {false, false};
-        for (int t0 = 0; t0 < nt; t0 += chunk_steps, slot ^= 1) {
-            const int n = std::min(chunk_steps, nt - t0);
-            if (used[slot]) NFX_CUDA(cudaStreamWaitEvent(cs, p.ev_done[slot], 0));
-            const unsigned char* hu = (const unsigned char*)u + (size_t)t0 * step_bytes;
-            const unsigned char* hv = (const unsigned char*)v + (size_t)t0 * step_bytes;
-            NFX_CUDA(cudaMemcpyAsync(p.stage_u[slot].p, hu, step_bytes * n, cudaMemcpyHostToDevice, cs));
-            NFX_CUDA(cudaMemcpyAsync(p.stage_v[slot].p, hv, step_bytes * n, cudaMemcpyHostToDevice, cs));
-            if (big_endian) {   // file bytes as stored: swap on the device, behind the copy on the copy stream
-                bswap_inplace(p.stage_u[slot].p, step_bytes * n / esize, (int)esize, cs);
-                bswap_inplace(p.stage_v[slot].p, step_bytes * n / esize, (int)esize, cs);
-            }
-            NFX_CUDA(cudaEventRecord(p.ev_ready[slot], cs));
-            NFX_CUDA(cudaStreamWaitEvent(ks, p.ev_ready[slot], 0));
-            if (fused) {
-                flux_series_fast(p, p.stage_u[slot].p, p.stage_v[slot].p, dtype, p.stage_thick.p, p.stage_arc1.p,
-                                 p.stage_arc2.p, n, nz, ncell, sverdrup, fill, order, p.stage_series.p + (size_t)t0 * M,
-                                 ks);
-            } else {
-                edgeflux_assemble(p.stage_u[slot].p, p.stage_v[slot].p, dtype, p.stage_thick.p, p.stage_arc1.p,
-                                  p.stage_arc2.p, n, nz, ncell, sverdrup, fill, p.stage_eflux[slot].p, g_k2opt, ks);
-                csr_integrate(c, M, p.stage_eflux[slot].p, ncell * 2, n, p.stage_series.p + (size_t)t0 * M, ks);
-            }
-            NFX_CUDA(cudaEventRecord(p.ev_done[slot], ks));
-            used[slot] = true;
-        }
-        NFX_CUDA(cudaMemcpyAsync(series, p.stage_series.p, sizeof(double) * (size_t)nt * M, cudaMemcpyDeviceToHost, ks));
-        NFX_CUDA(cudaStreamSynchronize(ks));
-        NFX_CUDA(cudaStreamSynchronize(cs));
-        if (fused && fused_error_flag(p, ks) != 0)
-            throw Error(NFX_E_INTERNAL, "fused K2+K3 pass aborted (a bounded wait overflowed)");
+        NFX_REQUIRE(thickness, "NULL pointer");
+        flux_series_host_impl(self, u, v, dtype_flags, thickness, nullptr, nullptr, 0, 0, arc1, arc2, nt, nz, sverdrup,
+                              fill, order, chunk_steps, series);
+    });
+}
+
+int nfx_flux_series_host_e3(nfx_pli** self, const void* u, const void* v, const void* e3u, const void* e3v,
+                            int dtype_flags, int e3_nt, int e3_on_device, const double* arc1, const double* arc2, int nt,
+                            int nz, int sverdrup, double fill, int order, int chunk_steps, double* series) {
+    return guarded([&] {
+        NFX_REQUIRE(e3u && e3v, "e3u / e3v is NULL");
+        flux_series_host_impl(self, u, v, dtype_flags, nullptr, e3u, e3v, e3_nt, e3_on_device, arc1, arc2, nt, nz,
+                              sverdrup, fill, order, chunk_steps, series);
     });
 }
 

@@ -159,7 +159,7 @@ struct PliDev {
     // scratch reused by the host-buffer entry points
     DevBuf<double> scratch_data, scratch_res;
     // persistent staging of nfx_flux_series_host (two slots)
-    DevBuf<unsigned char> stage_u[2], stage_v[2];
+    DevBuf<unsigned char> stage_u[2], stage_v[2], stage_e3u[2], stage_e3v[2];
     DevBuf<double> stage_eflux[2], stage_series, stage_thick, stage_arc1, stage_arc2;
     cudaStream_t copy_stream = nullptr, compute_stream = nullptr;
     cudaEvent_t ev_ready[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};

@@ -149,6 +149,36 @@ class DataGen(object):
             w.close()
 
 
+    def saveMeshMask(self, partialCells=0.0):
+        """<prefix>mesh_mask.nc with NEMO's names (not part of the reference's datagen; feeds Field(meshFile=...)):
+        e3u_0, e3v_0 (t=1, z, y, x): the layer thickness zbot-ztop of every level, the deepest level thinned to
+        (1 - partialCells * r(j, i)) of it with a fixed pseudo-random r in [0, 1) -- a partial bottom cell;
+        e2u, e1v (t=1, y, x): lengths in metres of the east and north edges of the cells as field.py:170-181
+        measures them on the saved bounds, times the earth radius of field.py:12."""
+        dz = numpy.asarray(self.zbot, numpy.float64) - numpy.asarray(self.ztop, numpy.float64)
+        e3 = numpy.broadcast_to(dz[:, None, None], (self.nz, self.ny, self.nx))
+        e3u, e3v = e3.copy(), e3.copy()
+        if partialCells > 0.:
+            jj, ii = numpy.meshgrid(numpy.arange(self.ny), numpy.arange(self.nx), indexing='ij')
+            r = ((jj * 7919 + ii * 104729 + 12345) % 1000) / 1000.0
+            e3u[-1] *= 1.0 - partialCells * r
+            e3v[-1] *= 1.0 - partialCells * r[::-1, ::-1]
+        points = numpy.zeros((self.ny * self.nx, 4, 3), numpy.float64)
+        points[:, :, 0] = numpy.asarray(self.bounds_lon).reshape(-1, 4)
+        points[:, :, 1] = numpy.asarray(self.bounds_lat).reshape(-1, 4)
+        arc = geo.cellArcLengths(points)
+        radius = 6371000.0
+        w = ncio.Writer(self.prefix + 'mesh_mask.nc')
+        for name, n in (('t', 1), ('z', self.nz), ('y', self.ny), ('x', self.nx)):
+            w.createDimension(name, n)
+        w.createVariable('e3u_0', REAL, ('t', 'z', 'y', 'x'), data=e3u[None])
+        w.createVariable('e3v_0', REAL, ('t', 'z', 'y', 'x'), data=e3v[None])
+        w.createVariable('e2u', REAL, ('t', 'y', 'x'), data=(arc[:, 1] * radius).reshape(1, self.ny, self.nx))
+        w.createVariable('e1v', REAL, ('t', 'y', 'x'), data=(arc[:, 2] * radius).reshape(1, self.ny, self.nx))
+        w.close()
+        return e3u, e3v
+
+
 def parseDeltaDeg(text):
     vals = [float(s) for s in str(text).replace('(', ' ').replace(')', ' ').replace(',', ' ').split()]
     if len(vals) != 2:
@@ -157,7 +187,8 @@ def parseDeltaDeg(text):
 
 
 def main(*, streamFunction="(cos(t*2*pi/nt)+2)*(0.5*(y/180)**2 + sin(2*pi*x/360))", prefix='', xmin=-180.,
-         xmax=180., ymin=-90., ymax=90., zmin=0., zmax=1.0, nx=36, ny=18, nz=1, nt=1, deltaDeg="(0.,0.)"):
+         xmax=180., ymin=-90., ymax=90., zmin=0., zmax=1.0, nx=36, ny=18, nz=1, nt=1, deltaDeg="(0.,0.)",
+         meshMask=False, partialCells=0.0):
     """Generate data (datagen.py:211-242)"""
     gen = DataGen(prefix)
     gen.setSizes(nx, ny, nz, nt)
@@ -169,6 +200,8 @@ def main(*, streamFunction="(cos(t*2*pi/nt)+2)*(0.5*(y/180)**2 + sin(2*pi*x/360)
     gen.applyStreamFunction(streamFunction)
     gen.computeUVFromPotential()
     gen.save()
+    if meshMask:
+        gen.saveMeshMask(partialCells=partialCells)
     return gen
 
 
@@ -185,6 +218,8 @@ def cli(argv=None):
                                ('nz', 1, 'number of vertical cells'), ('nt', 1, 'number of time steps')):
         ap.add_argument('--' + name, type=int, default=default, help=hlp)
     ap.add_argument('-d', '--deltaDeg', default='(0.,0.)', help='longitude, latitude pole displacement')
+    ap.add_argument('--meshMask', action='store_true', help='also write <prefix>mesh_mask.nc (e3u_0, e3v_0, e2u, e1v)')
+    ap.add_argument('--partialCells', type=float, default=0., help='with --meshMask: thin the deepest cells by up to this fraction')
     a = ap.parse_args(argv)
     main(**vars(a))
 

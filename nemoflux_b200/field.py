@@ -10,7 +10,10 @@ What differs: ONE locator is built per grid and shared by all transects (the ref
 transect, field.py:44-49); the vertical integration, edge-flux assembly and the transect integrals run in
 libnemoflux_gpu.so (K2, K3); ``fluxSeries()`` is new and evaluates every time step and transect in a few
 launches (the loop of fluxplot.py:51-59).  ``vectorPoints`` / ``vectorValues`` (the arrow glyphs, field.py:71-95)
-come from nemoflux_gpu.VectorInterp.
+come from nemoflux_gpu.VectorInterp.  ``meshFile`` (optional, new -- SURVEY 8f rank 4): a NEMO mesh_mask-style
+file whose per-column vertical scale factors ``e3u_0/e3v_0`` (partial bottom cells) replace the 1-D
+``deptht_bounds`` thickness of field.py:51 and whose horizontal scale factors ``e2u/e1v`` (metres), when present,
+replace the arc lengths of field.py:170-181.
 """
 import re
 
@@ -41,7 +44,7 @@ class _TransectView(object):
 
 class Field(object):
 
-    def __init__(self, tFile, uFile, vFile, lonLatZPoints, sverdrup=False, verbose=True):
+    def __init__(self, tFile, uFile, vFile, lonLatZPoints, sverdrup=False, verbose=True, meshFile=None):
         import torch
         self.sverdrup = sverdrup
         with ncio.open_dataset(tFile) as nc:
@@ -74,6 +77,10 @@ class Field(object):
         self.dx = min((self.lonmax - self.lonmin) / float(self.nx), (self.latmax - self.latmin) / float(self.ny))
         self.arcLengths = numpy.zeros((numCells, 4), numpy.float64)
         self.computeArcLengths()
+        self.e3u = self.e3v = None              # (nz, ny, nx) in the storage dtype of uo/vo, from meshFile
+        self._d_e3u = self._d_e3v = None
+        if meshFile:
+            self.readMeshFile(meshFile, verbose)
         self._d_thickness = torch.from_numpy(numpy.ascontiguousarray(self.thickness)).to(self.device)
         self._d_arc1 = torch.from_numpy(numpy.ascontiguousarray(self.arcLengths[:, 1])).to(self.device)
         self._d_arc2 = torch.from_numpy(numpy.ascontiguousarray(self.arcLengths[:, 2])).to(self.device)
@@ -135,6 +142,45 @@ class Field(object):
     def computeArcLengths(self):
         self.arcLengths[:] = geo.cellArcLengths(self.gr.getPoints())
 
+    def readMeshFile(self, meshFile, verbose=False):
+        """NEMO mesh_mask conventions: e3u_0/e3v_0 (or e3u/e3v) as (1, z, y, x) or (z, y, x) -- time-invariant
+        vertical scale factors at the U and V points; e2u/e1v as (1, y, x) or (y, x) in metres -- the lengths of the
+        east and north cell edges, i.e. arcLengths[:, 1] and [:, 2] (field.py:195-196) times the earth radius.
+        The scale factors are kept in the storage dtype of uo/vo (the kernels stream all four arrays as one type)."""
+        import torch
+        want = numpy.dtype(self.ncU['uo'].dtype).newbyteorder('=')
+
+        def pick(nc, names, ndim):
+            for name in names:
+                if name in nc:
+                    a = numpy.asarray(nc[name][:], numpy.float64)       # missing values decoded to NaN (count as 0)
+                    while a.ndim > ndim:
+                        if a.shape[0] != 1:
+                            raise RuntimeError(f'ERROR: {name} in {meshFile} has {a.shape[0]} time steps, expected 1')
+                        a = a[0]
+                    return name, a
+            return None, None
+        with ncio.open_dataset(meshFile) as nc:
+            nu, e3u = pick(nc, ('e3u_0', 'e3u'), 3)
+            nv, e3v = pick(nc, ('e3v_0', 'e3v'), 3)
+            n2, e2u = pick(nc, ('e2u',), 2)
+            n1, e1v = pick(nc, ('e1v',), 2)
+        if e3u is None or e3v is None:
+            raise RuntimeError(f'ERROR: {meshFile} holds no e3u_0/e3v_0 (or e3u/e3v) variables')
+        shape = (self.nz, self.ny, self.nx)
+        if e3u.shape != shape or e3v.shape != shape:
+            raise RuntimeError(f'ERROR: {nu}/{nv} shapes {e3u.shape}/{e3v.shape} do not match uo {shape}')
+        self.e3u, self.e3v = e3u.astype(want), e3v.astype(want)
+        self._d_e3u = torch.from_numpy(self.e3u.reshape(1, self.nz, -1)).to(self.device)
+        self._d_e3v = torch.from_numpy(self.e3v.reshape(1, self.nz, -1)).to(self.device)
+        if e2u is not None and e1v is not None:
+            if e2u.shape != shape[1:] or e1v.shape != shape[1:]:
+                raise RuntimeError(f'ERROR: e2u/e1v shapes {e2u.shape}/{e1v.shape} do not match the grid {shape[1:]}')
+            self.arcLengths[:, 1] = e2u.reshape(-1) / EARTH_RADIUS
+            self.arcLengths[:, 2] = e1v.reshape(-1) / EARTH_RADIUS
+        if verbose:
+            print(f'mesh file: {nu}, {nv}' + (', e2u, e1v' if e2u is not None and e1v is not None else ''))
+
     def _slab(self, nc, fieldName, t0, n):
         """(n, nz, ny, nx) block of time steps AS STORED: the missing-value marker (_FillValue, 1e20 in NEMO and
         datagen.py:191) is not decoded on the host -- K2 maps it (and NaN) to 0, which is what xarray's decoding
@@ -173,7 +219,12 @@ class Field(object):
         import torch
         a = torch.from_numpy(self._slab(nc, fieldName, self.timeIndex, 1)).to(self.device)
         ones = torch.ones(self.ny * self.nx, dtype=torch.float64, device=self.device)
-        ef = nemoflux_gpu.edgeFluxAssemble(a, a, self._d_thickness, ones, ones, fill=self._fill(nc, fieldName))
+        if self._d_e3u is not None:
+            e3 = self._d_e3u if fieldName == 'uo' else self._d_e3v
+            ef = nemoflux_gpu.edgeFluxAssemble(a.reshape(1, self.nz, -1), a.reshape(1, self.nz, -1), None, ones, ones,
+                                               fill=self._fill(nc, fieldName), e3u=e3, e3v=e3)
+        else:
+            ef = nemoflux_gpu.edgeFluxAssemble(a, a, self._d_thickness, ones, ones, fill=self._fill(nc, fieldName))
         return ef[0, :self.ny * self.nx].reshape(self.ny, self.nx).cpu().numpy()
 
     def getUV(self):
@@ -185,8 +236,13 @@ class Field(object):
         import torch
         uh, vh, fill = self._uv_slabs(self.timeIndex, 1)
         u, v = torch.from_numpy(uh).to(self.device), torch.from_numpy(vh).to(self.device)
-        eflux = nemoflux_gpu.edgeFluxAssemble(u, v, self._d_thickness, self._d_arc1, self._d_arc2, sverdrup=self.sverdrup,
-                                              fill=fill)
+        if self._d_e3u is not None:
+            eflux = nemoflux_gpu.edgeFluxAssemble(u.reshape(1, self.nz, -1), v.reshape(1, self.nz, -1), None, self._d_arc1,
+                                                  self._d_arc2, sverdrup=self.sverdrup, fill=fill, e3u=self._d_e3u,
+                                                  e3v=self._d_e3v)
+        else:
+            eflux = nemoflux_gpu.edgeFluxAssemble(u, v, self._d_thickness, self._d_arc1, self._d_arc2,
+                                                  sverdrup=self.sverdrup, fill=fill)
         self.fluxes = self.pli.integrate(eflux).cpu().numpy()[0]
         ncell = self.ny * self.nx
         self.integratedVelocity[:] = nemoflux_gpu.edgeFluxToCellByCell(eflux, self.ny, self.nx)[0].cpu().numpy()
@@ -286,7 +342,7 @@ class Field(object):
                 th.start()
             nu, nv = views[slot]                    # numpy views of the pinned buffers (kept alive by `bufs`)
             out[t0:t0 + m] = self.pli.fluxSeries(nu[:m], nv[:m], self.thickness, arc1, arc2, sverdrup=self.sverdrup,
-                                                 fill=state.pop(i))
+                                                 fill=state.pop(i), e3u=self._d_e3u, e3v=self._d_e3v)
             if th is not None:
                 th.join()
             elif i + 1 < len(chunks):
@@ -326,6 +382,7 @@ def main(argv=None):
     ap.add_argument('-l', '--lonLatPoints', default='', help='target points "(lon0, lat0), (lon1, lat1),..."')
     ap.add_argument('-i', '--iFile', default='', help='alternatively read target points from text file')
     ap.add_argument('-s', '--sverdrup', action='store_true')
+    ap.add_argument('--meshFile', default='', help='optional mesh_mask file: e3u_0/e3v_0 (and e2u/e1v) scale factors')
     a = ap.parse_args(argv)
     if a.lonLatPoints:
         pts = parseLonLatPoints(a.lonLatPoints)
@@ -335,7 +392,7 @@ def main(argv=None):
     else:
         raise RuntimeError('ERROR must provide either iFile or lonLatPoints!')
     print(f'target points:\n {pts}')
-    f = Field(a.tFile, a.uFile, a.vFile, pts, a.sverdrup)
+    f = Field(a.tFile, a.uFile, a.vFile, pts, a.sverdrup, meshFile=a.meshFile or None)
     print(f'flux = {f.getFluxText()}')
     return f
 

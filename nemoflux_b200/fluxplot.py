@@ -25,10 +25,11 @@ def main(argv=None):
     ap.add_argument('-s', '--sverdrup', action='store_true')
     ap.add_argument('-o', '--output', default='', help='write the series as CSV (time, one column per transect)')
     ap.add_argument('--plot', action='store_true')
+    ap.add_argument('--meshFile', default='', help='optional mesh_mask file: e3u_0/e3v_0 (and e2u/e1v) scale factors')
     a = ap.parse_args(argv)
     pts, names = parseTransects(a.lonLatPoints, a.iFiles)
     print(f'target points:\n {pts}')
-    fld = Field(a.tFile, a.uFile, a.vFile, pts, a.sverdrup)
+    fld = Field(a.tFile, a.uFile, a.vFile, pts, a.sverdrup, meshFile=a.meshFile or None)
     series = fld.fluxSeries()
     timeVals = [fld.timeObj.getTimeAsDate(i) for i in range(fld.nt)]
     units = 'Sv' if a.sverdrup else 'A m^2/s'

@@ -42,8 +42,8 @@ def parseTransects(lonLatPoints='', iFiles=''):
 class FluxViz(object):
     """compute-only counterpart of fluxviz.FluxViz: holds the Field, steps in time, produces the title text"""
 
-    def __init__(self, tFile, uFile, vFile, lonLatZPoints, sverdrup=False):
-        self.field = Field(tFile, uFile, vFile, lonLatZPoints, sverdrup)
+    def __init__(self, tFile, uFile, vFile, lonLatZPoints, sverdrup=False, meshFile=None):
+        self.field = Field(tFile, uFile, vFile, lonLatZPoints, sverdrup, meshFile=meshFile)
 
     def update(self, key):
         if key == 't':
@@ -81,10 +81,11 @@ def main(argv=None):
     ap.add_argument('-i', '--iFiles', default='', help='alternatively read target points from text files')
     ap.add_argument('-s', '--sverdrup', action='store_true', help='use Sverdrup units (default is A m^2/s)')
     ap.add_argument('--allTimes', action='store_true', help='step through every time index')
+    ap.add_argument('--meshFile', default='', help='optional mesh_mask file: e3u_0/e3v_0 (and e2u/e1v) scale factors')
     a = ap.parse_args(argv)
     pts, _ = parseTransects(a.lonLatPoints, a.iFiles)
     print(f'target points:\n {pts}')
-    fv = FluxViz(a.tFile, a.uFile, a.vFile, pts, a.sverdrup)
+    fv = FluxViz(a.tFile, a.uFile, a.vFile, pts, a.sverdrup, meshFile=a.meshFile or None)
     fv.show(a.allTimes)
     return fv
 

@@ -262,16 +262,17 @@ class PolylineIntegral(object):
         batch_range=(b0, b1) (device tensors only): run only the batches b = t*npanels + q in [b0, b1) and return
         PARTIAL sums -- the building block of the balanced multi-GPU sharding in nemoflux_b200.dist.
 
-        e3u, e3v (device tensors only): per-column vertical scale factors, (1 or nt, nz, cells) with the dtype and
-        plane layout of uo/vo; they replace the 1-D thickness (fused pass with eflux=None when the
+        e3u, e3v: per-column vertical scale factors, (1 or nt, nz, cells) with the dtype and plane layout of
+        uo/vo (with host uo/vo: CUDA tensors uploaded once by the caller -- a mesh_mask's e3u_0/e3v_0 -- or host
+        arrays in the byte order of uo/vo, streamed with them when they hold nt time steps); they replace the 1-D thickness (fused pass with eflux=None when the
         policy of nfx_flux_series_e3 allows, else two launches)."""
         torch = _torch()
         if isinstance(u, torch.Tensor) and u.is_cuda:
             return self._flux_series_device(u, v, thickness, arc1, arc2, sverdrup, fill, order, eflux, out, batch_range,
                                             e3u, e3v)
-        if batch_range is not None or e3u is not None or e3v is not None:
-            raise ValueError('batch_range / e3u / e3v need CUDA tensors')
-        return self._flux_series_host(u, v, thickness, arc1, arc2, sverdrup, fill, order, chunk_steps)
+        if batch_range is not None:
+            raise ValueError('batch_range needs CUDA tensors')
+        return self._flux_series_host(u, v, thickness, arc1, arc2, sverdrup, fill, order, chunk_steps, e3u, e3v)
 
     def _flux_series_device(self, u, v, thickness, arc1, arc2, sverdrup, fill, order, eflux, out, batch_range=None,
                             e3u=None, e3v=None):
@@ -331,9 +332,9 @@ class PolylineIntegral(object):
                       _ORDERS[order], _t_ptr(eflux) if eflux is not None else None, _t_ptr(out), _stream_ptr())
         return out
 
-    def _flux_series_host(self, u, v, thickness, arc1, arc2, sverdrup, fill, order, chunk_steps):
+    def _flux_series_host(self, u, v, thickness, arc1, arc2, sverdrup, fill, order, chunk_steps, e3u=None, e3v=None):
         torch = _torch()
-        keep = (u, v)  # keep pinned tensors alive while numpy views are in use
+        keep = (u, v, e3u, e3v)  # keep pinned tensors alive while numpy views are in use
         if isinstance(u, torch.Tensor):
             u, v = u.numpy(), v.numpy()
         u = numpy.asarray(u)
@@ -349,13 +350,43 @@ class PolylineIntegral(object):
             u, v = numpy.ascontiguousarray(u), numpy.ascontiguousarray(v)
         nt, nz, ny, nx = u.shape
         ncell = ny * nx
-        th = numpy.ascontiguousarray(_to_numpy(thickness), numpy.float64)
         a1 = numpy.ascontiguousarray(_to_numpy(arc1), numpy.float64).reshape(-1)
         a2 = numpy.ascontiguousarray(_to_numpy(arc2), numpy.float64).reshape(-1)
-        if th.size != nz or a1.size != ncell or a2.size != ncell:
-            raise ValueError('thickness/arc1/arc2 sizes do not match uo')
+        if a1.size != ncell or a2.size != ncell:
+            raise ValueError('arc1/arc2 sizes do not match uo')
         m = self.getNumberOfTransects()
         out = numpy.zeros((nt, m), numpy.float64)
+        if e3u is not None or e3v is not None:
+            if e3u is None or e3v is None:
+                raise ValueError('e3u and e3v go together')
+            on_device = isinstance(e3u, torch.Tensor) and e3u.is_cuda
+            if on_device:
+                if not (isinstance(e3v, torch.Tensor) and e3v.is_cuda):
+                    raise ValueError('e3u and e3v must live on the same side')
+                want = torch.float64 if u.dtype.itemsize == 8 else torch.float32
+                for name, t in (('e3u', e3u), ('e3v', e3v)):
+                    if t.dtype != want or not t.is_contiguous():
+                        raise ValueError(f'{name} must be a contiguous CUDA tensor of the dtype of uo')
+                pu, pv = _t_ptr(e3u), _t_ptr(e3v)
+            else:
+                e3u, e3v = (numpy.asarray(x.numpy() if isinstance(x, torch.Tensor) else x) for x in (e3u, e3v))
+                for name, x in (('e3u', e3u), ('e3v', e3v)):
+                    if x.dtype != u.dtype:
+                        raise ValueError(f'{name} must have the dtype and byte order of uo ({u.dtype}), got {x.dtype}')
+                e3u, e3v = numpy.ascontiguousarray(e3u), numpy.ascontiguousarray(e3v)
+                pu, pv = _np_ptr(e3u), _np_ptr(e3v)
+            n3 = int(e3u.numel() if on_device else e3u.size)
+            if tuple(e3u.shape) != tuple(e3v.shape) or n3 not in (nz * ncell, nt * nz * ncell):
+                raise ValueError('e3u/e3v must hold (1 or nt, nz, ny*nx) values of the same shape')
+            e3_nt = n3 // (nz * ncell)
+            _lib.call('nfx_flux_series_host_e3', ctypes.byref(self._h), _np_ptr(u), _np_ptr(v), pu, pv, code, e3_nt,
+                      int(on_device), _np_ptr(a1), _np_ptr(a2), nt, nz, int(bool(sverdrup)), float(fill), _ORDERS[order],
+                      int(chunk_steps), _np_ptr(out))
+            del keep
+            return out
+        th = numpy.ascontiguousarray(_to_numpy(thickness), numpy.float64)
+        if th.size != nz:
+            raise ValueError('thickness size does not match uo')
         _lib.call('nfx_flux_series_host', ctypes.byref(self._h), _np_ptr(u), _np_ptr(v), code,
                   _np_ptr(th), _np_ptr(a1), _np_ptr(a2), nt, nz, int(bool(sverdrup)), float(fill), _ORDERS[order],
                   int(chunk_steps), _np_ptr(out))

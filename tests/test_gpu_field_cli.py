@@ -170,3 +170,74 @@ def test_vector_interp_matches_oracle_and_pictures(gpu, oracle, tmp_path):
     radial = f.vectorPoints[:, :2] - numpy.array([-180., 0.])
     inside = numpy.linalg.norm(radial, axis=1) > 15.
     assert ((f.vectorValues[inside, :2] * radial[inside]).sum(axis=1) > 0).all()
+
+
+def test_field_with_mesh_file_scale_factors(gpu, oracle, tmp_path, capsys):
+    """SURVEY 8f rank 4 through the tools: datagen --meshMask writes e3u_0/e3v_0/e2u/e1v, Field(meshFile=...) uses them
+    instead of deptht_bounds and the arc lengths.  Full cells: the same fluxes as without the file (to rounding:
+    arc*R/R); partial bottom cells: the oracle's series from its e3 edge fluxes; float32 files; the fluxplot flag"""
+    from nemoflux_b200 import fluxplot, ncio
+    from nemoflux_b200.field import EARTH_RADIUS, Field
+    args = [f'--streamFunction={SF_C2}', '--nx=72', '--ny=36', '--nz=5', '--nt=6', '--deltaDeg=20,30']
+    lines = [tr([(-100, -70), (100, -70), (0, 70)]), tr([(-150, -20), (-20, 35), (60, -40)])]
+    T, U, V = _files(tmp_path, *args, '--meshMask')
+    mesh = str(tmp_path) + '/mesh_mask.nc'
+    base = Field(T, U, V, lines, verbose=False)
+    s_base = base.fluxSeries(chunk_steps=4)
+    full = Field(T, U, V, lines, verbose=False, meshFile=mesh)
+    assert full.e3u.shape == (5, 36, 72) and numpy.allclose(full.arcLengths[:, 1:3], base.arcLengths[:, 1:3], rtol=1e-15)
+    s_full = full.fluxSeries(chunk_steps=4)
+    scale = numpy.abs(s_base).max()
+    assert numpy.abs(s_full - s_base).max() <= 1e-13 * scale
+    assert numpy.abs(full.fluxes - s_full[0]).max() <= 1e-13 * scale            # update() of time index 0
+    U0, _ = full.getUV()
+    Ub, _ = base.getUV()
+    assert numpy.allclose(U0, Ub, rtol=1e-14, atol=1e-300)
+    # partial bottom cells
+    sub = tmp_path / 'partial'
+    sub.mkdir()
+    T, U, V = _files(sub, *args, '--meshMask', '--partialCells=0.6')
+    mesh = str(sub) + '/mesh_mask.nc'
+    f = Field(T, U, V, lines, sverdrup=True, verbose=False, meshFile=mesh)
+    s = f.fluxSeries(chunk_steps=4)
+    with ncio.open_dataset(mesh) as nc:
+        e3u, e3v = nc['e3u_0'][:][0], nc['e3v_0'][:][0]
+        a1, a2 = nc['e2u'][:].reshape(-1) / EARTH_RADIUS, nc['e1v'][:].reshape(-1) / EARTH_RADIUS
+    assert e3u[-1].min() < 0.5 * e3u[0].max() and numpy.array_equal(e3u[0], numpy.full((36, 72), e3u[0, 0, 0]))
+    d = oracle.DataGen(nx=72, ny=36, nz=5, nt=6, deltaDeg=(20., 30.))
+    u, v = d.uv(SF_C2)
+    og = oracle.Grid(d.points())
+    ref, l1 = numpy.zeros((6, 2)), numpy.zeros((6, 2))
+    for m, xyz in enumerate(lines):
+        op = oracle.PolylineIntegral(og)
+        op.computeWeights(xyz)
+        keys, ws = op.merged_map()
+        for t in range(6):
+            eU, eV = oracle.edgeflux_step_c_e3(u[t], v[t], e3u, e3v, a1, a2, True)
+            iV = numpy.zeros((36, 72, 4))
+            iV[:, :, 1], iV[:, :, 2] = eU.reshape(36, 72), eV.reshape(36, 72)
+            iV[1:, :, 0] = iV[:-1, :, 2]
+            iV[:, 1:, 3] = iV[:, :-1, 1]
+            iV[:, 0, 3] = iV[:, -1, 1]
+            ref[t, m] = (ws * iV.reshape(-1)[keys]).sum()
+            l1[t, m] = numpy.abs(ws * iV.reshape(-1)[keys]).sum()
+    assert (numpy.abs(s - ref) <= 1e-12 * l1).all()
+    assert numpy.abs(s - 6.371 * s_base).max() > 1e-3 * scale                  # the thinner cells do change the flux
+    assert numpy.abs(f.fluxes - ref[0]).max() <= 1e-12 * l1[0].max()
+    # float32 velocity files: the scale factors are taken in the storage precision of uo/vo
+    for fname, vname, a in ((U, 'uo', u), (V, 'vo', v)):
+        w = ncio.Writer(fname)
+        for name, n in (('t', 6), ('z', 5), ('y', 36), ('x', 72)):
+            w.createDimension(name, n)
+        w.createVariable(vname, 'float32', ('t', 'z', 'y', 'x'), fill_value=1.e20, data=a.astype(numpy.float32))
+        w.close()
+    f32 = Field(T, U, V, lines, sverdrup=True, verbose=False, meshFile=mesh)
+    assert f32.e3u.dtype == numpy.float32
+    s32 = f32.fluxSeries(chunk_steps=4)
+    assert numpy.abs(s32 - ref).max() <= 1e-5 * numpy.abs(ref).max()
+    # the command-line flag
+    out = fluxplot.main(['-t', T, '-u', U, '-v', V, '-s', '--meshFile', mesh,
+                         '-l', '[(-100,-70),(100,-70),(0,70)],[(-150,-20),(-20,35),(60,-40)]'])
+    assert numpy.array_equal(out, s32)
+    with pytest.raises(RuntimeError):
+        Field(T, U, V, lines, verbose=False, meshFile=T)          # no e3u_0/e3v_0 in there

@@ -716,6 +716,27 @@ def test_fused_series_with_scale_factors(gpu, oracle, dtype, e3_nt, padded):
             assert numpy.array_equal(numpy.isfinite(fused), fin)
             assert (numpy.abs(fused[fin] - classic[fin]) <= 1e-13 * scale[fin] + 1e-300).all()
             assert (numpy.abs(fused[fin] - ref[fin]) <= FLUX_RTOL * scale[fin] + 1e-300).all()
+            # the host-buffer entry point (nfx_flux_series_host_e3): scale factors as host arrays (streamed in the
+            # chunks when time-varying, uploaded once otherwise), as device tensors, and big-endian as in a file
+            hu, hv = u.reshape(nt, nz, ny, nx), v.reshape(nt, nz, ny, nx)
+            host = p.fluxSeries(hu, hv, None, arc[:, 1].copy(), arc[:, 2].copy(), e3u=e3u, e3v=e3v, chunk_steps=2)
+            assert _lib_last_path() == 1
+            assert numpy.array_equal(host, fused, equal_nan=True)
+            dense = [torch.from_numpy(x).to(d) for x in (e3u, e3v)]
+            host_d = p.fluxSeries(hu, hv, None, arc[:, 1].copy(), arc[:, 2].copy(), e3u=dense[0], e3v=dense[1], chunk_steps=3)
+            assert numpy.array_equal(host_d, fused, equal_nan=True)
+            be = '>f8' if dtype == numpy.float64 else '>f4'
+            host_be = p.fluxSeries(hu.astype(be), hv.astype(be), None, arc[:, 1].copy(), arc[:, 2].copy(),
+                                   e3u=e3u.astype(be), e3v=e3v.astype(be), chunk_steps=2)
+            assert numpy.array_equal(host_be, fused, equal_nan=True)
+        _lib.set_option(_lib.NFX_OPT_FAST_SERIES, 0)            # two launches per chunk
+        host2 = p.fluxSeries(hu, hv, None, arc[:, 1].copy(), arc[:, 2].copy(), e3u=e3u, e3v=e3v, chunk_steps=2)
+        assert _lib_last_path() == 0
+        assert numpy.array_equal(host2, classic, equal_nan=True)
+        with pytest.raises(ValueError):
+            p.fluxSeries(hu, hv, None, arc[:, 1].copy(), arc[:, 2].copy(), e3u=e3u.astype(numpy.float16), e3v=e3v)
+        with pytest.raises(ValueError):
+            p.fluxSeries(hu, hv, None, arc[:, 1].copy(), arc[:, 2].copy(), e3u=e3u)
     finally:
         _lib.set_option(_lib.NFX_OPT_RING_SLOT_MB, 8)
         _lib.set_option(_lib.NFX_OPT_FAST_SERIES, 1)

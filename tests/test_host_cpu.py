@@ -160,6 +160,33 @@ def test_datagen_cli_writes_nemo_conventions(tmp_path):
         datagen.eval_stream_function('__import__("os").system("true")', 0., 0., 0., 0, 1, 0., 1.)
 
 
+def test_datagen_mesh_mask(tmp_path):
+    """datagen --meshMask [--partialCells f]: NEMO mesh_mask names and shapes; e3 = layer thickness except in the
+    thinned deepest level; e2u/e1v = the arc lengths of field.py:170-181 on the saved bounds, in metres"""
+    from nemoflux_b200 import datagen, geo, ncio
+    prefix = str(tmp_path) + '/'
+    datagen.cli(['-s', 'x', '--nx=24', '--ny=12', '--nz=3', '--nt=1', '--zmax=30', '--deltaDeg=20,30', '-p', prefix,
+                 '--meshMask', '--partialCells=0.5'])
+    with ncio.open_dataset(prefix + 'T.nc') as nc:
+        lon, lat, zb = nc['bounds_lon'][:], nc['bounds_lat'][:], nc['deptht_bounds'][:]
+    with ncio.open_dataset(prefix + 'mesh_mask.nc') as nc:
+        assert nc['e3u_0'].dimensions == ('t', 'z', 'y', 'x') and nc['e3u_0'].shape == (1, 3, 12, 24)
+        assert nc['e2u'].dimensions == ('t', 'y', 'x') and nc['e1v'].shape == (1, 12, 24)
+        e3u, e3v, e2u, e1v = nc['e3u_0'][:][0], nc['e3v_0'][:][0], nc['e2u'][:][0], nc['e1v'][:][0]
+    dz = zb[:, 1] - zb[:, 0]
+    assert numpy.array_equal(e3u[:2], numpy.broadcast_to(dz[:2, None, None], (2, 12, 24)))
+    assert numpy.array_equal(e3v[:2], e3u[:2])
+    for e3 in (e3u, e3v):
+        assert (e3[2] <= dz[2]).all() and (e3[2] > 0.5 * dz[2] - 1e-12).all() and len(numpy.unique(e3[2])) > 50
+    pts = numpy.zeros((12 * 24, 4, 3))
+    pts[:, :, 0], pts[:, :, 1] = lon.reshape(-1, 4), lat.reshape(-1, 4)
+    arc = geo.cellArcLengths(pts)
+    assert numpy.array_equal(e2u.reshape(-1), arc[:, 1] * 6371000.0) and numpy.array_equal(e1v.reshape(-1), arc[:, 2] * 6371000.0)
+    # without the flag no mesh file is written
+    datagen.cli(['-s', 'x', '-p', prefix + 'n'])
+    assert not os.path.exists(prefix + 'nmesh_mask.nc')
+
+
 def test_transect_argument_forms(tmp_path):
     from nemoflux_b200.field import parseLonLatPoints
     from nemoflux_b200.fluxviz import parseTransects

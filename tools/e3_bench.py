@@ -16,10 +16,17 @@ ap.add_argument('--shape', default='C3')
 ap.add_argument('--nt', type=int, default=24)
 ap.add_argument('--reps', type=int, default=10)
 ap.add_argument('--k2-variant', type=int, default=0)
+ap.add_argument('--k2-unroll', type=int, default=0)
+ap.add_argument('--k2-block', type=int, default=0)
+ap.add_argument('--out', default='gpurun_out/e3_bench.json')
 ap.add_argument('--dtypes', default='f64,f32')
 a = ap.parse_args()
 if a.k2_variant:
     _lib.set_option(_lib.NFX_OPT_K2_VARIANT, a.k2_variant)
+if a.k2_unroll:
+    _lib.set_option(_lib.NFX_OPT_K2_UNROLL, a.k2_unroll)
+if a.k2_block:
+    _lib.set_option(_lib.NFX_OPT_K2_BLOCK, a.k2_block)
 dev = torch.device('cuda', 0)
 syn = synth.make(a.shape)
 g = nemoflux_gpu.Grid()
@@ -64,4 +71,4 @@ for dname, tdt in (('f64', torch.float64), ('f32', torch.float32)):
             print(json.dumps(rows[-1]), flush=True)
     del u, v, e3u, e3v
 os.makedirs('gpurun_out', exist_ok=True)
-json.dump(dict(shape=a.shape, nt=a.nt, rows=rows), open('gpurun_out/e3_bench.json', 'w'), indent=1)
+json.dump(dict(shape=a.shape, nt=a.nt, k2_unroll=a.k2_unroll, k2_block=a.k2_block, rows=rows), open(a.out, 'w'), indent=1)

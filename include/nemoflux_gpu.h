@@ -193,6 +193,11 @@ int nfx_pli_get_num_panels(nfx_pli** self, int* npanels, int64_t* panel_cells);
 int nfx_flux_series_range(nfx_pli** self, const void* u, const void* v, int dtype, const double* thickness,
                           const double* arc1, const double* arc2, int nt, int nz, int64_t ld, int sverdrup, double fill,
                           int order, int64_t batch_begin, int64_t batch_end, double* series, void* stream);
+/* the same sub-range of batches with per-column scale factors (arguments as nfx_flux_series_e3) */
+int nfx_flux_series_range_e3(nfx_pli** self, const void* u, const void* v, const void* e3u, const void* e3v, int dtype,
+                             int e3_nt, const double* arc1, const double* arc2, int nt, int nz, int64_t ld, int sverdrup,
+                             double fill, int order, int64_t batch_begin, int64_t batch_end, double* series,
+                             void* stream);
 /* everything from HOST buffers (the call a non-CUDA host makes): u, v host (nt,nz,ny,nx), thickness
  * host (nz), arc1/arc2 host (ncell); series host (nt, ntransects).  Streams time chunks through
  * double-buffered device staging (host buffers may be pinned or pageable). chunk_steps <= 0 = auto */

@@ -686,6 +686,24 @@ int nfx_flux_series_range(nfx_pli** self, const void* u, const void* v, int dtyp
     });
 }
 
+int nfx_flux_series_range_e3(nfx_pli** self, const void* u, const void* v, const void* e3u, const void* e3v, int dtype,
+                             int e3_nt, const double* arc1, const double* arc2, int nt, int nz, int64_t ld, int sverdrup,
+                             double fill, int order, int64_t batch_begin, int64_t batch_end, double* series,
+                             void* stream) {
+    return guarded([&] {
+        NFX_REQUIRE(self && *self, "NULL handle");
+        PliDev& p = (*self)->d;
+        NFX_REQUIRE(p.grid, "setGrid was not called");
+        DeviceGuard g(p.grid->device);
+        NFX_REQUIRE(u && v && e3u && e3v && arc1 && arc2 && series, "NULL pointer");
+        NFX_REQUIRE(ld >= p.grid->ncell, "ld must be >= the number of cells");
+        NFX_REQUIRE(e3_nt == 1 || e3_nt == nt, "e3u/e3v must hold 1 (time-invariant) or nt time steps");
+        g_last_series_fused = 1;
+        flux_series_fast(p, u, v, dtype, nullptr, arc1, arc2, nt, nz, ld, sverdrup, fill, order, series,
+                         (cudaStream_t)stream, batch_begin, batch_end, e3u, e3v, e3_nt == 1 ? 0 : (int64_t)nz * ld);
+    });
+}
+
 int nfx_flux_series(nfx_pli** self, const void* u, const void* v, int dtype, const double* thickness,
                     const double* arc1, const double* arc2, int nt, int nz, int sverdrup, double fill, int order,
                     double* eflux, double* series, void* stream) {

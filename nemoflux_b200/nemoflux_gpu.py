@@ -298,13 +298,20 @@ class PolylineIntegral(object):
         if nt == 0 or m == 0:       # nothing to integrate: no launch (empty tensors have no device address)
             return out if out is not None else torch.zeros((nt, m), dtype=torch.float64, device=u.device)
         if use_e3:
-            if batch_range is not None:
-                raise ValueError('batch_range and e3u/e3v cannot be combined')
             e3_nt = _check_e3(e3u, e3v, u, nt, nz, ncell, ld)
             if eflux is not None:
                 _require_cuda(eflux, torch.float64, 'eflux')
             if out is None:
                 out = torch.empty((nt, m), dtype=torch.float64, device=u.device)
+            if batch_range is not None:
+                if eflux is not None:
+                    raise ValueError('batch_range and eflux cannot be combined')
+                with torch.cuda.device(u.device):
+                    _lib.call('nfx_flux_series_range_e3', ctypes.byref(self._h), _t_ptr(u), _t_ptr(v), _t_ptr(e3u),
+                              _t_ptr(e3v), _dtype_code(str(u.dtype)), e3_nt, _t_ptr(arc1), _t_ptr(arc2), nt, nz, ld,
+                              int(bool(sverdrup)), float(fill), _ORDERS[order], int(batch_range[0]), int(batch_range[1]),
+                              _t_ptr(out), _stream_ptr())
+                return out
             with torch.cuda.device(u.device):
                 _lib.call('nfx_flux_series_e3', ctypes.byref(self._h), _t_ptr(u), _t_ptr(v), _t_ptr(e3u), _t_ptr(e3v),
                           _dtype_code(str(u.dtype)), e3_nt, _t_ptr(arc1), _t_ptr(arc2), nt, nz, ld, int(bool(sverdrup)),

@@ -716,6 +716,19 @@ def test_fused_series_with_scale_factors(gpu, oracle, dtype, e3_nt, padded):
             assert numpy.array_equal(numpy.isfinite(fused), fin)
             assert (numpy.abs(fused[fin] - classic[fin]) <= 1e-13 * scale[fin] + 1e-300).all()
             assert (numpy.abs(fused[fin] - ref[fin]) <= FLUX_RTOL * scale[fin] + 1e-300).all()
+            if slot_mb == 1:      # balanced sharding with scale factors: the partial series of 3 'ranks' add up
+                from nemoflux_b200 import dist
+                total = numpy.zeros_like(fused)
+                eu_t = lambda t0, n: eu if e3_nt == 1 else eu[t0:t0 + n]      # noqa: E731
+                ev_t = lambda t0, n: ev if e3_nt == 1 else ev[t0:t0 + n]      # noqa: E731
+                for r in range(3):
+                    sh = dist.shard_batches(nt, 2, 3, r)
+                    t0, n = sh['t_first'], sh['nt_touched']
+                    part = p.fluxSeries(ud[t0:t0 + n], vd[t0:t0 + n], None, a1, a2, e3u=eu_t(t0, n), e3v=ev_t(t0, n),
+                                        batch_range=(sh['b0'], sh['b1']))
+                    total[t0:t0 + n] += part.cpu().numpy()
+                assert numpy.array_equal(numpy.isfinite(total), fin)
+                assert (numpy.abs(total[fin] - fused[fin]) <= 1e-13 * scale[fin] + 1e-300).all()
             # the host-buffer entry point (nfx_flux_series_host_e3): scale factors as host arrays (streamed in the
             # chunks when time-varying, uploaded once otherwise), as device tensors, and big-endian as in a file
             hu, hv = u.reshape(nt, nz, ny, nx), v.reshape(nt, nz, ny, nx)

@@ -245,7 +245,9 @@ template <typename T, int VEC>
 void dispatch_ldg(const T* u, const T* v, const double* dz, const double* arc1, const double* arc2, double* eflux, int nt,
                   int nz, int64_t ncell, int64_t ld, double scale, int use_scale, T fill, int has_fill, int keep_l2,
                   const E3Args& e3, const K2Options& opt, cudaStream_t s) {
-    const int unroll = opt.unroll > 0 ? opt.unroll : 5;
+    // four float32 streams (e3u/e3v): 15 levels in flight at 80 registers stream 14 % faster than 5 at 72
+    // (6.37 vs 5.58 TB/s, tools/e3_bench.py --k2-unroll); every other shape is within 1 % from 3 to 15
+    const int unroll = opt.unroll > 0 ? opt.unroll : (e3.e3u && sizeof(T) == 4 && VEC > 1) ? 15 : 5;
     const int block = opt.block > 0 ? opt.block : 256;
 #define NFX_K2_CASE(U, B)                                                                                          \
     if (unroll == U && block == B) {                                                                               \

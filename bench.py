@@ -237,9 +237,14 @@ def run_b200(args):
     assert torch.cuda.is_available(), 'bench.py needs a CUDA device (no CPU fallback)'
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
+    cpu_binding = 0
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         dist.init_process_group('nccl', device_id=dev)
+        # one process per GPU: keep the rank (and the pinned host buffers of the e2e leg) on the CPUs next to its GPU.
+        # No effect where NVML reports no affinity (the pool's 8-GPU boxes are single-node VMs, profiles/r1_numa_probe8.md)
+        from nemoflux_b200 import dist as _nd
+        cpu_binding = _nd.bind_to_gpu_cpus(local_rank)
 
     if args.k2_variant:
         _lib.set_option(_lib.NFX_OPT_K2_VARIANT, args.k2_variant)
@@ -544,6 +549,7 @@ def run_b200(args):
         'hbm_gbs_aggregate': 2.0 * esize * units_step_all / (ms_per_step * 1e-3) / 1e9,
         'roofline': roofline, 'clocks': clocks, 'gpu_launches': int(launches),
         'one_off': {'locator_s': t_locator, 'k1_compute_weights_s': t_k1},
+        'cpus_bound_per_rank': cpu_binding,
         'parity': parity,
     }
     if e2e is not None:

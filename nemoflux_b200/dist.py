@@ -141,3 +141,49 @@ def check_partition(nt, world):
         t0, n = shard_time(nt, world, r)
         covered[t0:t0 + n] += 1
     return bool((covered == 1).all())
+
+
+def gpu_local_cpus(device_index):
+    """CPUs NVML reports as local to the GPU (same NUMA node / PCIe root), intersected with the CPUs this process
+    may use; an empty set when NVML or the information is not available (containers often hide it)."""
+    import os
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        try:
+            uuid = str(torch.cuda.get_device_properties(device_index).uuid)
+            h = None
+            for i in range(pynvml.nvmlDeviceGetCount()):     # CUDA_VISIBLE_DEVICES renumbers: match by UUID
+                hi = pynvml.nvmlDeviceGetHandleByIndex(i)
+                u = pynvml.nvmlDeviceGetUUID(hi)
+                u = u.decode() if isinstance(u, bytes) else u
+                if uuid in u:
+                    h = hi
+                    break
+            if h is None:
+                return set()
+            ncpu = os.cpu_count() or 1
+            words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        finally:
+            pynvml.nvmlShutdown()
+    except Exception:
+        return set()
+    cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+    return cpus & set(os.sched_getaffinity(0))
+
+
+def bind_to_gpu_cpus(device_index):
+    """Run this process (and the pinned host buffers it allocates from now on: first touch) on the CPUs next to its
+    GPU.  With one process per GPU on a two-socket box this keeps every rank's host->device stream on its own
+    socket's memory controllers and PCIe root instead of crossing the socket link.  Returns the number of CPUs the
+    process was bound to, 0 if nothing was changed."""
+    import os
+    cpus = gpu_local_cpus(device_index)
+    if not cpus or cpus == set(os.sched_getaffinity(0)):
+        return 0
+    try:
+        os.sched_setaffinity(0, cpus)
+    except OSError:
+        return 0
+    return len(cpus)

@@ -290,6 +290,21 @@ print('ok', rank)
 '''
 
 
+def test_gpu_cpu_binding_is_harmless_without_nvml_affinity():
+    """bind_to_gpu_cpus: no GPU / no affinity information -> nothing changes and 0 is returned"""
+    from nemoflux_b200 import dist
+    before = os.sched_getaffinity(0)
+    import torch
+    if not torch.cuda.is_available():
+        assert dist.gpu_local_cpus(0) == set()
+        assert dist.bind_to_gpu_cpus(0) == 0
+    else:
+        n = dist.bind_to_gpu_cpus(0)
+        assert n == 0 or n == len(os.sched_getaffinity(0))
+        os.sched_setaffinity(0, before)
+    assert os.sched_getaffinity(0) == before
+
+
 @pytest.mark.parametrize('nt', [7, 8])
 def test_allgather_series_two_ranks_gloo(tmp_path, nt):
     """world_size 2 on CPU: uneven (4+3) and even shards assemble to the single-rank series bit for bit"""

@@ -221,3 +221,46 @@ def test_edge_cases(oracle):
     iV = iV.reshape(18, 36, 4)
     assert (iV[0, :, 0] == 0).all() and numpy.array_equal(iV[:, 0, 3], eU.reshape(18, 36)[:, -1])
     assert oracle.lib().orc_flux_index(0, 0, 18, 36) == -1 and oracle.lib().orc_flux_index(36, 3, 18, 36) == 71
+
+
+def test_orientation_and_additivity_properties(oracle):
+    """properties any line integral of a 1-form has, with random single-valued edge data: reversing the transect
+    flips the sign, cutting it at a vertex splits the integral, every segment inside the grid is fully covered
+    (sum of (tb - ta) * coeff = 1) -- on a curvilinear (pole-displaced) and on a rectilinear grid; inserting a vertex
+    on a segment changes nothing on the rectilinear grid (on a curvilinear cell the weights integrate along the
+    straight line in PARAMETER space between the sub-segment's ends, so an extra vertex changes the path)"""
+    rng = numpy.random.default_rng(42)
+    for delta in ((20., 30.), (0., 0.)):
+        d = oracle.DataGen(nx=48, ny=24, deltaDeg=delta, ymin=-80., ymax=80., dy=160. / 24)
+        g = oracle.Grid(d.points())
+        data = rng.standard_normal((48 * 24, 4))
+        # single valued per edge (east of c = west of c+1, north of c = south of the cell above), as C-grid fluxes are
+        dd = data.reshape(24, 48, 4)
+        dd[:, 1:, 3] = dd[:, :-1, 1]
+        dd[:, 0, 3] = dd[:, -1, 1]
+        dd[1:, :, 0] = dd[:-1, :, 2]
+        scale = numpy.abs(data).max()
+
+        def integral(pts):
+            p = oracle.PolylineIntegral(g)
+            p.computeWeights(tr(pts))
+            return p.getIntegral(data), p
+
+        for _ in range(12):
+            k = int(rng.integers(3, 7))
+            lat = 60. if delta == (0., 0.) else 45.     # the displaced grid leaves a 10 degree cap around (., +-60) uncovered
+            pts = [(float(rng.uniform(-170, 170)), float(rng.uniform(-lat, lat))) for _ in range(k)]
+            f, p = integral(pts)
+            l1 = numpy.abs(p.emission_list()[2]).sum() * scale
+            frev, _ = integral(pts[::-1])
+            assert abs(f + frev) <= 1e-12 * l1
+            cut = int(rng.integers(1, k - 1))
+            fa, _ = integral(pts[:cut + 1])
+            fb, _ = integral(pts[cut:])
+            assert abs(f - (fa + fb)) <= 1e-12 * l1
+            assert numpy.abs(p.segment_totals(k - 1) - 1.0).max() <= 1e-12
+            if delta == (0., 0.):
+                s = float(rng.uniform(0.2, 0.8))
+                mid = (pts[0][0] + s * (pts[1][0] - pts[0][0]), pts[0][1] + s * (pts[1][1] - pts[0][1]))
+                fins, _ = integral([pts[0], mid] + pts[1:])
+                assert abs(f - fins) <= 1e-11 * l1

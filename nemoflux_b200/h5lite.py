@@ -1,0 +1,607 @@
+"""Minimal read-only HDF5 reader for NetCDF-4 files in the classic data model (what NEMO and subsetNEMO.py:78
+write): one root group of N-dimensional numeric datasets with attributes.  Used by ncio.py when the netCDF4
+package is not installed, so that files like the reference's data/sa/T.nc can be read.
+
+Supported, following the HDF5 file format specification v3: superblock versions 0-3; old-style groups (symbol
+table: local heap + version-1 B-tree) and new-style groups (link messages, or dense storage: fractal heap + version-2
+B-tree of depth 0/1); object headers of versions 1 and 2 with continuation blocks; dataspaces v1/v2; fixed-point and
+floating-point datatypes of either byte order, fixed and variable length strings (attributes); data layouts compact,
+contiguous and chunked (version-1 chunk B-tree; layout message versions 3 and 4 with the v1 B-tree index) with the
+deflate, shuffle and fletcher32 filters; attributes in the header or in dense storage.
+
+Not supported (raises H5Error): compound/array/enum/reference datatypes, external storage, virtual datasets,
+the newer chunk indexes of layout version 4 (single chunk, implicit, fixed/extensible array, v2 B-tree), user
+filters.  Test status: validated on the reference's data/sa/T.nc (netCDF 4.7.3 / HDF5 1.10.5: v2 object headers,
+dense links, contiguous float32/float64 datasets, dense attributes); the chunked + deflate + shuffle path follows
+the specification and is exercised on hand-built chunk trees in tests/test_host_cpu.py, not on a file written by
+the HDF5 library.
+"""
+import struct
+import zlib
+
+import numpy
+
+UNDEF = 0xFFFFFFFFFFFFFFFF
+SIGNATURE = b'\x89HDF\r\n\x1a\n'
+
+
+class H5Error(RuntimeError):
+    pass
+
+
+class Dataset(object):
+    """one HDF5 dataset: name, shape, dtype (numpy, in the file's byte order), attrs, read()"""
+
+    def __init__(self, f, name, shape, dtype, layout, filters, attrs, fill):
+        self._f, self.name, self.shape, self.dtype = f, name, tuple(shape), dtype
+        self._layout, self._filters, self.attrs, self.fill = layout, filters, attrs, fill
+
+    def read(self):
+        """the whole array, in the file's byte order"""
+        kind = self._layout[0]
+        n = int(numpy.prod(self.shape, dtype=numpy.int64)) if self.shape else 1
+        if kind == 'compact':
+            return numpy.frombuffer(self._layout[1], self.dtype, n).reshape(self.shape).copy()
+        if kind == 'contiguous':
+            addr, size = self._layout[1], self._layout[2]
+            if addr == UNDEF:                                   # never written: the fill value (default 0)
+                a = numpy.zeros(self.shape, self.dtype)
+                if self.fill is not None:
+                    a[...] = numpy.frombuffer(self.fill, self.dtype, 1)[0]
+                return a
+            buf = self._f._read(addr, n * self.dtype.itemsize)
+            return numpy.frombuffer(buf, self.dtype, n).reshape(self.shape).copy()
+        if kind == 'single_chunk':
+            addr, cdims, fsize, mask = self._layout[1:5]
+            nraw = fsize if fsize is not None else n * self.dtype.itemsize
+            raw = apply_filters_reverse(self._f._read(addr, nraw), self._filters if fsize is not None else [], mask,
+                                        self.dtype.itemsize)
+            return numpy.frombuffer(raw, self.dtype, n).reshape(self.shape).copy()
+        if kind == 'chunked':
+            return self._read_chunked()
+        raise H5Error(f'{self.name}: unsupported data layout {kind}')
+
+    def _read_chunked(self):
+        addr, cdims = self._layout[1], self._layout[2]          # chunk dims in elements (without the element size)
+        out = numpy.zeros(self.shape, self.dtype)
+        if self.fill is not None:
+            out[...] = numpy.frombuffer(self.fill, self.dtype, 1)[0]
+        if addr == UNDEF:
+            return out
+        rank = len(self.shape)
+        csize = int(numpy.prod(cdims)) * self.dtype.itemsize
+        for offsets, nbytes, mask, caddr in self._f._chunk_btree(addr, rank):
+            raw = self._f._read(caddr, nbytes)
+            raw = apply_filters_reverse(raw, self._filters, mask, self.dtype.itemsize)
+            if len(raw) < csize:
+                raise H5Error(f'{self.name}: a chunk holds {len(raw)} bytes, expected {csize}')
+            chunk = numpy.frombuffer(raw, self.dtype, csize // self.dtype.itemsize).reshape(cdims)
+            sel_out, sel_in = [], []
+            for d in range(rank):                               # edge chunks hang over the dataset
+                lo = offsets[d]
+                hi = min(lo + cdims[d], self.shape[d])
+                if hi <= lo:
+                    break
+                sel_out.append(slice(lo, hi))
+                sel_in.append(slice(0, hi - lo))
+            else:
+                out[tuple(sel_out)] = chunk[tuple(sel_in)]
+        return out
+
+
+def apply_filters_reverse(raw, filters, mask, itemsize):
+    """undo the filter pipeline of one chunk (filters listed in the order they were applied when writing)"""
+    for i in reversed(range(len(filters))):
+        if (mask >> i) & 1:
+            continue                                            # this filter was skipped for this chunk
+        fid, cdata = filters[i]
+        if fid == 1:
+            raw = zlib.decompress(raw)
+        elif fid == 2:                                          # shuffle: byte planes -> elements
+            size = cdata[0] if cdata else itemsize
+            n = len(raw) // size
+            if n and size > 1:
+                a = numpy.frombuffer(raw, numpy.uint8, n * size).reshape(size, n)
+                raw = a.T.tobytes() + raw[n * size:]
+        elif fid == 3:                                          # fletcher32: a 4-byte checksum at the end
+            raw = raw[:-4]
+        else:
+            raise H5Error(f'unsupported HDF5 filter id {fid}')
+    return raw
+
+
+class File(object):
+    def __init__(self, path):
+        self.path = path
+        self._fh = open(path, 'rb')
+        try:
+            import mmap
+            self._buf = mmap.mmap(self._fh.fileno(), 0, access=mmap.ACCESS_READ)
+        except (ValueError, OSError):
+            self._buf = self._fh.read()
+        self.datasets = {}
+        self.attrs = {}
+        self._gcol = {}
+        self._parse_superblock()
+        root = self._object(self._root_addr)
+        self.attrs = root['attrs']
+        for name, addr in self._links(root):
+            obj = self._object(addr)
+            if obj['shape'] is not None and obj['dtype'] is not None and obj['layout'] is not None:
+                self.datasets[name] = Dataset(self, name, obj['shape'], obj['dtype'], obj['layout'], obj['filters'],
+                                              obj['attrs'], obj['fill'])
+
+    def close(self):
+        try:
+            if hasattr(self._buf, 'close'):
+                self._buf.close()
+        except (BufferError, ValueError):
+            pass
+        self._fh.close()
+
+    # ---- raw access -------------------------------------------------------------------------------------
+    def _read(self, addr, n):
+        a = self._base + addr
+        if addr == UNDEF or a + n > len(self._buf):
+            raise H5Error(f'{self.path}: read of {n} bytes at {addr} is outside the file')
+        return bytes(self._buf[a:a + n])
+
+    def _uint(self, buf, off, size):
+        return int.from_bytes(buf[off:off + size], 'little')
+
+    def _parse_superblock(self):
+        b = self._buf
+        self._base = 0
+        if bytes(b[:8]) != SIGNATURE:
+            raise H5Error(f'{self.path}: not an HDF5 file')
+        ver = b[8]
+        if ver in (0, 1):
+            self._O, self._L = b[13], b[14]
+            off = 24 + (4 if ver == 1 else 0)
+            O = self._O
+            base = self._uint(b, off, O)
+            self._base = 0 if base == UNDEF else base
+            ste = off + 4 * O                                   # root group symbol table entry
+            self._root_addr = self._uint(b, ste + O, O)
+        elif ver in (2, 3):
+            self._O, self._L = b[9], b[10]
+            O = self._O
+            base = self._uint(b, 12, O)
+            self._base = 0 if base == UNDEF else base
+            self._root_addr = self._uint(b, 12 + 3 * O, O)
+        else:
+            raise H5Error(f'{self.path}: unsupported superblock version {ver}')
+        if self._O != 8 or self._L != 8:
+            raise H5Error(f'{self.path}: only 8-byte offsets and lengths are supported')
+
+    # ---- object headers ------------------------------------------------------------------------------------
+    def _messages(self, addr):
+        """[(type, flags, data)] of the object header at addr (versions 1 and 2, continuation blocks followed)"""
+        head = self._read(addr, 16)
+        out = []
+        if head[:4] == b'OHDR':
+            if head[4] != 2:
+                raise H5Error(f'object header version {head[4]} is not supported')
+            flags = head[5]
+            p = 6
+            if flags & 0x20:
+                p += 16                                         # access, modification, change, birth times
+            if flags & 0x10:
+                p += 4                                          # max compact / min dense attributes
+            nsz = 1 << (flags & 3)
+            head = self._read(addr, p + nsz)
+            chunk0 = self._uint(head, p, nsz)
+            p += nsz
+            corder = 2 if flags & 0x04 else 0
+            blocks = [(addr + p, chunk0)]
+            while blocks:
+                baddr, blen = blocks.pop(0)
+                buf = self._read(baddr, blen)
+                q = 0
+                while q + 4 + corder <= blen:
+                    mtype, msize, mflags = buf[q], self._uint(buf, q + 1, 2), buf[q + 3]
+                    q += 4 + corder
+                    data = buf[q:q + msize]
+                    q += msize
+                    if mtype == 0x10:                           # continuation: OCHK signature + messages + checksum
+                        caddr, clen = self._uint(data, 0, 8), self._uint(data, 8, 8)
+                        if self._read(caddr, 4) != b'OCHK':
+                            raise H5Error('bad object header continuation block')
+                        blocks.append((caddr + 4, clen - 8))
+                    elif mtype != 0:
+                        out.append((mtype, mflags, data))
+            return out
+        if head[0] != 1:
+            raise H5Error(f'object header at {addr}: unknown version {head[0]}')
+        nmsg = self._uint(head, 2, 2)
+        size = self._uint(head, 8, 4)
+        blocks = [(addr + 16, size)]
+        while blocks and len(out) < nmsg + 64:
+            baddr, blen = blocks.pop(0)
+            buf = self._read(baddr, blen)
+            q = 0
+            while q + 8 <= blen:
+                mtype, msize, mflags = self._uint(buf, q, 2), self._uint(buf, q + 2, 2), buf[q + 4]
+                q += 8
+                data = buf[q:q + msize]
+                q += msize
+                if mtype == 0x10:
+                    blocks.append((self._uint(data, 0, 8), self._uint(data, 8, 8)))
+                elif mtype != 0:
+                    out.append((mtype, mflags, data))
+        return out
+
+    def _object(self, addr):
+        o = dict(shape=None, dtype=None, layout=None, filters=[], attrs={}, fill=None, links=[], link_info=None,
+                 symtab=None, attr_info=None)
+        for mtype, mflags, data in self._messages(addr):
+            if mflags & 0x02:
+                continue                                        # shared message: not used by netCDF-4 variables
+            if mtype == 0x01:
+                o['shape'] = self._dataspace(data)[0]
+            elif mtype == 0x03:
+                o['dtype'] = self._datatype(data)[0]
+            elif mtype == 0x05:
+                o['fill'] = self._fill_value(data)
+            elif mtype == 0x08:
+                o['layout'] = self._layout(data)
+            elif mtype == 0x0B:
+                o['filters'] = self._filters(data)
+            elif mtype == 0x0C:
+                try:
+                    name, value = self._attribute(data)
+                    o['attrs'][name] = value
+                except H5Error:
+                    pass                                        # an attribute of a type we do not decode
+            elif mtype == 0x06:
+                lk = self._link(data)
+                if lk:
+                    o['links'].append(lk)
+            elif mtype == 0x02:
+                o['link_info'] = data
+            elif mtype == 0x11:
+                o['symtab'] = (self._uint(data, 0, 8), self._uint(data, 8, 8))
+            elif mtype == 0x15:
+                o['attr_info'] = data
+        if o['attr_info'] is not None:                          # dense attribute storage
+            d = o['attr_info']
+            p = 2 + (2 if d[1] & 1 else 0)
+            heap, bt = self._uint(d, p, 8), self._uint(d, p + 8, 8)
+            if heap != UNDEF and bt != UNDEF:
+                for rec in self._btree2_records(bt):
+                    try:
+                        name, value = self._attribute(self._heap_object(heap, rec[:8]))
+                        o['attrs'][name] = value
+                    except H5Error:
+                        pass
+        if o['layout'] is not None and o['layout'][0] == 'chunked' and o['shape'] is not None:
+            o['layout'] = ('chunked', o['layout'][1], tuple(o['layout'][2][:len(o['shape'])]))
+        return o
+
+    # ---- groups --------------------------------------------------------------------------------------------
+    def _links(self, group):
+        """[(name, object header address)] of a group object"""
+        out = list(group['links'])
+        if group['link_info'] is not None:
+            d = group['link_info']
+            p = 2 + (8 if d[1] & 1 else 0)
+            heap, bt = self._uint(d, p, 8), self._uint(d, p + 8, 8)
+            if heap != UNDEF and bt != UNDEF:
+                for rec in self._btree2_records(bt):
+                    lk = self._link(self._heap_object(heap, rec[4:11]))
+                    if lk:
+                        out.append(lk)
+        if group['symtab'] is not None:
+            btree, heap = group['symtab']
+            hd = self._read(heap, 32)
+            if hd[:4] != b'HEAP':
+                raise H5Error('bad local heap')
+            data_addr = self._uint(hd, 24, 8)
+            for snod in self._group_btree(btree):
+                n = self._uint(self._read(snod, 8), 6, 2)
+                ent = self._read(snod + 8, n * 40)
+                for i in range(n):
+                    noff, oaddr = self._uint(ent, 40 * i, 8), self._uint(ent, 40 * i + 8, 8)
+                    raw = self._read(data_addr + noff, 256)
+                    out.append((raw.split(b'\0', 1)[0].decode(), oaddr))
+        return out
+
+    def _group_btree(self, addr):
+        """symbol table node addresses under a version-1 group B-tree"""
+        hd = self._read(addr, 24)
+        if hd[:4] == b'SNOD':
+            return [addr]
+        if hd[:4] != b'TREE' or hd[4] != 0:
+            raise H5Error('bad group B-tree node')
+        level, n = hd[5], self._uint(hd, 6, 2)
+        body = self._read(addr + 24, (2 * n + 1) * 8)
+        out = []
+        for i in range(n):
+            child = self._uint(body, 8 + 16 * i, 8)
+            out += self._group_btree(child) if level > 0 else [child]
+        return out
+
+    def _link(self, d):
+        """link message -> (name, address) for hard links, None otherwise"""
+        flags = d[1]
+        p = 2
+        ltype = 0
+        if flags & 0x08:
+            ltype = d[p]
+            p += 1
+        if flags & 0x04:
+            p += 8
+        if flags & 0x10:
+            p += 1
+        nsz = 1 << (flags & 3)
+        nlen = self._uint(d, p, nsz)
+        p += nsz
+        name = bytes(d[p:p + nlen]).decode('utf-8', 'replace')
+        p += nlen
+        if ltype != 0:
+            return None
+        return name, self._uint(d, p, 8)
+
+    # ---- fractal heap + version-2 B-tree (dense links / attributes) ---------------------------------------------
+    def _btree2_records(self, addr):
+        hd = self._read(addr, 38)
+        if hd[:4] != b'BTHD':
+            raise H5Error('bad version-2 B-tree header')
+        node_size, rec_size, depth = self._uint(hd, 6, 4), self._uint(hd, 10, 2), self._uint(hd, 12, 2)
+        root, nroot = self._uint(hd, 16, 8), self._uint(hd, 24, 2)
+        if root == UNDEF or nroot == 0:
+            return []
+        if depth == 0:
+            return self._btree2_leaf(root, nroot, rec_size)
+        if depth != 1:
+            raise H5Error('version-2 B-trees deeper than 1 are not supported')
+        # internal node: records, then child pointers (address, number of records sized for a leaf's capacity)
+        max_leaf = (node_size - 10) // rec_size
+        nbytes = max(1, (max_leaf.bit_length() + 7) // 8)
+        buf = self._read(root, node_size)
+        if buf[:4] != b'BTIN':
+            raise H5Error('bad version-2 B-tree internal node')
+        p = 6
+        recs = [buf[p + i * rec_size:p + (i + 1) * rec_size] for i in range(nroot)]
+        p += nroot * rec_size
+        out = []
+        for i in range(nroot + 1):
+            child, n = self._uint(buf, p, 8), self._uint(buf, p + 8, nbytes)
+            p += 8 + nbytes
+            out += self._btree2_leaf(child, n, rec_size)
+            if i < nroot:
+                out.append(recs[i])
+        return out
+
+    def _btree2_leaf(self, addr, n, rec_size):
+        buf = self._read(addr, 6 + n * rec_size)
+        if buf[:4] != b'BTLF':
+            raise H5Error('bad version-2 B-tree leaf')
+        return [buf[6 + i * rec_size:6 + (i + 1) * rec_size] for i in range(n)]
+
+    def _heap_header(self, addr):
+        hd = self._read(addr, 146)
+        if hd[:4] != b'FRHP':
+            raise H5Error('bad fractal heap header')
+        h = dict(id_len=self._uint(hd, 5, 2), filt_len=self._uint(hd, 7, 2), flags=hd[9],
+                 max_managed=self._uint(hd, 10, 4), width=self._uint(hd, 110, 2), start=self._uint(hd, 112, 8),
+                 max_direct=self._uint(hd, 120, 8), max_bits=self._uint(hd, 128, 2), root=self._uint(hd, 132, 8),
+                 cur_rows=self._uint(hd, 140, 2))
+        if h['filt_len']:
+            raise H5Error('filtered fractal heaps are not supported')
+        return h
+
+    def _heap_object(self, heap_addr, hid):
+        h = self._heap_header(heap_addr)
+        if (hid[0] >> 4) & 3 != 0:
+            raise H5Error('only managed fractal heap objects are supported')
+        obytes = (h['max_bits'] + 7) // 8
+        lbits = min(h['max_direct'], h['max_managed']).bit_length()
+        lbytes = max(1, min(len(hid) - 1 - obytes, (lbits + 7) // 8))
+        off = self._uint(hid, 1, obytes)
+        length = self._uint(hid, 1 + obytes, lbytes)
+        if h['cur_rows'] == 0:                                  # the root block is a direct block covering offset 0..
+            return self._read(h['root'] + off, length)
+        # one indirect root block: rows of `width` direct blocks, sizes start, start, 2*start, 4*start, ...
+        hdr = 5 + 8 + obytes
+        nrows_direct = (h['max_direct'] // h['start']).bit_length() + 1
+        rows = min(h['cur_rows'], nrows_direct)
+        table = self._read(h['root'] + hdr, rows * h['width'] * 8)
+        pos, k = 0, 0
+        for r in range(rows):
+            bsize = h['start'] * (1 if r < 2 else 1 << (r - 1))
+            for _ in range(h['width']):
+                baddr = self._uint(table, 8 * k, 8)
+                k += 1
+                if pos <= off < pos + bsize:
+                    if baddr == UNDEF:
+                        raise H5Error('fractal heap object in an unallocated block')
+                    return self._read(baddr + (off - pos), length)
+                pos += bsize
+        raise H5Error('fractal heap object outside the direct blocks of the root indirect block')
+
+    # ---- messages ---------------------------------------------------------------------------------------------
+    def _dataspace(self, d):
+        ver, rank, flags = d[0], d[1], d[2]
+        if ver == 1:
+            p = 8
+        elif ver == 2:
+            p = 4
+            if d[3] == 2:
+                return None, 4                                  # null dataspace
+        else:
+            raise H5Error(f'dataspace version {ver}')
+        shape = tuple(self._uint(d, p + 8 * i, 8) for i in range(rank))
+        p += 8 * rank
+        if flags & 1:
+            p += 8 * rank
+        return shape, p
+
+    def _datatype(self, d):
+        """(numpy dtype or ('vlen_str',) / ('str', n), bytes consumed)"""
+        cls, ver = d[0] & 0x0F, d[0] >> 4
+        bits0 = d[1]
+        size = self._uint(d, 4, 4)
+        order = '>' if bits0 & 1 else '<'
+        if cls == 0:
+            kind = 'i' if bits0 & 0x08 else 'u'
+            return numpy.dtype(f'{order}{kind}{size}'), 12
+        if cls == 1:
+            if size not in (2, 4, 8):
+                raise H5Error(f'floating point size {size}')
+            return numpy.dtype(f'{order}f{size}'), 20
+        if cls == 3:
+            return ('str', size), 8
+        if cls == 9:
+            base, used = self._datatype(d[8:])
+            if (bits0 & 0x0F) == 1:
+                return ('vlen_str',), 8 + used
+            raise H5Error('variable-length sequences are not supported')
+        raise H5Error(f'datatype class {cls} (version {ver}) is not supported')
+
+    def _fill_value(self, d):
+        ver = d[0]
+        if ver in (1, 2):
+            defined = d[3] if ver == 2 else 1
+            if not defined:
+                return None
+            n = self._uint(d, 4, 4)
+            return bytes(d[8:8 + n]) if n else None
+        if ver == 3:
+            if not d[1] & 0x20:
+                return None
+            n = self._uint(d, 2, 4)
+            return bytes(d[6:6 + n]) if n else None
+        return None
+
+    def _layout(self, d):
+        ver = d[0]
+        if ver == 3 or ver == 4:
+            cls = d[1]
+            if cls == 0:
+                n = self._uint(d, 2, 2)
+                return ('compact', bytes(d[4:4 + n]))
+            if cls == 1:
+                return ('contiguous', self._uint(d, 2, 8), self._uint(d, 10, 8))
+            if cls == 2 and ver == 3:
+                nd = d[2]
+                addr = self._uint(d, 3, 8)
+                dims = [self._uint(d, 11 + 4 * i, 4) for i in range(nd)]
+                return ('chunked', addr, dims[:-1])
+            if cls == 2 and ver == 4:
+                flags, nd, enc = d[2], d[3], d[4]
+                dims = [self._uint(d, 5 + enc * i, enc) for i in range(nd)]
+                p = 5 + enc * nd
+                index = d[p]
+                p += 1
+                if index == 1:                                  # one chunk holds the whole dataset
+                    fsize, mask = None, 0
+                    if flags & 2:
+                        fsize, mask = self._uint(d, p, 8), self._uint(d, p + 8, 4)
+                        p += 12
+                    return ('single_chunk', self._uint(d, p, 8), dims[:-1], fsize, mask)
+                raise H5Error(f'chunk index type {index} of data layout version 4 is not supported')
+        if ver in (1, 2):
+            nd, cls = d[1], d[2]
+            p = 8
+            if cls == 0:
+                n = self._uint(d, p + 4 * nd, 4)
+                return ('compact', bytes(d[p + 4 * nd + 4:p + 4 * nd + 4 + n]))
+            addr = self._uint(d, p, 8)
+            dims = [self._uint(d, p + 8 + 4 * i, 4) for i in range(nd)]
+            if cls == 1:
+                return ('contiguous', addr, 0)
+            return ('chunked', addr, dims[:-1])
+        raise H5Error(f'data layout version {ver}')
+
+    def _filters(self, d):
+        ver, n = d[0], d[1]
+        p = 8 if ver == 1 else 2
+        out = []
+        for _ in range(n):
+            fid = self._uint(d, p, 2)
+            p += 2
+            nlen = 0
+            if ver == 1 or fid >= 256:
+                nlen = self._uint(d, p, 2)
+                p += 2
+            p += 2                                              # flags
+            ncd = self._uint(d, p, 2)
+            p += 2
+            if ver == 1:
+                nlen = (nlen + 7) // 8 * 8
+            p += nlen
+            cdata = [self._uint(d, p + 4 * i, 4) for i in range(ncd)]
+            p += 4 * ncd
+            if ver == 1 and ncd % 2:
+                p += 4
+            out.append((fid, cdata))
+        return out
+
+    def _chunk_btree(self, addr, rank):
+        """(offsets, nbytes, filter mask, address) of every chunk under a version-1 chunk B-tree node"""
+        hd = self._read(addr, 24)
+        if hd[:4] != b'TREE' or hd[4] != 1:
+            raise H5Error('bad chunk B-tree node')
+        level, n = hd[5], self._uint(hd, 6, 2)
+        ksize = 8 + 8 * (rank + 1)
+        body = self._read(addr + 24, n * (ksize + 8) + ksize)
+        out = []
+        for i in range(n):
+            k = i * (ksize + 8)
+            nbytes, mask = self._uint(body, k, 4), self._uint(body, k + 4, 4)
+            offs = tuple(self._uint(body, k + 8 + 8 * j, 8) for j in range(rank))
+            child = self._uint(body, k + ksize, 8)
+            if level > 0:
+                out += self._chunk_btree(child, rank)
+            else:
+                out.append((offs, nbytes, mask, child))
+        return out
+
+    def _attribute(self, d):
+        ver = d[0]
+        nsz, tsz, ssz = self._uint(d, 2, 2), self._uint(d, 4, 2), self._uint(d, 6, 2)
+        p = 8 + (1 if ver == 3 else 0)
+        pad = (lambda x: (x + 7) // 8 * 8) if ver == 1 else (lambda x: x)
+        name = bytes(d[p:p + nsz]).split(b'\0', 1)[0].decode('utf-8', 'replace')
+        p += pad(nsz)
+        dtype, _ = self._datatype(d[p:p + tsz])
+        p += pad(tsz)
+        shape, _ = self._dataspace(d[p:p + ssz]) if ssz else ((), 0)
+        p += pad(ssz)
+        n = int(numpy.prod(shape, dtype=numpy.int64)) if shape else 1
+        if shape is None:
+            return name, None
+        if isinstance(dtype, numpy.dtype):
+            a = numpy.frombuffer(bytes(d[p:p + n * dtype.itemsize]), dtype, n).astype(dtype.newbyteorder('='))
+            return name, (a[0] if shape == () else a.reshape(shape))
+        if dtype[0] == 'str':
+            vals = [bytes(d[p + i * dtype[1]:p + (i + 1) * dtype[1]]).split(b'\0', 1)[0].decode('utf-8', 'replace')
+                    for i in range(n)]
+            return name, (vals[0] if n == 1 else vals)
+        vals = []
+        for i in range(n):                                       # variable length strings live in a global heap
+            q = p + 16 * i
+            length, gaddr, idx = self._uint(d, q, 4), self._uint(d, q + 4, 8), self._uint(d, q + 12, 4)
+            vals.append(self._global_heap_object(gaddr, idx)[:length].decode('utf-8', 'replace'))
+        return name, (vals[0] if n == 1 else vals)
+
+    def _global_heap_object(self, addr, idx):
+        if addr not in self._gcol:
+            hd = self._read(addr, 16)
+            if hd[:4] != b'GCOL':
+                raise H5Error('bad global heap collection')
+            size = self._uint(hd, 8, 8)
+            buf = self._read(addr, size)
+            objs, p = {}, 16
+            while p + 16 <= size:
+                i, n = self._uint(buf, p, 2), self._uint(buf, p + 8, 8)
+                if i == 0:
+                    break
+                objs[i] = buf[p + 16:p + 16 + n]
+                p += 16 + (n + 7) // 8 * 8
+            self._gcol[addr] = objs
+        try:
+            return self._gcol[addr][idx]
+        except KeyError:
+            raise H5Error('missing global heap object')

@@ -2,8 +2,9 @@
 
 The reference reads with xarray (field.py:22-35, horizgrid.py:12-15) and writes with netCDF4
 (datagen.py:168-208).  Neither is installed in this image, so this module uses netCDF4 when it is
-importable and falls back to ``scipy.io.netcdf_file`` (classic / 64-bit-offset NetCDF-3 only; a
-NetCDF-4/HDF5 file then raises a clear error).  Missing values (``_FillValue`` / ``missing_value``)
+importable and falls back to ``scipy.io.netcdf_file`` for classic / 64-bit-offset NetCDF-3 files and to the
+package's own minimal HDF5 reader (``h5lite``) for NetCDF-4 files in the classic data model -- the format of the
+reference's data/sa/T.nc and of real NEMO output.  Missing values (``_FillValue`` / ``missing_value``)
 are decoded to NaN like xarray's default ``mask_and_scale`` does, so ``fillna(0)`` semantics
 (field.py:157) carry over.
 """
@@ -59,6 +60,29 @@ class Variable(object):
         return a
 
 
+class _H5Data(object):
+    """array-like over one h5lite dataset (shape, dtype, indexing): a numpy.memmap of the file for contiguous
+    storage -- a time slice of uo/vo touches only its own bytes --, the decoded array (cached) otherwise"""
+
+    def __init__(self, path, h5file, ds):
+        self._ds, self._a = ds, None
+        self.shape, self.dtype = ds.shape, ds.dtype
+        lay = ds._layout
+        if lay[0] == 'contiguous' and lay[1] != 0xFFFFFFFFFFFFFFFF and all(n > 0 for n in ds.shape) and ds.shape:
+            self._a = numpy.memmap(path, dtype=ds.dtype, mode='r', offset=h5file._base + lay[1], shape=ds.shape)
+
+    def _array(self):
+        if self._a is None:
+            self._a = self._ds.read()
+        return self._a
+
+    def __getitem__(self, idx):
+        return self._array()[idx]
+
+    def __len__(self):
+        return self.shape[0] if self.shape else 0
+
+
 class Dataset(object):
     """read-only view: ds['uo'] -> Variable; ds.attrs; ds.close()"""
 
@@ -81,10 +105,12 @@ class Dataset(object):
             self.attrs = {k: h.getncattr(k) for k in h.ncattrs()}
             return
         with open(path, 'rb') as f:
-            magic = f.read(4)
+            magic = f.read(8)
+        if magic == b'\x89HDF\r\n\x1a\n':
+            self._open_hdf5(path)
+            return
         if magic[:3] != b'CDF':
-            raise RuntimeError(f'{path}: not a classic NetCDF-3 file (magic {magic!r}); reading NetCDF-4/HDF5 files '
-                               'needs the netCDF4 package, which is not installed')
+            raise RuntimeError(f'{path}: neither a classic NetCDF-3 nor a NetCDF-4/HDF5 file (magic {magic[:4]!r})')
         from scipy.io import netcdf_file
         h = netcdf_file(path, 'r', mmap=True, maskandscale=False)
         self._h = h
@@ -92,6 +118,35 @@ class Dataset(object):
             attrs = {k: (v.decode() if isinstance(v, bytes) else v) for k, v in var._attributes.items()}
             self.variables[name] = Variable(name, var.data, var.dimensions, attrs)
         self.attrs = {k: (v.decode() if isinstance(v, bytes) else v) for k, v in h._attributes.items()}
+
+    def _open_hdf5(self, path):
+        """NetCDF-4 (HDF5) through h5lite: contiguous variables are memory-mapped in place, chunked ones are decoded
+        on first access; dimension names come from the dimension scales (_Netcdf4Dimid / _Netcdf4Coordinates)"""
+        from . import h5lite
+        h = h5lite.File(path)
+        self._h = h
+        hidden = ('CLASS', 'NAME', 'DIMENSION_LIST', 'REFERENCE_LIST', '_Netcdf4Dimid', '_Netcdf4Coordinates',
+                  '_NCProperties')
+        dim_by_id, dim_by_size = {}, {}
+        for name, ds in h.datasets.items():
+            if ds.attrs.get('CLASS') == 'DIMENSION_SCALE' and len(ds.shape) == 1:
+                if '_Netcdf4Dimid' in ds.attrs:
+                    dim_by_id[int(ds.attrs['_Netcdf4Dimid'])] = name
+                dim_by_size.setdefault(ds.shape[0], name)
+        for name, ds in h.datasets.items():
+            note = ds.attrs.get('NAME')
+            if isinstance(note, str) and note.startswith('This is a netCDF dimension but not a netCDF variable'):
+                continue
+            coords = ds.attrs.get('_Netcdf4Coordinates')
+            if coords is not None and len(numpy.atleast_1d(coords)) == len(ds.shape):
+                dims = [dim_by_id.get(int(c), f'dim{i}') for i, c in enumerate(numpy.atleast_1d(coords))]
+            elif len(ds.shape) == 1 and ds.attrs.get('CLASS') == 'DIMENSION_SCALE':
+                dims = [name]
+            else:
+                dims = [dim_by_size.get(n, f'dim{i}') for i, n in enumerate(ds.shape)]
+            attrs = {k: v for k, v in ds.attrs.items() if k not in hidden}
+            self.variables[name] = Variable(name, _H5Data(path, h, ds), dims, attrs)
+        self.attrs = {k: v for k, v in h.attrs.items() if k not in hidden}
 
     def __getitem__(self, name):
         return self.variables[name]

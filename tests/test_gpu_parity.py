@@ -88,6 +88,46 @@ def test_k1_random_transects_bit_exact(gpu, oracle, delta):
     assert n > 1000
 
 
+def test_k1_real_nemo_grid_bit_exact(gpu, oracle):
+    """the reference's real NEMO T grid (data/sa/T.nc, a 100 x 100 ORCA025 window, committed as
+    tests/golden/sa_T_grid.npz) with the reference's transect data/sa/S3_sa.txt, transects along its grid lines and
+    random ones: lists bit for bit against the oracle; a nodal stream function integrates to psi(B) - psi(A)"""
+    import os
+    import torch
+    from conftest import GOLDEN
+    g = numpy.load(os.path.join(GOLDEN, 'sa_T_grid.npz'))
+    lon, lat = g['bounds_lon'].astype(numpy.float64), g['bounds_lat'].astype(numpy.float64)
+    P = numpy.zeros((100, 100, 4, 3))
+    P[..., 0], P[..., 1] = lon, lat
+    P = P.reshape(-1, 4, 3)
+    rng = numpy.random.default_rng(31)
+    transects = [tr([(16., -40.4), (28., -34.5), (31., -28.5), (36., -30.5)])]                 # data/sa/S3_sa.txt:5-8
+    transects += random_transects(rng, 12, lon_range=(13., 37.), lat_range=(-41., -21.5))
+    transects += [tr([(lon[10, 3, 0], lat[10, 3, 0]), (lon[10, 90, 0], lat[10, 90, 0])]),        # along a grid line
+                  tr([(lon[5, 40, 0], lat[5, 40, 0]), (lon[95, 40, 0], lat[95, 40, 0])]),
+                  tr([(5., -30.), (45., -30.)])]                                                # enters and leaves the window
+    nodes = []
+    for _ in range(6):
+        ja, ia, jb, ib = (int(v) for v in rng.integers(5, 95, 4))
+        a, b = (lon[ja, ia, 0], lat[ja, ia, 0]), (lon[jb, ib, 0], lat[jb, ib, 0])
+        transects.append(tr([a, (float(rng.uniform(15., 35.)), float(rng.uniform(-39., -23.))), b]))
+        nodes.append((a, b))
+    _, p = _build(gpu, P, 100, 100)
+    p.computeWeights(transects)
+    n = _check_lists(oracle, p, oracle.Grid(P), transects)
+    assert n > 1500
+
+    def psi(x, y):
+        return numpy.sin(numpy.radians(3 * x)) * (y + 45.) + 0.01 * x * y
+    se, ne, nw = psi(lon[..., 1], lat[..., 1]), psi(lon[..., 2], lat[..., 2]), psi(lon[..., 3], lat[..., 3])
+    # compact edge fluxes [eU | eV] (field.py:195-196: east edge, north edge) of the nodal stream function
+    ef = torch.from_numpy(numpy.concatenate([(ne - se).reshape(-1), (ne - nw).reshape(-1)])[None]).cuda()
+    series = p.integrate(ef).cpu().numpy()[0]
+    for k, (a, b) in enumerate(nodes):
+        exact = psi(*b) - psi(*a)
+        assert abs(series[len(transects) - 6 + k] - exact) <= 1e-10 * max(1.0, abs(exact))
+
+
 def test_k1_record_list_and_fallback_agree(gpu, oracle):
     """the count pass records its hits so that the fill pass is a scatter; when the record list (sized from the
     previous call on the handle) is too small the fill pass traverses again -- same lists either way"""

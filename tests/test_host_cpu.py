@@ -187,6 +187,91 @@ def test_datagen_mesh_mask(tmp_path):
     assert not os.path.exists(prefix + 'nmesh_mask.nc')
 
 
+def test_hdf5_reader_on_the_reference_grid_file():
+    """nemoflux's real-data files are NetCDF-4 (HDF5); the reference ships one, data/sa/T.nc (README.md:118ff).  The
+    package's own reader (h5lite via ncio: v2 object headers, dense links in a fractal heap, contiguous float32
+    data, dense attributes) must give the arrays committed as tests/golden/sa_T_grid.npz, and those must be a
+    sane NEMO T grid: vertices SW, SE, NE, NW, neighbours sharing their nodes, S3_sa.txt inside"""
+    from nemoflux_b200 import ncio
+    g = numpy.load(os.path.join(GOLDEN, 'sa_T_grid.npz'))
+    lon, lat, zb = g['bounds_lon'], g['bounds_lat'], g['deptht_bounds']
+    assert lon.shape == lat.shape == (100, 100, 4) and zb.shape == (75, 2) and lon.dtype == numpy.float32
+    assert (lon[..., 1] > lon[..., 0]).all() and (lon[..., 2] == lon[..., 1]).all() and (lon[..., 3] == lon[..., 0]).all()
+    assert (lat[..., 3] > lat[..., 0]).all() and (lat[..., 2] > lat[..., 1]).all()
+    assert numpy.array_equal(lon[:, 1:, 0], lon[:, :-1, 1]) and numpy.array_equal(lat[1:, :, 0], lat[:-1, :, 3])
+    assert (zb[1:, 0] == zb[:-1, 1]).all() and zb[0, 0] == 0.0 and 5000. < zb[-1, 1] < 6500.     # 75 NEMO levels
+    for x, y in ((16., -40.4), (28., -34.5), (31., -28.5), (36., -30.5)):                       # data/sa/S3_sa.txt:5-8
+        assert lon.min() < x < lon.max() and lat.min() < y < lat.max()
+    path = '/root/reference/data/sa/T.nc'
+    if not os.path.exists(path):
+        pytest.skip('the reference tree is not mounted here')
+    with ncio.open_dataset(path) as nc:
+        assert set(nc.variables) == {'bounds_lon', 'bounds_lat', 'deptht', 'deptht_bounds'}
+        assert nc['bounds_lon'].dimensions == ('y', 'x', 'nvertex') and nc['deptht_bounds'].dimensions == ('deptht', 'axis_nbounds')
+        assert nc['deptht'].standard_name == 'depth' and nc['deptht'].units == 'm' and nc['deptht'].bounds == 'deptht_bounds'
+        for name in ('bounds_lon', 'bounds_lat', 'deptht_bounds', 'deptht'):
+            assert numpy.array_equal(nc[name][:], g[name]), name
+        assert numpy.array_equal(nc['bounds_lat'][3, 5:7], g['bounds_lat'][3, 5:7])             # partial reads (memmap)
+
+
+def test_hdf5_chunked_deflate_shuffle_decoding():
+    """the chunked layout of h5lite on a hand-built version-1 chunk B-tree (two levels, edge chunks hanging over the
+    dataset, a missing chunk = fill value, deflate + shuffle + fletcher32 filters, one chunk with deflate skipped)"""
+    import struct
+    import zlib
+    from nemoflux_b200 import h5lite
+    rng = numpy.random.default_rng(1)
+    shape, cdims = (5, 7), (2, 4)
+    dtype = numpy.dtype('<f4')
+    data = rng.standard_normal(shape).astype(dtype)
+    filters = [(2, [4]), (1, [4]), (3, [])]                    # shuffle, deflate, fletcher32 (order of application)
+    buf = bytearray(b'\0' * 64)
+
+    def put(b):
+        addr = len(buf)
+        buf.extend(b)
+        buf.extend(b'\0' * (-len(buf) % 8))
+        return addr
+
+    def encode(chunk, skip_deflate):
+        raw = chunk.tobytes()
+        raw = numpy.frombuffer(raw, numpy.uint8).reshape(-1, 4).T.tobytes()        # shuffle
+        if not skip_deflate:
+            raw = zlib.compress(raw, 4)
+        return raw + b'ABCD'                                                       # fletcher32 checksum (not verified)
+
+    entries = []
+    for j0 in range(0, shape[0], cdims[0]):
+        for i0 in range(0, shape[1], cdims[1]):
+            if (j0, i0) == (2, 4):
+                continue                                        # never written
+            chunk = numpy.zeros(cdims, dtype)
+            sub = data[j0:j0 + cdims[0], i0:i0 + cdims[1]]
+            chunk[:sub.shape[0], :sub.shape[1]] = sub
+            skip = (j0, i0) == (0, 4)
+            raw = encode(chunk, skip)
+            entries.append(((j0, i0), len(raw), 2 if skip else 0, put(raw)))
+
+    def node(level, items):                                     # items: (offsets, nbytes, mask, child address)
+        b = b'TREE' + bytes([1, level]) + struct.pack('<H', len(items)) + struct.pack('<QQ', h5lite.UNDEF, h5lite.UNDEF)
+        for offs, nbytes, mask, child in items:
+            b += struct.pack('<II', nbytes, mask) + struct.pack('<QQQ', offs[0], offs[1], 0) + struct.pack('<Q', child)
+        b += struct.pack('<II', 0, 0) + struct.pack('<QQQ', shape[0], shape[1], 0)
+        return put(b)
+
+    leaf_a, leaf_b = node(0, entries[:3]), node(0, entries[3:])
+    root = node(1, [(entries[0][0], 0, 0, leaf_a), (entries[3][0], 0, 0, leaf_b)])
+    f = h5lite.File.__new__(h5lite.File)
+    f._buf, f._base, f.path = bytes(buf), 0, '<memory>'
+    ds = h5lite.Dataset(f, 'v', shape, dtype, ('chunked', root, cdims), filters, {}, numpy.float32(-9.).tobytes())
+    got = ds.read()
+    want = data.copy()
+    want[2:4, 4:7] = -9.
+    assert numpy.array_equal(got, want)
+    with pytest.raises(h5lite.H5Error):
+        h5lite.apply_filters_reverse(b'1234', [(32015, [])], 0, 4)
+
+
 def test_transect_argument_forms(tmp_path):
     from nemoflux_b200.field import parseLonLatPoints
     from nemoflux_b200.fluxviz import parseTransects

@@ -264,3 +264,51 @@ def test_orientation_and_additivity_properties(oracle):
                 mid = (pts[0][0] + s * (pts[1][0] - pts[0][0]), pts[0][1] + s * (pts[1][1] - pts[0][1]))
                 fins, _ = integral([pts[0], mid] + pts[1:])
                 assert abs(f - fins) <= 1e-11 * l1
+
+
+def _sa_grid():
+    """the reference's real NEMO T grid (data/sa/T.nc, committed as tests/golden/sa_T_grid.npz): (ncell,4,3) points"""
+    import os
+    from conftest import GOLDEN
+    g = numpy.load(os.path.join(GOLDEN, 'sa_T_grid.npz'))
+    lon, lat = g['bounds_lon'].astype(numpy.float64), g['bounds_lat'].astype(numpy.float64)
+    pts = numpy.zeros((100, 100, 4, 3))
+    pts[..., 0], pts[..., 1] = lon, lat
+    return pts.reshape(-1, 4, 3), lon, lat
+
+
+def test_real_nemo_grid_transect(oracle):
+    """K1/K3 of the oracle on the real ORCA025 window south of Africa with the reference's own transect
+    data/sa/S3_sa.txt: every segment fully covered; with edge fluxes derived from a nodal stream function the
+    integral between two grid nodes is psi(B) - psi(A), whatever the path (fluxexact.py:36-46), with the
+    reference's sign convention (field.py:195-196: eU = +U*dy on the east edge, eV = -V*dx on the north edge)"""
+    P, lon, lat = _sa_grid()
+    og = oracle.Grid(P)
+    s3 = tr([(16., -40.4), (28., -34.5), (31., -28.5), (36., -30.5)])             # data/sa/S3_sa.txt:5-8 as (lon, lat)
+    p = oracle.PolylineIntegral(og)
+    p.computeWeights(s3)
+    assert len(p.subsegs) > 100
+    assert numpy.abs(p.segment_totals(3) - 1.0).max() <= 1e-12
+    # nodal stream function -> C-grid edge fluxes: east edge (SE->NE) carries psi(NE)-psi(SE), north edge (NW->NE)
+    # carries -(psi(NE)-psi(NW)) before the minus sign of field.py:196, i.e. iV[:,2] = psi(NE)-psi(NW)
+    def psi(x, y):
+        return numpy.sin(numpy.radians(3 * x)) * (y + 45.) + 0.01 * x * y
+    se, ne, nw = psi(lon[..., 1], lat[..., 1]), psi(lon[..., 2], lat[..., 2]), psi(lon[..., 3], lat[..., 3])
+    iV = numpy.zeros((100, 100, 4))
+    iV[..., 1] = ne - se
+    iV[..., 2] = ne - nw
+    iV[1:, :, 0] = iV[:-1, :, 2]
+    iV[:, 1:, 3] = iV[:, :-1, 1]
+    iV[0, :, 0] = psi(lon[0, :, 1], lat[0, :, 1]) - psi(lon[0, :, 0], lat[0, :, 0])
+    iV[:, 0, 3] = psi(lon[:, 0, 3], lat[:, 0, 3]) - psi(lon[:, 0, 0], lat[:, 0, 0])
+    rng = numpy.random.default_rng(4)
+    for _ in range(6):
+        ja, ia, jb, ib = (int(v) for v in rng.integers(5, 95, 4))
+        a = (lon[ja, ia, 0], lat[ja, ia, 0])                    # SW nodes of two cells
+        b = (lon[jb, ib, 0], lat[jb, ib, 0])
+        mid = (float(rng.uniform(15., 35.)), float(rng.uniform(-39., -23.)))
+        q = oracle.PolylineIntegral(og)
+        q.computeWeights(tr([a, mid, b]))
+        exact = psi(*b) - psi(*a)
+        got = q.getIntegral(iV.reshape(-1, 4))
+        assert abs(got - exact) <= 1e-10 * max(1.0, abs(exact)), (got, exact)

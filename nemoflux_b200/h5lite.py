@@ -35,6 +35,7 @@ class Dataset(object):
     def __init__(self, f, name, shape, dtype, layout, filters, attrs, fill):
         self._f, self.name, self.shape, self.dtype = f, name, tuple(shape), dtype
         self._layout, self._filters, self.attrs, self.fill = layout, filters, attrs, fill
+        self._chunks = None                                     # chunk index, read on first use
 
     def read(self):
         """the whole array, in the file's byte order"""
@@ -62,29 +63,38 @@ class Dataset(object):
         raise H5Error(f'{self.name}: unsupported data layout {kind}')
 
     def _read_chunked(self):
+        return self.read_region([0] * len(self.shape), list(self.shape))
+
+    def read_region(self, starts, stops):
+        """the block [starts, stops) of a chunked dataset: only the chunks that overlap it are read and decoded (a
+        time slice of a NEMO uo(t, z, y, x) variable touches its own chunks, not the whole file)"""
+        if self._layout[0] != 'chunked':
+            return self.read()[tuple(slice(a, b) for a, b in zip(starts, stops))]
         addr, cdims = self._layout[1], self._layout[2]          # chunk dims in elements (without the element size)
-        out = numpy.zeros(self.shape, self.dtype)
+        rank = len(self.shape)
+        out = numpy.zeros([max(0, b - a) for a, b in zip(starts, stops)], self.dtype)
         if self.fill is not None:
             out[...] = numpy.frombuffer(self.fill, self.dtype, 1)[0]
-        if addr == UNDEF:
+        if addr == UNDEF or out.size == 0:
             return out
-        rank = len(self.shape)
+        if self._chunks is None:
+            self._chunks = self._f._chunk_btree(addr, rank)
         csize = int(numpy.prod(cdims)) * self.dtype.itemsize
-        for offsets, nbytes, mask, caddr in self._f._chunk_btree(addr, rank):
-            raw = self._f._read(caddr, nbytes)
-            raw = apply_filters_reverse(raw, self._filters, mask, self.dtype.itemsize)
-            if len(raw) < csize:
-                raise H5Error(f'{self.name}: a chunk holds {len(raw)} bytes, expected {csize}')
-            chunk = numpy.frombuffer(raw, self.dtype, csize // self.dtype.itemsize).reshape(cdims)
+        for offsets, nbytes, mask, caddr in self._chunks:
             sel_out, sel_in = [], []
-            for d in range(rank):                               # edge chunks hang over the dataset
-                lo = offsets[d]
-                hi = min(lo + cdims[d], self.shape[d])
+            for d in range(rank):                               # overlap of the chunk with the block (edge chunks
+                lo = max(offsets[d], starts[d])                 # hang over the dataset)
+                hi = min(offsets[d] + cdims[d], stops[d], self.shape[d])
                 if hi <= lo:
                     break
-                sel_out.append(slice(lo, hi))
-                sel_in.append(slice(0, hi - lo))
+                sel_out.append(slice(lo - starts[d], hi - starts[d]))
+                sel_in.append(slice(lo - offsets[d], hi - offsets[d]))
             else:
+                raw = self._f._read(caddr, nbytes)
+                raw = apply_filters_reverse(raw, self._filters, mask, self.dtype.itemsize)
+                if len(raw) < csize:
+                    raise H5Error(f'{self.name}: a chunk holds {len(raw)} bytes, expected {csize}')
+                chunk = numpy.frombuffer(raw, self.dtype, csize // self.dtype.itemsize).reshape(cdims)
                 out[tuple(sel_out)] = chunk[tuple(sel_in)]
         return out
 

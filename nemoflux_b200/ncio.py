@@ -77,7 +77,39 @@ class _H5Data(object):
         return self._a
 
     def __getitem__(self, idx):
+        if self._a is None and self._ds._layout[0] == 'chunked':
+            block = self._block(idx)
+            if block is not None:
+                return block
         return self._array()[idx]
+
+    def _block(self, idx):
+        """ints and unit-stride slices on a chunked variable: decode only the chunks under the block"""
+        if idx is Ellipsis:
+            return None                                         # the whole variable: decode once and keep it
+        idx = idx if isinstance(idx, tuple) else (idx,)
+        if any(i is Ellipsis for i in idx) or len(idx) > len(self.shape):
+            return None
+        starts, stops, squeeze = [], [], []
+        for d, n in enumerate(self.shape):
+            i = idx[d] if d < len(idx) else slice(None)
+            if isinstance(i, (int, numpy.integer)):
+                i = int(i) + (n if i < 0 else 0)
+                if not 0 <= i < n:
+                    raise IndexError(f'index {idx[d]} is out of bounds for axis {d} with size {n}')
+                starts.append(i)
+                stops.append(i + 1)
+                squeeze.append(d)
+            elif isinstance(i, slice):
+                a, b, step = i.indices(n)
+                if step != 1:
+                    return None
+                starts.append(a)
+                stops.append(max(a, b))
+            else:
+                return None
+        out = self._ds.read_region(starts, stops)
+        return out.reshape([m for d, m in enumerate(out.shape) if d not in squeeze])
 
     def __len__(self):
         return self.shape[0] if self.shape else 0

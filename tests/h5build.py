@@ -1,0 +1,145 @@
+"""Test helper: writes a small HDF5 file in the OLDEST on-disk flavour (superblock 0, symbol-table root group with a
+local heap and a version-1 B-tree, version-1 object headers, data layout message version 3), by hand from the HDF5
+file format specification -- the counterpart of the reference's data/sa/T.nc (superblock 0 with version-2 object
+headers and dense links), so that both generations of structures in nemoflux_b200/h5lite.py see a file.
+Datasets are float arrays, contiguous or chunked (optionally shuffle + deflate), with numeric / string attributes."""
+import struct
+import zlib
+
+import numpy
+
+UNDEF = 0xFFFFFFFFFFFFFFFF
+
+
+def _pad8(b):
+    return b + b'\0' * (-len(b) % 8)
+
+
+def _msg(mtype, data):
+    data = _pad8(data)
+    return struct.pack('<HHBBBB', mtype, len(data), 0, 0, 0, 0) + data
+
+
+def _dataspace(shape):
+    return struct.pack('<BBBB4x', 1, len(shape), 0, 0) + b''.join(struct.pack('<Q', n) for n in shape)
+
+
+def _datatype(dt):
+    dt = numpy.dtype(dt)
+    be = 1 if dt.byteorder == '>' else 0
+    if dt.kind == 'f':
+        if dt.itemsize == 4:
+            return struct.pack('<BBBBI', 0x11, 0x20 | be, 31, 0, 4) + struct.pack('<HHBBBBI', 0, 32, 23, 8, 0, 23, 127)
+        return struct.pack('<BBBBI', 0x11, 0x20 | be, 63, 0, 8) + struct.pack('<HHBBBBI', 0, 64, 52, 11, 0, 52, 1023)
+    if dt.kind in 'iu':
+        return struct.pack('<BBBBI', 0x10, be | (0x08 if dt.kind == 'i' else 0), 0, 0, dt.itemsize) + \
+            struct.pack('<HH', 0, 8 * dt.itemsize)
+    raise ValueError(dt)
+
+
+def _attribute(name, value):
+    if isinstance(value, str):
+        raw = value.encode() + b'\0'
+        dtype = struct.pack('<BBBBI', 0x13, 0, 0, 0, len(raw))
+        space = _dataspace(())
+    else:
+        a = numpy.atleast_1d(numpy.asarray(value))
+        raw = a.tobytes()
+        dtype = _datatype(a.dtype)
+        space = _dataspace(a.shape if numpy.ndim(value) else ())
+    nm = name.encode() + b'\0'
+    return struct.pack('<BBHHH', 1, 0, len(nm), len(dtype), len(space)) + _pad8(nm) + _pad8(dtype) + _pad8(space) + raw
+
+
+def write(path, variables):
+    """variables: {name: dict(data=array, chunks=None or tuple, deflate=False, shuffle=False, attrs={})}"""
+    buf = bytearray(b'\0' * 96)                                  # superblock, filled in at the end
+
+    def put(b):
+        addr = len(buf)
+        buf.extend(_pad8(bytes(b)))
+        return addr
+
+    def chunk_tree(data, cdims, deflate, shuffle):
+        rank = data.ndim
+        items = []
+        grid = [range(0, n, c) for n, c in zip(data.shape, cdims)]
+        for offs in numpy.stack(numpy.meshgrid(*grid, indexing='ij'), -1).reshape(-1, rank):
+            chunk = numpy.zeros(cdims, data.dtype)
+            sub = data[tuple(slice(o, o + c) for o, c in zip(offs, cdims))]
+            chunk[tuple(slice(0, m) for m in sub.shape)] = sub
+            raw = chunk.tobytes()
+            if shuffle:
+                raw = numpy.frombuffer(raw, numpy.uint8).reshape(-1, data.dtype.itemsize).T.tobytes()
+            if deflate:
+                raw = zlib.compress(raw, 5)
+            items.append((tuple(int(o) for o in offs), len(raw), put(raw)))
+
+        def node(level, entries, last_key):
+            b = b'TREE' + bytes([1, level]) + struct.pack('<H', len(entries)) + struct.pack('<QQ', UNDEF, UNDEF)
+            for offs, nbytes, child in entries:
+                b += struct.pack('<II', nbytes, 0) + b''.join(struct.pack('<Q', o) for o in offs) + struct.pack('<Q', 0)
+                b += struct.pack('<Q', child)
+            b += struct.pack('<II', 0, 0) + b''.join(struct.pack('<Q', o) for o in last_key) + struct.pack('<Q', 0)
+            return put(b)
+
+        end = tuple(int(n) for n in data.shape)
+        if len(items) <= 4:
+            return node(0, items, end)
+        leaves = []
+        for i in range(0, len(items), 4):                        # two levels: leaves of up to 4 chunks
+            part = items[i:i + 4]
+            nxt = items[i + 4][0] if i + 4 < len(items) else end
+            leaves.append((part[0][0], 0, node(0, part, nxt)))
+        return node(1, leaves, end)
+
+    heap_data = bytearray(b'\0' * 8)
+    symbols = []
+    for name, spec in sorted(variables.items()):
+        data = numpy.ascontiguousarray(spec['data'])
+        msgs = _msg(0x01, _dataspace(data.shape)) + _msg(0x03, _datatype(data.dtype))
+        msgs += _msg(0x05, struct.pack('<BBBB', 2, 2, 0, 0))     # fill value message v2, undefined
+        chunks = spec.get('chunks')
+        if chunks:
+            filt = []
+            if spec.get('shuffle'):
+                filt.append((2, [data.dtype.itemsize]))
+            if spec.get('deflate'):
+                filt.append((1, [5]))
+            if filt:
+                body = struct.pack('<BB6x', 1, len(filt))
+                for fid, cd in filt:
+                    body += struct.pack('<HHHH', fid, 0, 1, len(cd)) + b''.join(struct.pack('<I', c) for c in cd)
+                    if len(cd) % 2:
+                        body += b'\0' * 4
+                msgs += _msg(0x0B, body)
+            tree = chunk_tree(data, tuple(chunks), spec.get('deflate', False), spec.get('shuffle', False))
+            lay = struct.pack('<BBB', 3, 2, data.ndim + 1) + struct.pack('<Q', tree)
+            lay += b''.join(struct.pack('<I', c) for c in chunks) + struct.pack('<I', data.dtype.itemsize)
+        else:
+            addr = put(data.tobytes())
+            lay = struct.pack('<BB', 3, 1) + struct.pack('<QQ', addr, data.nbytes)
+        msgs += _msg(0x08, lay)
+        for k, v in spec.get('attrs', {}).items():
+            msgs += _msg(0x0C, _attribute(k, v))
+        nmsg = 4 + (1 if chunks and (spec.get('shuffle') or spec.get('deflate')) else 0) + len(spec.get('attrs', {}))
+        oh = put(struct.pack('<BBHII4x', 1, 0, nmsg, 1, len(msgs)) + msgs)
+        noff = len(heap_data)
+        heap_data.extend(_pad8(name.encode() + b'\0'))
+        symbols.append((noff, oh))
+    heap_seg = put(heap_data)
+    heap = put(b'HEAP' + struct.pack('<B3x', 0) + struct.pack('<QQQ', len(heap_data), UNDEF, heap_seg))
+    snod = b'SNOD' + struct.pack('<BBH', 1, 0, len(symbols))
+    for noff, oh in symbols:
+        snod += struct.pack('<QQII16x', noff, oh, 0, 0)
+    snod_addr = put(snod)
+    btree = put(b'TREE' + bytes([0, 0]) + struct.pack('<H', 1) + struct.pack('<QQ', UNDEF, UNDEF) +
+                struct.pack('<QQQ', 0, snod_addr, symbols[-1][0]))
+    root_msgs = _msg(0x11, struct.pack('<QQ', btree, heap))
+    root = put(struct.pack('<BBHII4x', 1, 0, 1, 1, len(root_msgs)) + root_msgs)
+    sb = b'\x89HDF\r\n\x1a\n' + bytes([0, 0, 0, 0, 0, 8, 8, 0]) + struct.pack('<HHI', 4, 16, 0)
+    sb += struct.pack('<QQQQ', 0, UNDEF, len(buf), UNDEF)
+    sb += struct.pack('<QQII', 0, root, 1, 0) + struct.pack('<QQ', btree, heap)
+    buf[:len(sb)] = sb
+    with open(path, 'wb') as f:
+        f.write(bytes(buf))

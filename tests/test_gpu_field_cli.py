@@ -241,3 +241,43 @@ def test_field_with_mesh_file_scale_factors(gpu, oracle, tmp_path, capsys):
     assert numpy.array_equal(out, s32)
     with pytest.raises(RuntimeError):
         Field(T, U, V, lines, verbose=False, meshFile=T)          # no e3u_0/e3v_0 in there
+
+
+def test_field_reads_netcdf4_velocity_files(gpu, oracle, tmp_path):
+    """real NEMO output is NetCDF-4: uo/vo chunked per time step and level slab, shuffled and deflated, float32 with
+    _FillValue over land.  Field streams such files through the package's own HDF5 reader into the same pipeline
+    (here written by tests/h5build.py) and gives the series of the identical data in classic files, bit for bit"""
+    import h5build
+    from nemoflux_b200 import ncio
+    from nemoflux_b200.field import Field
+    T, U, V = _files(tmp_path, f'--streamFunction={SF_C2}', '--nx=48', '--ny=24', '--nz=6', '--nt=5', '--deltaDeg=20,30')
+    d = oracle.DataGen(nx=48, ny=24, nz=6, nt=5, deltaDeg=(20., 30.))
+    u, v = d.uv(SF_C2)
+    u32, v32 = u.astype(numpy.float32), v.astype(numpy.float32)
+    land = numpy.zeros((6, 24, 48), bool)
+    land[:, 8:12, 10:20] = True
+    land[4:] |= numpy.random.default_rng(3).random((24, 48)) < 0.3
+    u32[:, land] = numpy.float32(1.e20)
+    v32[:, land] = numpy.float32(1.e20)
+    lines = [tr([(-150, -50), (-20, 35), (60, -40), (170, 60)]), tr([(-100, -70), (100, -70), (0, 70)])]
+    for fname, vname, a in ((U, 'uo', u32), (V, 'vo', v32)):               # classic NetCDF-3 first
+        w = ncio.Writer(fname)
+        for name, n in (('t', 5), ('z', 6), ('y', 24), ('x', 48)):
+            w.createDimension(name, n)
+        w.createVariable(vname, 'float32', ('t', 'z', 'y', 'x'), fill_value=1.e20, data=a)
+        w.close()
+    s3 = Field(T, U, V, lines, verbose=False).fluxSeries(chunk_steps=2)
+    U4, V4 = str(tmp_path / 'U4.nc'), str(tmp_path / 'V4.nc')
+    for fname, vname, a in ((U4, 'uo', u32), (V4, 'vo', v32)):
+        h5build.write(fname, {vname: dict(data=a, chunks=(1, 2, 24, 48), deflate=True, shuffle=True,
+                                          attrs={'_FillValue': numpy.float32(1.e20), 'units': 'm/s'}),
+                              'time_counter': dict(data=numpy.arange(5.), chunks=(1,))})
+    f4 = Field(T, U4, V4, lines, verbose=False)
+    s4 = f4.fluxSeries(chunk_steps=2)
+    assert numpy.array_equal(s4, s3)
+    assert numpy.abs(f4.fluxes - s4[0]).max() <= 1e-13 * numpy.abs(s4).max()
+    un, vn = u32.astype(numpy.float64), v32.astype(numpy.float64)
+    un[:, land] = numpy.nan
+    vn[:, land] = numpy.nan
+    ref = oracle.flux_series(d.points(), lines, un, vn, d.thickness())
+    assert numpy.abs(s4 - ref).max() <= 1e-12 * numpy.abs(ref).max()

@@ -268,8 +268,56 @@ def test_hdf5_chunked_deflate_shuffle_decoding():
     want = data.copy()
     want[2:4, 4:7] = -9.
     assert numpy.array_equal(got, want)
+    # partial reads decode only the chunks under the block (what a time slice of uo/vo does)
+    from nemoflux_b200 import ncio
+    lazy = ncio._H5Data('<memory>', f, h5lite.Dataset(f, 'v', shape, dtype, ('chunked', root, cdims), filters, {},
+                                                      numpy.float32(-9.).tobytes()))
+    reads = []
+    orig = f._read
+    f._read = lambda addr, n: (reads.append(addr), orig(addr, n))[1]
+    assert numpy.array_equal(lazy[1, 1:3], want[1, 1:3])
+    assert len([a for a in reads if a in {e[3] for e in entries}]) == 1          # one chunk was enough
+    assert numpy.array_equal(lazy[3:5, 2:7], want[3:5, 2:7]) and numpy.array_equal(lazy[-1], want[-1])
+    assert numpy.array_equal(lazy[4, -1], want[4, -1]) and numpy.array_equal(lazy[::2, 1], want[::2, 1])
+    assert numpy.array_equal(lazy[...], want)
+    with pytest.raises(IndexError):
+        lazy[5]
     with pytest.raises(h5lite.H5Error):
         h5lite.apply_filters_reverse(b'1234', [(32015, [])], 0, 4)
+
+
+def test_hdf5_old_style_file_roundtrip(tmp_path):
+    """a file in the oldest HDF5 flavour (symbol-table group, version-1 object headers, chunked + shuffle + deflate
+    data, version-1 attribute messages) written by tests/h5build.py: variables, attributes, partial reads"""
+    import h5build
+    from nemoflux_b200 import ncio
+    rng = numpy.random.default_rng(0)
+    uo = rng.standard_normal((3, 4, 9, 11)).astype('<f4')
+    uo[:, :, 2:4, 5:8] = numpy.float32(1.e20)
+    vo = rng.standard_normal((3, 4, 9, 11)).astype('>f8')
+    tc = numpy.arange(3, dtype='<f8') * 86400.
+    path = str(tmp_path / 'old.nc')
+    h5build.write(path, {
+        'uo': dict(data=uo, chunks=(1, 2, 9, 11), deflate=True, shuffle=True,
+                   attrs={'_FillValue': numpy.float32(1.e20), 'units': 'm/s', 'standard_name': 'sea_water_x_velocity'}),
+        'vo': dict(data=vo, attrs={'units': 'm/s'}),
+        'time_counter': dict(data=tc, chunks=(2,), attrs={'standard_name': 'time'}),
+        'many': dict(data=numpy.arange(40, dtype='<i4').reshape(20, 2), chunks=(3, 2))})      # two-level chunk tree
+    with ncio.open_dataset(path) as nc:
+        assert set(nc.variables) == {'uo', 'vo', 'time_counter', 'many'}
+        assert nc['uo'].shape == (3, 4, 9, 11) and nc['uo'].units == 'm/s' and nc['uo'].fill_value() == float(numpy.float32(1.e20))
+        assert numpy.array_equal(nc['uo'].raw(), uo) and numpy.array_equal(nc['uo'].raw((1, slice(1, 3))), uo[1, 1:3])
+        assert numpy.isnan(nc['uo'][0, 0, 2, 5]) and nc['uo'][0, 0, 0, 0] == uo[0, 0, 0, 0]
+        assert numpy.array_equal(nc['vo'].raw(), vo.astype('<f8')) and nc['vo'].raw().dtype.isnative
+        dst = numpy.zeros((2, 9, 11), numpy.float32)
+        nc['uo'].read_into(dst, (2, slice(2, 4)))
+        assert numpy.array_equal(dst, uo[2, 2:4])
+        assert numpy.array_equal(nc['time_counter'][:], tc) and nc['time_counter'].standard_name == 'time'
+        assert numpy.array_equal(nc['many'][:], numpy.arange(40).reshape(20, 2)) and numpy.array_equal(nc['many'][7:15, 1], numpy.arange(15, 31, 2))
+    with open(str(tmp_path / 'bad.nc'), 'wb') as f:
+        f.write(b'not a netcdf file at all')
+    with pytest.raises(RuntimeError):
+        ncio.open_dataset(str(tmp_path / 'bad.nc'))
 
 
 def test_transect_argument_forms(tmp_path):

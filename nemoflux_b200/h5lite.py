@@ -312,8 +312,9 @@ class File(object):
                 ent = self._read(snod + 8, n * 40)
                 for i in range(n):
                     noff, oaddr = self._uint(ent, 40 * i, 8), self._uint(ent, 40 * i + 8, 8)
-                    raw = self._read(data_addr + noff, 256)
-                    out.append((raw.split(b'\0', 1)[0].decode(), oaddr))
+                    a = self._base + data_addr + noff            # NUL-terminated name in the heap's data segment
+                    raw = bytes(self._buf[a:a + 1024])
+                    out.append((raw.split(b'\0', 1)[0].decode('utf-8', 'replace'), oaddr))
         return out
 
     def _group_btree(self, addr):

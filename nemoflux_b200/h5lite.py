@@ -10,13 +10,12 @@ contiguous and chunked (version-1 chunk B-tree; layout message versions 3 and 4 
 deflate, shuffle and fletcher32 filters; attributes in the header or in dense storage.
 
 Not supported (raises H5Error): compound/array/enum/reference datatypes, external storage, virtual datasets,
-the newer chunk indexes of layout version 4 (single chunk, implicit, fixed/extensible array, v2 B-tree), user
-filters.  Test status: validated on the reference's data/sa/T.nc (netCDF 4.7.3 / HDF5 1.10.5: v2 object headers,
-dense links, contiguous float32/float64 datasets, dense attributes); the chunked + deflate + shuffle path follows
-the specification and is exercised on hand-built chunk trees in tests/test_host_cpu.py, not on a file written by
-the HDF5 library.
+the chunk indexes of layout version 4 other than "single chunk" (implicit, fixed/extensible array, v2 B-tree),
+user filters.  Test status: validated on the reference's data/sa/T.nc (netCDF 4.7.3 / HDF5 1.10.5: v2 object headers,
+dense links, contiguous float32 datasets, attributes); the older structures (symbol-table groups, version-1 object
+headers) and the chunked + deflate + shuffle path follow the specification and are exercised on files written by
+hand from it (tests/h5build.py), not on a chunked file written by the HDF5 library.
 """
-import struct
 import zlib
 
 import numpy

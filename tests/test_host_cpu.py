@@ -423,6 +423,28 @@ print('ok', rank)
 '''
 
 
+def test_bench_reference_arm_contract():
+    """bench.py --impl reference (the CPU arm the driver times next to ours): one JSON line with the contract's keys,
+    no GPU needed; under a multi-rank launch only rank 0 prints"""
+    cmd = [sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--workload', 'tiny', '--steps', '2',
+           '--warmup', '1', '--cpu-steps', '3']
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.startswith('{')]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ('impl', 'metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better', 'scaling',
+                'vs_baseline', 'dtype', 'data', 'config', 'cpu_baseline', 'e2e'):
+        assert key in d, key
+    assert d['impl'] == 'reference' and d['value'] > 0 and d['steps'] == 2 and d['vs_baseline'] is None
+    assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['value'] == d['value'] and d['cpu_baseline']['cores'] >= 1
+    assert d['e2e'] == {'value': d['value'], 'unit': d['unit'], 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
+    assert 'workload' in d['config'] and 'model' not in d['config']
+    env = dict(os.environ, RANK='1', WORLD_SIZE='2', LOCAL_RANK='1')
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT, env=env)
+    assert out.returncode == 0 and not [ln for ln in out.stdout.splitlines() if ln.startswith('{')]
+
+
 def test_gpu_cpu_binding_is_harmless_without_nvml_affinity():
     """bind_to_gpu_cpus: no GPU / no affinity information -> nothing changes and 0 is returned"""
     from nemoflux_b200 import dist

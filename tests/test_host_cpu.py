@@ -212,6 +212,16 @@ def test_hdf5_reader_on_the_reference_grid_file():
         for name in ('bounds_lon', 'bounds_lat', 'deptht_bounds', 'deptht'):
             assert numpy.array_equal(nc[name][:], g[name]), name
         assert numpy.array_equal(nc['bounds_lat'][3, 5:7], g['bounds_lat'][3, 5:7])             # partial reads (memmap)
+    # the reference's data-preparation tool on its own file (subsetNEMO.py:6-93): NetCDF-4 in, classic out
+    import tempfile
+    from nemoflux_b200 import subsetnemo
+    with tempfile.TemporaryDirectory() as tmp:
+        subsetnemo.subset(tfile=path, outputdir=tmp, jmin=10, jmax=40, imin=20, imax=90, verbose=False)
+        with ncio.open_dataset(os.path.join(tmp, 'T.nc')) as nc:
+            assert nc['bounds_lon'].dimensions == ('y', 'x', 'nvertex') and nc['bounds_lon'].shape == (30, 70, 4)
+            assert numpy.array_equal(nc['bounds_lon'][:], g['bounds_lon'][10:40, 20:90])
+            assert numpy.array_equal(nc['bounds_lat'][:], g['bounds_lat'][10:40, 20:90])
+            assert numpy.array_equal(nc['deptht_bounds'][:], g['deptht_bounds']) and nc['deptht'].units == 'm'
 
 
 def test_hdf5_chunked_deflate_shuffle_decoding():

@@ -260,7 +260,7 @@ class File(object):
                 try:
                     name, value = self._attribute(data)
                     o['attrs'][name] = value
-                except H5Error:
+                except (H5Error, IndexError, ValueError, OverflowError):
                     pass                                        # an attribute of a type we do not decode
             elif mtype == 0x06:
                 lk = self._link(data)
@@ -281,7 +281,7 @@ class File(object):
                     try:
                         name, value = self._attribute(self._heap_object(heap, rec[:8]))
                         o['attrs'][name] = value
-                    except H5Error:
+                    except (H5Error, IndexError, ValueError, OverflowError):
                         pass
         if o['layout'] is not None and o['layout'][0] == 'chunked' and o['shape'] is not None:
             o['layout'] = ('chunked', o['layout'][1], tuple(o['layout'][2][:len(o['shape'])]))

@@ -402,7 +402,10 @@ def run_b200(args):
                 'frac': achieved / peak, 'traffic': None,
                 'peak_source': 'MEASURED_PEAKS.json hbm_gbs (of measured)' if peaks else 'fallback 6650 GB/s',
                 'algorithmic_bytes_per_launch': k2_bytes, 'k2_ms': k2_ms, 'k3_ms': k3_ms,
-                'frac_of_nominal_8TBs': achieved / 8000.0}
+                'frac_of_nominal_8TBs': achieved / 8000.0,
+                # `peak` is a COPY rate (reads + writes, 6.3-6.5 TB/s on these parts); this pass only reads.  The read-only
+                # ceiling measured with the same access pattern and arithmetic (tools/readbw.cu, profiles/r1_readbw.txt)
+                'read_only_ceiling_gbs': 7471.9, 'frac_of_read_only_ceiling': achieved / 7471.9}
     tr_path = os.path.join(ROOT, 'profiles', 'k2_traffic.json')
     if os.path.exists(tr_path):
         try:

@@ -330,6 +330,37 @@ def test_hdf5_old_style_file_roundtrip(tmp_path):
         ncio.open_dataset(str(tmp_path / 'bad.nc'))
 
 
+def test_hdf5_new_style_file_roundtrip(tmp_path):
+    """the newer HDF5 structures written by tests/h5build.write_new: superblock 2, version-2 object headers with
+    times / creation order / a continuation block, link messages, variable-length strings in a global heap, and a
+    variable whose many attributes live in dense storage (fractal heap with an indirect root block + version-2
+    B-tree) -- what real NEMO uo/vo variables with their ~10 attributes look like"""
+    import h5build
+    from nemoflux_b200 import ncio
+    rng = numpy.random.default_rng(5)
+    uo = rng.standard_normal((3, 4, 9, 11)).astype('<f4')
+    attrs = {'_FillValue': numpy.float32(1.e20), 'units': 'm/s', 'standard_name': 'sea_water_x_velocity',
+             'long_name': 'vlen:ocean current along i-axis', 'online_operation': 'average', 'interval_operation': '1 h',
+             'interval_write': '1 month', 'cell_methods': 'time: mean (interval: 1 h)', 'missing_value': numpy.float32(1.e20),
+             'coordinates': 'time_centered nav_lat nav_lon', 'valid_range': numpy.array([-10., 10.]),
+             'comment': 'x' * 300, 'comment2': 'y' * 200, 'comment3': 'z' * 180}
+    path = str(tmp_path / 'new.nc')
+    h5build.write_new(path, {
+        'uo': dict(data=uo, chunks=(1, 2, 9, 11), deflate=True, shuffle=True, attrs=attrs, dense_attrs=True),
+        'vo': dict(data=uo.astype('>f8'), attrs={'units': 'm/s', 'title': 'vlen:northward'}),
+        'time_counter': dict(data=numpy.arange(3.), attrs={'standard_name': 'time'})})
+    with ncio.open_dataset(path) as nc:
+        assert nc.attrs == {'Conventions': 'CF-1.6'} and set(nc.variables) == {'uo', 'vo', 'time_counter'}
+        got = nc['uo'].attrs
+        assert set(got) == set(attrs)
+        for k, v in attrs.items():
+            want = v[5:] if isinstance(v, str) and v.startswith('vlen:') else v
+            assert numpy.array_equal(got[k], want), k
+        assert numpy.array_equal(nc['uo'].raw(), uo) and numpy.array_equal(nc['uo'].raw((2, slice(0, 2))), uo[2, :2])
+        assert numpy.array_equal(nc['vo'].raw(), uo.astype('f8')) and nc['vo'].title == 'northward'
+        assert nc['time_counter'].standard_name == 'time' and numpy.array_equal(nc['time_counter'][:], [0., 1., 2.])
+
+
 def test_transect_argument_forms(tmp_path):
     from nemoflux_b200.field import parseLonLatPoints
     from nemoflux_b200.fluxviz import parseTransects

@@ -12,9 +12,10 @@ deflate, shuffle and fletcher32 filters; attributes in the header or in dense st
 Not supported (raises H5Error): compound/array/enum/reference datatypes, external storage, virtual datasets,
 the chunk indexes of layout version 4 other than "single chunk" (implicit, fixed/extensible array, v2 B-tree),
 user filters.  Test status: validated on the reference's data/sa/T.nc (netCDF 4.7.3 / HDF5 1.10.5: v2 object headers,
-dense links, contiguous float32 datasets, attributes); the older structures (symbol-table groups, version-1 object
-headers) and the chunked + deflate + shuffle path follow the specification and are exercised on files written by
-hand from it (tests/h5build.py), not on a chunked file written by the HDF5 library.
+dense links, contiguous float32 datasets, attributes); the other structures (symbol-table groups, version-1 object
+headers, superblock 2, link messages, global-heap strings, dense attributes behind an indirect fractal-heap root,
+chunked + deflate + shuffle data) follow the specification and are exercised on files written by hand from it
+(tests/h5build.py), not on files written by the HDF5 library.
 """
 import zlib
 

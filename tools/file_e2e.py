@@ -15,7 +15,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from nemoflux_b200 import ncio, synth  # noqa: E402
 
 
-def write_files(syn, nt, d, dtype):
+def write_files(syn, nt, d, dtype, fmt='classic'):
     os.makedirs(d, exist_ok=True)
     w = ncio.Writer(os.path.join(d, 'T.nc'))
     for name, n in (('z', syn.nz), ('y', syn.ny), ('x', syn.nx), ('nvertex', 4), ('axis_nbounds', 2)):
@@ -24,6 +24,14 @@ def write_files(syn, nt, d, dtype):
     w.createVariable('bounds_lat', 'float64', ('y', 'x', 'nvertex'), data=syn.bounds_lat)
     w.createVariable('bounds_lon', 'float64', ('y', 'x', 'nvertex'), data=syn.bounds_lon)
     w.close()
+    if fmt == 'hdf5':      # NetCDF-4 style container (little-endian, contiguous), written by the test helper
+        sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests'))
+        import h5build
+        for fname, vname, k in (('U.nc', 'uo', 0), ('V.nc', 'vo', 1)):
+            a = numpy.stack([syn.uv_host(t)[k].astype(dtype) for t in range(nt)])
+            a[numpy.isnan(a)] = 1.e20
+            h5build.write(os.path.join(d, fname), {vname: dict(data=a, attrs={'_FillValue': a.dtype.type(1.e20)})})
+        return
     for fname, vname, k in (('U.nc', 'uo', 0), ('V.nc', 'vo', 1)):
         w = ncio.Writer(os.path.join(d, fname))
         for name, n in (('t', nt), ('z', syn.nz), ('y', syn.ny), ('x', syn.nx)):
@@ -45,10 +53,12 @@ def main():
     ap.add_argument('--chunk-steps', default='0', help='comma list; the first is the reported one (0 = default)')
     ap.add_argument('--reps', type=int, default=5)
     ap.add_argument('--out', default='gpurun_out/file_e2e.json')
+    ap.add_argument('--format', default='classic', choices=['classic', 'hdf5'])
+    ap.add_argument('--skip-cpu', action='store_true')
     a = ap.parse_args()
     syn = synth.make(a.workload)
     t0 = time.perf_counter()
-    write_files(syn, a.nt, a.dir, a.dtype)
+    write_files(syn, a.nt, a.dir, a.dtype, a.format)
     t_write = time.perf_counter() - t0
     T, U, V = (os.path.join(a.dir, f) for f in ('T.nc', 'U.nc', 'V.nc'))
     units = syn.units_per_step() * a.nt
@@ -72,6 +82,18 @@ def main():
         print('chunk_steps', cs, sweep[cs], flush=True)
     t_gpu = sweep[int(a.chunk_steps.split(',')[0])]['median_s']
 
+    if a.skip_cpu:
+        fbytes = int(os.path.getsize(U) + os.path.getsize(V))
+        res = dict(workload=a.workload, nt=a.nt, dtype=a.dtype, format=a.format, transects=len(syn.transects),
+                   file_bytes=fbytes, write_s=t_write, chunk_sweep=sweep,
+                   gpu=dict(init_s=t_init, series_s=t_gpu, units_per_s=units / t_gpu, file_gbs=fbytes / t_gpu / 1e9),
+                   series_abs_max=float(numpy.abs(s_gpu).max()))
+        print(json.dumps(res, indent=1))
+        os.makedirs(os.path.dirname(a.out), exist_ok=True)
+        json.dump(res, open(a.out, 'w'), indent=1)
+        for f in (T, U, V):
+            os.unlink(f)
+        return
     # CPU: the reference's loop restated (oracle), reading the same files through the same reader
     from oracle import oracle as O
     t0 = time.perf_counter()

@@ -312,3 +312,28 @@ def test_real_nemo_grid_transect(oracle):
         exact = psi(*b) - psi(*a)
         got = q.getIntegral(iV.reshape(-1, 4))
         assert abs(got - exact) <= 1e-10 * max(1.0, abs(exact)), (got, exact)
+
+
+def test_golden_fixtures_are_what_the_reference_code_produces(tmp_path):
+    """with the reference tree mounted (the build container): re-run tests/golden/make_golden.py -- which imports the
+    reference's OWN datagen / geo / field / latlonreader modules -- into a scratch directory and compare every array
+    with the committed fixture, bit for bit.  Skipped where /root/reference does not exist (the GPU box)."""
+    import json
+    import os
+    import subprocess
+    import sys
+    from conftest import GOLDEN
+    if not os.path.isdir('/root/reference/nemoflux'):
+        pytest.skip('the reference tree is not mounted here')
+    env = dict(os.environ, NFX_GOLDEN_OUT=str(tmp_path))
+    out = subprocess.run([sys.executable, os.path.join(GOLDEN, 'make_golden.py')], capture_output=True, text=True, env=env,
+                         timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    names = sorted(f for f in os.listdir(GOLDEN) if f.endswith('.npz') and f != 'sa_T_grid.npz')
+    assert len(names) >= 7
+    for name in names:
+        a, b = numpy.load(os.path.join(GOLDEN, name)), numpy.load(str(tmp_path / name))
+        assert sorted(a.files) == sorted(b.files), name
+        for key in a.files:
+            assert numpy.array_equal(a[key], b[key], equal_nan=a[key].dtype.kind == 'f'), (name, key)
+    assert json.load(open(os.path.join(GOLDEN, 'golden_summary.json'))) == json.load(open(str(tmp_path / 'golden_summary.json')))

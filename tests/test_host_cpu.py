@@ -294,6 +294,10 @@ def test_hdf5_chunked_deflate_shuffle_decoding():
         lazy[5]
     with pytest.raises(h5lite.H5Error):
         h5lite.apply_filters_reverse(b'1234', [(32015, [])], 0, 4)
+    for size in (1, 2, 3, 4, 8, 16):                             # the vectorised unshuffle against a plain transpose
+        elems = rng.integers(0, 256, (37, size), dtype=numpy.uint8)
+        planes = elems.T.tobytes()
+        assert h5lite.unshuffle(planes, size, 37) == elems.tobytes(), size
 
 
 def test_hdf5_old_style_file_roundtrip(tmp_path):

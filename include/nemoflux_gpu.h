@@ -68,6 +68,9 @@ extern "C" {
                                       gathers unrolled x8 (default 3) */
 #define NFX_OPT_FUSED_F64_CTAS 10  /* fused pass, float64 storage, 256-bit loads: register budget for 2 or 4 CTAs per
                                       SM (0 = default 3) */
+#define NFX_OPT_FUSED_F32_CONV 11  /* fused pass, float32 storage, 128-bit loads: 0 (default) = the measured bit-shuffle
+                                      conversion, 1 = a variant with fewer ALU instructions (one ordered compare, one
+                                      wide multiply); same bits by construction, not yet measured on the device */
 
 typedef struct nfx_grid nfx_grid;
 typedef struct nfx_pli nfx_pli;

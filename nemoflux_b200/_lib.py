@@ -21,6 +21,7 @@ NFX_OPT_FUSED_F32_SHAPE = 7
 NFX_OPT_LAST_SERIES_PATH = 8
 NFX_OPT_FUSED_ORDER = 9
 NFX_OPT_FUSED_F64_CTAS = 10
+NFX_OPT_FUSED_F32_CONV = 11
 
 c_i64 = ctypes.c_int64
 c_int = ctypes.c_int

@@ -173,6 +173,10 @@ int nfx_set_option(int option, int value) {
             case NFX_OPT_FUSED_F32_SHAPE: g_fused_f32_shape = value; break;
             case NFX_OPT_FUSED_ORDER: g_fused_order = value; break;
             case NFX_OPT_FUSED_F64_CTAS: g_fused_f64_ctas = value; break;
+            case NFX_OPT_FUSED_F32_CONV:
+                NFX_REQUIRE(value == 0 || value == 1, "NFX_OPT_FUSED_F32_CONV must be 0 or 1");
+                g_fused_f32_conv = value;
+                break;
             case NFX_OPT_LAST_SERIES_PATH: throw Error(NFX_E_INVALID, "NFX_OPT_LAST_SERIES_PATH is read only");
             case NFX_OPT_FAST_SERIES:
                 NFX_REQUIRE(value >= 0 && value <= 2, "NFX_OPT_FAST_SERIES must be 0, 1 or 2");
@@ -198,6 +202,7 @@ int nfx_get_option(int option, int* value) {
             case NFX_OPT_FUSED_F32_SHAPE: *value = g_fused_f32_shape; break;
             case NFX_OPT_FUSED_ORDER: *value = g_fused_order; break;
             case NFX_OPT_FUSED_F64_CTAS: *value = g_fused_f64_ctas; break;
+            case NFX_OPT_FUSED_F32_CONV: *value = g_fused_f32_conv; break;
             case NFX_OPT_LAST_SERIES_PATH: *value = g_last_series_fused; break;
             case NFX_OPT_FAST_SERIES: *value = g_fast_series; break;
             case NFX_OPT_RING_SLOT_MB: *value = (int)(g_slot_bytes >> 20); break;

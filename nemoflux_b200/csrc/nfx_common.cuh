@@ -221,6 +221,7 @@ int fused_tile_columns(int dtype, const void* u, const void* v, int64_t ncell, i
                        uintptr_t more_bits = 0);
 int fused_error_flag(PliDev& p, cudaStream_t s);
 extern int g_fused_f32_shape;
+extern int g_fused_f32_conv;
 extern int g_fused_order;
 extern int g_fused_f64_ctas;
 int k3_group_for(int64_t nnz, int64_t nrows);

@@ -29,6 +29,7 @@ namespace nfx {
 
 int g_fused_f32_shape = 0;   // NFX_OPT_FUSED_F32_SHAPE (tuning knob)
 int g_fused_f64_ctas = 0;    // NFX_OPT_FUSED_F64_CTAS (tuning knob): 2 or 4 resident CTAs per SM instead of 3
+int g_fused_f32_conv = 0;    // NFX_OPT_FUSED_F32_CONV: 1 = clean_scaled_v2 (fewer ALU instructions; to be measured)
 int g_fused_order = 3;       // NFX_OPT_FUSED_ORDER: bit 0 = visit the batches panel-major, bit 1 = K3 gathers unrolled x8
                              // (same-box A/B, profiles/r1_fused_order_ab.md: -3 % and -1 % time on multi-panel grids)
 
@@ -105,7 +106,7 @@ constexpr int fused_min_ctas(int wanted) {
 
 // E3: e3u[t,k,c] / e3v[t,k,c] replace the 1-D thickness dz[k], the arithmetic of
 // k2_edgeflux_ldg<..., E3 = true> (nfx_k2_edgeflux.cu) operation for operation -> the same edge fluxes bit for bit
-template <typename T, int VEC, int UNROLL, int CTAS = 0, bool E3 = false>
+template <typename T, int VEC, int UNROLL, int CTAS = 0, bool E3 = false, int CONV = 0>
 __global__ void __launch_bounds__(kFusedBlock, fused_min_ctas<T, VEC, UNROLL, E3>(CTAS))
 k23_fused(const FusedArgs a) {
     extern __shared__ double s_dz[];
@@ -140,6 +141,8 @@ k23_fused(const FusedArgs a) {
     const uint64_t pol = l2_evict_last_policy();
     const uint64_t pol_ef = l2_evict_first_policy();
     const T fill = (T)a.fill;
+    // CONV = 1: one ordered compare against the marker, or against +inf when there is none (nfx_stream_ops.cuh)
+    const T fill_v2 = a.has_fill ? fill : (T)__int_as_float(0x7f800000);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 
     // Tried and dropped (same-box A/B, profiles/r1_fused_notes.md): fetching the next item id while the current
@@ -218,6 +221,9 @@ k23_fused(const FusedArgs a) {
                                 const double xv = __dmul_rn(clean_scaled(y[e], fill, a.has_fill, amax), kScaleUp);
                                 su[e] = __dadd_rn(su[e], __dmul_rn(du, xu));
                                 sv[e] = __dadd_rn(sv[e], __dmul_rn(dv, xv));
+                            } else if constexpr (kScaled && CONV == 1) {
+                                su[e] = __dadd_rn(su[e], __dmul_rn(d, clean_scaled_v2(x[e], fill_v2, amax)));
+                                sv[e] = __dadd_rn(sv[e], __dmul_rn(d, clean_scaled_v2(y[e], fill_v2, amax)));
                             } else if constexpr (kScaled) {
                                 su[e] = __dadd_rn(su[e], __dmul_rn(d, clean_scaled(x[e], fill, a.has_fill, amax)));
                                 sv[e] = __dadd_rn(sv[e], __dmul_rn(d, clean_scaled(y[e], fill, a.has_fill, amax)));
@@ -337,7 +343,7 @@ k23_fused(const FusedArgs a) {
     }
 }
 
-template <typename T, int VEC, int UNROLL, int CTAS = 0, bool E3 = false>
+template <typename T, int VEC, int UNROLL, int CTAS = 0, bool E3 = false, int CONV = 0>
 int fused_grid() {
     static int grid[64] = {0};   // per device ordinal
     int dev = 0;
@@ -346,17 +352,17 @@ int fused_grid() {
     if (g == 0) {
         int sms = 0, per_sm = 0;
         NFX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        NFX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k23_fused<T, VEC, UNROLL, CTAS, E3>, kFusedBlock,
+        NFX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k23_fused<T, VEC, UNROLL, CTAS, E3, CONV>, kFusedBlock,
                                                                sizeof(double) * 256));
         g = sms * std::max(per_sm, 1);
     }
     return g;
 }
 
-template <typename T, int VEC, int UNROLL, int CTAS = 0, bool E3 = false>
+template <typename T, int VEC, int UNROLL, int CTAS = 0, bool E3 = false, int CONV = 0>
 void launch_fused(const FusedArgs& a, cudaStream_t s) {
-    k23_fused<T, VEC, UNROLL, CTAS, E3>
-        <<<fused_grid<T, VEC, UNROLL, CTAS, E3>(), kFusedBlock, sizeof(double) * a.nz * 2, s>>>(a);
+    k23_fused<T, VEC, UNROLL, CTAS, E3, CONV>
+        <<<fused_grid<T, VEC, UNROLL, CTAS, E3, CONV>(), kFusedBlock, sizeof(double) * a.nz * 2, s>>>(a);
 }
 
 // e3u/e3v kernels: four streamed arrays, so half the columns per thread of the thickness kernels keep the same
@@ -373,6 +379,7 @@ int fused_grid_for(int dtype, int vec, int unroll, int ctas) {
     }
     if (unroll == 3) return vec == 8 ? fused_grid<float, 8, 3>() : fused_grid<float, 4, 3>();
     if (vec == 4 && ctas == 3) return fused_grid<float, 4, 5, 3>();
+    if (vec == 4 && unroll == 5 && g_fused_f32_conv == 1) return fused_grid<float, 4, 5, 0, false, 1>();
     return vec == 8 ? fused_grid<float, 8, 5>() : vec == 4 ? fused_grid<float, 4, 5>() : fused_grid<float, 1, 5>();
 }
 
@@ -535,6 +542,7 @@ void flux_series_fused(PliDev& p, const PanelPlan& pl, const void* u, const void
         else if (unroll == 3 && vec == 4) launch_fused<float, 4, 3>(a, s);
         else if (vec == 8) launch_fused<float, 8, 5>(a, s);
         else if (vec == 4 && ctas == 3) launch_fused<float, 4, 5, 3>(a, s);
+        else if (vec == 4 && g_fused_f32_conv == 1) launch_fused<float, 4, 5, 0, false, 1>(a, s);
         else if (vec == 4) launch_fused<float, 4, 5>(a, s);
         else launch_fused<float, 1, 5>(a, s);
     }

@@ -490,6 +490,47 @@ def test_bench_reference_arm_contract():
     assert out.returncode == 0 and not [ln for ln in out.stdout.splitlines() if ln.startswith('{')]
 
 
+def test_f32_conversion_flavours_agree_bitwise_in_emulation():
+    """nfx_stream_ops.cuh: clean_scaled (the measured default) and clean_scaled_v2 (NFX_OPT_FUSED_F32_CONV = 1: one
+    ordered compare, one signed wide multiply by 2^29) restated with numpy integer arithmetic: both give exactly
+    x * 2^-896 for every finite float (normals, denormals, +-0, FLT_MAX), 0 for NaN and the missing-value marker,
+    and every infinity is flagged by the running maximum (those threads recompute with the plain conversion)"""
+    rng = numpy.random.default_rng(12)
+    bits = rng.integers(0, 2 ** 32, 200000, dtype=numpy.uint64).astype(numpy.uint32)
+    special = numpy.array([0x00000000, 0x80000000, 0x00000001, 0x80000001, 0x007fffff, 0x00800000, 0x7f7fffff, 0xff7fffff,
+                           0x7f800000, 0xff800000, 0x7fc00000, 0xffc00000, 0x7f800001, 0x60ad78ec, 0xe0ad78ec], numpy.uint32)
+    bits = numpy.concatenate([special, bits])
+    x = bits.view(numpy.float32)
+    marker = numpy.float32(1.e20)                               # bits 0x60ad78ec
+
+    def pack(b):                                                # hi = (b >> 3 arithmetic) & 0x8fffffff, lo = b << 29
+        hi = (b.astype(numpy.int32) >> 3).astype(numpy.uint32) & numpy.uint32(0x8fffffff)
+        lo = (b.astype(numpy.uint64) << numpy.uint64(29)).astype(numpy.uint32)
+        return ((hi.astype(numpy.uint64) << numpy.uint64(32)) | lo.astype(numpy.uint64)).view(numpy.float64)
+
+    for fill in (marker, numpy.float32('nan')):
+        has_fill = not numpy.isnan(fill)
+        with numpy.errstate(invalid='ignore'):
+            keep1 = (~(x == fill) | numpy.isnan(x)) & (numpy.abs(x) <= numpy.finfo(numpy.float32).max)   # NEU and |x| <= FLT_MAX
+            keep1 &= ~numpy.isnan(x)
+            cmp2 = fill if has_fill else numpy.float32('inf')
+            keep2 = ~numpy.isnan(x) & (x != cmp2)                                                       # ordered NE
+        v1 = pack(numpy.where(keep1, bits, numpy.uint32(0)))
+        wide = numpy.where(keep2, bits, numpy.uint32(0)).astype(numpy.int32).astype(numpy.int64) * numpy.int64(2 ** 29)
+        hi2 = ((wide >> numpy.int64(32)) & numpy.int64(0xffffffff)).astype(numpy.uint32) & numpy.uint32(0x8fffffff)
+        lo2 = (wide & numpy.int64(0xffffffff)).astype(numpy.uint32)
+        v2 = ((hi2.astype(numpy.uint64) << numpy.uint64(32)) | lo2.astype(numpy.uint64)).view(numpy.float64)
+        finite = numpy.isfinite(x)
+        assert numpy.array_equal(v1[finite].view(numpy.uint64), v2[finite].view(numpy.uint64))
+        with numpy.errstate(invalid='ignore'):
+            want = numpy.where(has_fill & (x == fill), 0.0, x.astype(numpy.float64) * 2.0 ** -896)[finite]
+        assert numpy.array_equal(v1[finite], want) and numpy.array_equal(numpy.signbit(v1[finite]), numpy.signbit(want))
+        nan = numpy.isnan(x)
+        assert (v1[nan] == 0).all() and (v2[nan] == 0).all()
+        inf = numpy.isinf(x)
+        assert inf.any() and numpy.isinf(numpy.abs(x[inf]).max())         # what the FMNMX3 running maximum sees
+
+
 def test_gpu_cpu_binding_is_harmless_without_nvml_affinity():
     """bind_to_gpu_cpus: no GPU / no affinity information -> nothing changes and 0 is returned"""
     from nemoflux_b200 import dist

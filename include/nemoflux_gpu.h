@@ -187,6 +187,18 @@ int nfx_flux_series(nfx_pli** self, const void* u, const void* v, int dtype, con
 int nfx_flux_series_ld(nfx_pli** self, const void* u, const void* v, int dtype, const double* thickness,
                        const double* arc1, const double* arc2, int nt, int nz, int64_t ld, int sverdrup, double fill,
                        int order, double* eflux, double* series, void* stream);
+/* The device-path series calls (nfx_flux_series*, nfx_flux_series_range*) are asynchronous on `stream`.  Their fused
+ * pass spins on per-batch counters with a bound; a pass that ever overflowed it aborts and leaves NaN in `series`.
+ * nfx_pli_series_status synchronises `stream` and reports that: returns 0 with *status = 0 when every pass launched
+ * on the handle so far completed, NFX_E_INTERNAL with *status = 1 otherwise (the flag is cleared by the report).
+ * The flag is sticky: the next nfx_flux_series* call on the handle fails with NFX_E_INTERNAL as well, so an aborted
+ * pass is never handed back silently.  (mint's getIntegral is synchronous and returns ier != 0 on failure,
+ * field.py:102; this is the asynchronous equivalent.) */
+int nfx_pli_series_status(nfx_pli** self, void* stream, int* status);
+/* Read-only HBM ceiling of the current device with the access pattern of the edge-flux kernels (level planes of two
+ * arrays, 256-bit evict-first loads, K2's arithmetic, no stores): best of `reps` launches over the caller's device
+ * buffer (32-byte aligned, >= 9.3 GB, contents arbitrary) in GB/s.  Measurement aid for bench.py's roofline. */
+int nfx_probe_read_bandwidth(const void* buf, int64_t nbytes, int reps, double* gbs, void* stream);
 /* Finer-than-time-step sharding over GPUs.  The fused pass works on batches b = t*npanels + q (time step t of
  * the nt resident ones, panel q of npanels panels of panel_cells consecutive cells); this call runs only the
  * batches [batch_begin, batch_end) and returns PARTIAL sums in series (nt, ntransects): complete for the time

@@ -78,6 +78,8 @@ SIGNATURES = {
     'nfx_flux_series_ld': [P(c_vp), c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_int, c_i64, c_int, c_dbl, c_int, c_vp,
                            c_vp, c_vp],
     'nfx_pli_get_num_panels': [P(c_vp), P(c_int), P(c_i64)],
+    'nfx_pli_series_status': [P(c_vp), c_vp, P(c_int)],
+    'nfx_probe_read_bandwidth': [c_vp, c_i64, c_int, P(c_dbl), c_vp],
     'nfx_flux_series_range': [P(c_vp), c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_int, c_i64, c_int, c_dbl, c_int,
                               c_i64, c_i64, c_vp, c_vp],
     'nfx_flux_series_range_e3': [P(c_vp), c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_vp, c_int, c_int, c_i64, c_int,

@@ -148,6 +148,9 @@ struct PliDev {
     PanelPlan plan[2];            // per summation order
     DevBuf<double> ring, partial;  // L2-resident eflux ring and per-panel partial sums of the fused pass
     DevBuf<int> fused_sync;        // work counter, error flag, per-batch completion counters
+    DevBuf<int> fused_sticky_buf;  // device: 1 once any fused pass on this handle aborted
+    int* h_fused_err = nullptr;    // pinned: error flag of the fused passes launched so far, copied back behind every
+                                   // launch (sticky until reported by the next call on the handle / nfx_pli_series_status)
     DevBuf<unsigned char> scratch; // computeWeights temporaries (Arena), kept between calls when small
     int64_t nsub_hint = 0;         // sub-segments of the previous computeWeights: sizes the record list of the next
     size_t scratch_hint = 0;       // bytes the arena ended with
@@ -220,6 +223,8 @@ void flux_series_fused(PliDev& p, const PanelPlan& pl, const void* u, const void
 int fused_tile_columns(int dtype, const void* u, const void* v, int64_t ncell, int64_t ld, int64_t panel,
                        uintptr_t more_bits = 0);
 int fused_error_flag(PliDev& p, cudaStream_t s);
+void fused_check_sticky_error(PliDev& p);   // throws if a fused pass launched earlier on this handle aborted
+double probe_read_bandwidth(const void* buf, int64_t nbytes, int reps, double* sink, cudaStream_t s);   // nfx_probe.cu
 extern int g_fused_f32_shape;
 extern int g_fused_f32_conv;
 extern int g_fused_order;

@@ -343,6 +343,10 @@ k23_fused(const FusedArgs a) {
     }
 }
 
+__global__ void k_or_flag(const int* flag, int* sticky) {
+    if (*flag != 0) *sticky = 1;
+}
+
 template <typename T, int VEC, int UNROLL, int CTAS = 0, bool E3 = false, int CONV = 0>
 int fused_grid() {
     static int grid[64] = {0};   // per device ordinal
@@ -467,7 +471,7 @@ void flux_series_fused(PliDev& p, const PanelPlan& pl, const void* u, const void
     a.idx = pl.idx.p;
     a.w = pl.w.p;
     a.out = out;
-    NFX_REQUIRE(nz <= 6000, "edgeflux: at most 6000 levels");
+    NFX_REQUIRE(nz <= 3072, "edgeflux: at most 3072 levels (dz and dz * 2^896 live in 48 KB of shared memory)");
     NFX_REQUIRE((int64_t)(a.nbatches + 1) * (a.ntiles + a.nk3) < 2000000000ll, "fused pass: too many work items");
     // enough slots that every resident CTA finds a K2 tile while the K3 of older batches drains (x2 margin),
     // but no more than ~64 MB of evict-last lines in the 126 MB L2
@@ -548,6 +552,25 @@ void flux_series_fused(PliDev& p, const PanelPlan& pl, const void* u, const void
     }
     count_launch();
     NFX_CUDA(cudaGetLastError());
+    // the error flag travels to a pinned word behind the pass: the next call on the handle (or nfx_pli_series_status)
+    // reports an aborted pass instead of handing back NaN with return code 0.  k_or_flag keeps it sticky.
+    if (!p.h_fused_err) {
+        NFX_CUDA(cudaHostAlloc((void**)&p.h_fused_err, sizeof(int), cudaHostAllocDefault));
+        *p.h_fused_err = 0;
+        p.fused_sticky_buf.alloc(1);
+        NFX_CUDA(cudaMemsetAsync(p.fused_sticky_buf.p, 0, sizeof(int), s));
+    }
+    k_or_flag<<<1, 1, 0, s>>>(a.sync + 1, p.fused_sticky_buf.p);
+    NFX_CUDA(cudaMemcpyAsync(p.h_fused_err, p.fused_sticky_buf.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+}
+
+void fused_check_sticky_error(PliDev& p) {
+    if (p.h_fused_err && *(volatile int*)p.h_fused_err != 0) {
+        *(volatile int*)p.h_fused_err = 0;
+        if (p.fused_sticky_buf.p) cudaMemset(p.fused_sticky_buf.p, 0, sizeof(int));
+        throw Error(NFX_E_INTERNAL, "a fused K2+K3 pass launched earlier on this handle aborted (a bounded wait "
+                                    "overflowed): its flux series is NaN");
+    }
 }
 
 // error flag of the last fused pass (1 = a bounded spin overflowed); synchronises the stream

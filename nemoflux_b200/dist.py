@@ -187,3 +187,72 @@ def bind_to_gpu_cpus(device_index):
     except OSError:
         return 0
     return len(cpus)
+
+
+def apportion_by_rate(total, rates):
+    """Split `total` time steps over the ranks in proportion to `rates` (each rank's measured host->device rate),
+    largest-remainder rounding, so that the slowest link no longer sets the time of a host-fed pass: with equal
+    shards the rank behind a 23 GB/s link finishes 50 % after the one behind a 35 GB/s link
+    (profiles/r1_numa_probe8.md).  Returns the list of counts (sum == total, every count >= 0); a time step is the
+    unit, and the series of a time step does not depend on the rank that computes it (fluxplot.py:51-59 carries
+    no state), so the gathered series is bit-identical to the equal-shard one."""
+    total = int(total)
+    r = numpy.asarray(rates, dtype=numpy.float64)
+    if r.ndim != 1 or r.size == 0 or total < 0:
+        raise ValueError('apportion_by_rate needs a non-empty 1-D list of rates and total >= 0')
+    if not numpy.all(numpy.isfinite(r)) or numpy.any(r < 0):
+        raise ValueError('rates must be finite and >= 0')
+    if r.sum() <= 0:
+        r = numpy.ones_like(r)
+    ideal = total * r / r.sum()
+    counts = numpy.floor(ideal).astype(numpy.int64)
+    left = total - int(counts.sum())
+    order = numpy.argsort(-(ideal - counts), kind='stable')     # ties: lower rank first
+    counts[order[:left]] += 1
+    # exchange steps while it lowers the makespan max(count/rate): floor+remainder is optimal for the sum, not the max
+    span = lambda c: float(numpy.max(numpy.where(c > 0, c / numpy.maximum(r, 1e-300), 0.0)))   # noqa: E731
+    for _ in range(4 * r.size):
+        worst = int(numpy.argmax(numpy.where(counts > 0, counts / numpy.maximum(r, 1e-300), -1.0)))
+        trial_best, best = None, span(counts)
+        for j in range(r.size):
+            if j == worst or r[j] <= 0:
+                continue
+            c = counts.copy()
+            c[worst] -= 1
+            c[j] += 1
+            s = span(c)
+            if s < best - 1e-15:
+                trial_best, best = c, s
+        if trial_best is None:
+            break
+        counts = trial_best
+    return [int(c) for c in counts]
+
+
+def blocks_from_counts(counts):
+    """[(t0, n)] contiguous blocks of time steps for the per-rank counts"""
+    out, t0 = [], 0
+    for c in counts:
+        out.append((t0, int(c)))
+        t0 += int(c)
+    return out
+
+
+def measure_h2d_rate(device, nbytes=256 << 20, reps=3, group=None):
+    """This rank's host->device rate in GB/s while EVERY rank copies at the same time (pinned buffer, CUDA events):
+    the figure that matters for a host-fed pass on a box whose links share host memory bandwidth."""
+    import torch
+    import torch.distributed as dist
+    host = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    devb = torch.empty(nbytes, dtype=torch.uint8, device=device)
+    devb.copy_(host, non_blocking=True)
+    torch.cuda.synchronize(device)
+    if dist.is_available() and dist.is_initialized():
+        dist.barrier(group=group)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        devb.copy_(host, non_blocking=True)
+    e1.record()
+    torch.cuda.synchronize(device)
+    return reps * nbytes / (e0.elapsed_time(e1) * 1e-3) / 1e9

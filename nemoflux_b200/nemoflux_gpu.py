@@ -249,6 +249,14 @@ class PolylineIntegral(object):
         _lib.call('nfx_pli_get_num_panels', ctypes.byref(self._h), ctypes.byref(n), ctypes.byref(pc))
         return n.value, pc.value
 
+    def seriesStatus(self):
+        """Synchronise the current stream and raise NemofluxGpuError if a fused K2+K3 pass launched on this handle
+        aborted (its series is NaN); returns 0 otherwise.  The device-path fluxSeries is asynchronous: call this
+        before trusting a series that never leaves the device (a later fluxSeries call on the handle also reports it)."""
+        st = ctypes.c_int()
+        _lib.call('nfx_pli_series_status', ctypes.byref(self._h), _stream_ptr(), ctypes.byref(st))
+        return st.value
+
     def fluxSeries(self, u, v, thickness, arc1, arc2, sverdrup=False, fill=float('nan'), order='map', eflux=None,
                    out=None, chunk_steps=0, batch_range=None, e3u=None, e3v=None):
         """flux time series of every transect: (nt, M).
@@ -555,6 +563,19 @@ def edgeFluxToCellByCell(eflux, ny, nx, out=None):
     with torch.cuda.device(eflux.device):
         _lib.call('nfx_edgeflux_to_cell_by_cell', _t_ptr(eflux), nt, ny, nx, _t_ptr(out), _stream_ptr())
     return out
+
+
+def probeReadBandwidth(buf, reps=5):
+    """read-only HBM ceiling (GB/s) of the device of `buf` (a CUDA tensor of >= 9.3 GB whose contents do not matter)
+    with the access pattern of the edge-flux kernels -- the denominator bench.py quotes next to the copy peak"""
+    torch = _torch()
+    if not isinstance(buf, torch.Tensor) or not buf.is_cuda or not buf.is_contiguous():
+        raise TypeError('buf must be a contiguous CUDA tensor')
+    r = ctypes.c_double()
+    with torch.cuda.device(buf.device):
+        _lib.call('nfx_probe_read_bandwidth', _t_ptr(buf), int(buf.numel() * buf.element_size()), int(reps),
+                  ctypes.byref(r), _stream_ptr())
+    return r.value
 
 
 def edgeFluxAbsMax(eflux):

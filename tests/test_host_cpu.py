@@ -557,3 +557,46 @@ def test_allgather_series_two_ranks_gloo(tmp_path, nt):
     outs = [p.communicate(timeout=180)[0].decode() for p in procs]
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
+
+
+def test_bench_arms_share_config_and_defaults():
+    """bench.py: at N = 1 the workload is BASELINE config 3, at N >= 2 config 4 sharded by time (strong scaling); the
+    `config` dict is a function of (workload, N, dtype) only, so the reference arm and the GPU arm print the same one"""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location('nfx_bench', os.path.join(ROOT, 'bench.py'))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    from nemoflux_b200 import synth
+
+    class A(object):
+        workload, nt_local, nt_total = 'auto', 0, 0
+    assert bench.pick_workload(A, 1) == ('C3', 365, 'weak')
+    for n in (2, 4, 8):
+        assert bench.pick_workload(A, n) == ('C4', 365, 'strong')
+    c1 = bench.make_config('C4', synth.CONFIGS['C4'], 8, 'f64', 365, 'strong')
+    c2 = bench.make_config('C4', dict(synth.CONFIGS['C4']), 8, 'f64', 365, 'strong')
+    assert c1 == c2 and c1['workload'].startswith('C4') and 'model' not in c1
+    assert c1['sharding'].startswith('time steps [46, 46, 46, 46, 46, 45, 45, 45]')
+    assert bench.make_config('C3', synth.CONFIGS['C3'], 1, 'f32', 365, 'weak')['storage_dtype'] == 'f32'
+
+
+def test_apportion_by_rate():
+    """dist.apportion_by_rate: host-fed time steps in proportion to the measured H2D rates (the 8-GPU boxes of the pool
+    give GPUs 0-3 23 GB/s and 4-7 35 GB/s, profiles/r1_numa_probe8.md); never worse than equal shards"""
+    from nemoflux_b200 import dist as nd
+    rates = [23, 23, 23, 23, 35, 35, 35, 35]
+    c = nd.apportion_by_rate(32, rates)
+    assert sum(c) == 32 and c == [3, 3, 3, 3, 5, 5, 5, 5]
+    span = lambda cc: max(x / r for x, r in zip(cc, rates))   # noqa: E731
+    for total in (1, 7, 8, 24, 33, 100, 365):
+        c = nd.apportion_by_rate(total, rates)
+        assert sum(c) == total and min(c) >= 0
+        assert span(c) <= span(nd.shard_counts(total, 8)) + 1e-12
+    assert nd.apportion_by_rate(9, [1.0, 1.0, 1.0]) == [3, 3, 3]
+    assert nd.apportion_by_rate(0, [3.0, 4.0]) == [0, 0]
+    assert sum(nd.apportion_by_rate(5, [0.0, 0.0])) == 5
+    assert nd.blocks_from_counts([2, 0, 3]) == [(0, 2), (2, 0), (2, 3)]
+    with pytest.raises(ValueError):
+        nd.apportion_by_rate(3, [])
+    with pytest.raises(ValueError):
+        nd.apportion_by_rate(3, [1.0, float('nan')])

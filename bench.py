@@ -750,7 +750,7 @@ def run_config(cx, args, name, nt_total, scaling, steps, warmup, balance, with_e
         t0_rank, nt_local = nfx_dist.shard_time(nt_total, world, rank)
     bal = None
     if balance and world > 1:
-        npanels, _pc = wl.pli.getNumberOfPanels()
+        npanels, _pc = wl.pli.getNumberOfPanels(args.dtype)
         bal = nfx_dist.shard_batches(nt_total, npanels, world, rank)
         bal['npanels'] = npanels
         t0_rank, nt_local = bal['t_first'], bal['nt_touched']

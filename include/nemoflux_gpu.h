@@ -58,7 +58,9 @@ extern "C" {
 #define NFX_OPT_K2_BLOCK 3         /* threads per CTA (0 = default 256) */
 #define NFX_OPT_FAST_SERIES 4      /* nfx_flux_series with eflux == NULL: 1 (default) fused L2-resident pass where it
                                       is the faster one, 2 always fused, 0 never (two launches) */
-#define NFX_OPT_RING_SLOT_MB 5     /* size of one edge-flux ring slot of the fused pass in MB (default 8) */
+#define NFX_OPT_RING_SLOT_MB 5     /* size of one edge-flux ring slot of the fused pass in MB; 0 (default) = automatic:
+                                      a time step of up to 8 MB is one panel, larger grids are cut into panels of
+                                      about 4 MB (float64 storage) or 8 MB (float32) */
 #define NFX_OPT_K2_ALU_MASK 6      /* float32 storage, two-launch K2: which of every 5 levels take the bit-shuffle
                                       conversion instead of F2F (-1 = default, all; 0 = none) */
 #define NFX_OPT_FUSED_F32_SHAPE 7  /* fused pass, float32 storage: 10 * vector width + unroll (85, 45, 83, 43; 0 = 45) */
@@ -68,9 +70,8 @@ extern "C" {
                                       gathers unrolled x8 (default 3) */
 #define NFX_OPT_FUSED_F64_CTAS 10  /* fused pass, float64 storage, 256-bit loads: register budget for 2 or 4 CTAs per
                                       SM (0 = default 3) */
-#define NFX_OPT_FUSED_F32_CONV 11  /* fused pass, float32 storage, 128-bit loads: 0 (default) = the measured bit-shuffle
-                                      conversion, 1 = a variant with fewer ALU instructions (one ordered compare, one
-                                      wide multiply); same bits by construction, not yet measured on the device */
+#define NFX_OPT_FUSED_K3_LAG 15    /* fused pass: the K3 items of batch b - lag are queued behind the K2 tiles of batch b
+                                      (0 = automatic: one-panel grids the batches the resident CTAs span + 1, else 1) */
 
 typedef struct nfx_grid nfx_grid;
 typedef struct nfx_pli nfx_pli;
@@ -204,7 +205,8 @@ int nfx_probe_read_bandwidth(const void* buf, int64_t nbytes, int reps, double* 
  * batches [batch_begin, batch_end) and returns PARTIAL sums in series (nt, ntransects): complete for the time
  * steps whose panels all lie in the range, contributions of the missing panels are 0.  The owner of the other
  * panels adds its part (nemoflux_b200/dist.py).  Always the fused pass. */
-int nfx_pli_get_num_panels(nfx_pli** self, int* npanels, int64_t* panel_cells);
+int nfx_pli_get_num_panels(nfx_pli** self, int* npanels, int64_t* panel_cells);   /* float64 storage */
+int nfx_pli_get_num_panels_dtype(nfx_pli** self, int dtype, int* npanels, int64_t* panel_cells);
 int nfx_flux_series_range(nfx_pli** self, const void* u, const void* v, int dtype, const double* thickness,
                           const double* arc1, const double* arc2, int nt, int nz, int64_t ld, int sverdrup, double fill,
                           int order, int64_t batch_begin, int64_t batch_end, double* series, void* stream);

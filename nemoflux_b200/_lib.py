@@ -21,7 +21,7 @@ NFX_OPT_FUSED_F32_SHAPE = 7
 NFX_OPT_LAST_SERIES_PATH = 8
 NFX_OPT_FUSED_ORDER = 9
 NFX_OPT_FUSED_F64_CTAS = 10
-NFX_OPT_FUSED_F32_CONV = 11
+NFX_OPT_FUSED_K3_LAG = 15
 
 c_i64 = ctypes.c_int64
 c_int = ctypes.c_int
@@ -78,6 +78,7 @@ SIGNATURES = {
     'nfx_flux_series_ld': [P(c_vp), c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_int, c_i64, c_int, c_dbl, c_int, c_vp,
                            c_vp, c_vp],
     'nfx_pli_get_num_panels': [P(c_vp), P(c_int), P(c_i64)],
+    'nfx_pli_get_num_panels_dtype': [P(c_vp), c_int, P(c_int), P(c_i64)],
     'nfx_pli_series_status': [P(c_vp), c_vp, P(c_int)],
     'nfx_probe_read_bandwidth': [c_vp, c_i64, c_int, P(c_dbl), c_vp],
     'nfx_flux_series_range': [P(c_vp), c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_int, c_i64, c_int, c_dbl, c_int,

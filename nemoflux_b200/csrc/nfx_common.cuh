@@ -226,8 +226,8 @@ int fused_error_flag(PliDev& p, cudaStream_t s);
 void fused_check_sticky_error(PliDev& p);   // throws if a fused pass launched earlier on this handle aborted
 double probe_read_bandwidth(const void* buf, int64_t nbytes, int reps, double* sink, cudaStream_t s);   // nfx_probe.cu
 extern int g_fused_f32_shape;
-extern int g_fused_f32_conv;
 extern int g_fused_order;
+extern int g_fused_k3_lag;
 extern int g_fused_f64_ctas;
 int k3_group_for(int64_t nnz, int64_t nrows);
 

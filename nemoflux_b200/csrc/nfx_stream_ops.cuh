@@ -211,27 +211,6 @@ __device__ __forceinline__ double clean_scaled(float x, float fill, bool has_fil
     const uint32_t lo = b << 29;
     return __hiloint2double((int)hi, (int)lo);
 }
-// Second flavour (NFX_OPT_FUSED_F32_CONV = 1, not the default until measured): the same value with fewer ALU-pipe
-// instructions.  (a) ONE ordered compare: setp.ne.f32 is false for NaN and for x == marker; without a marker the
-// caller passes +inf, which the running maximum sends to the recompute path anyway (as every infinity: the garbage
-// an infinity leaves here is discarded there).  (b) hi and lo word from ONE signed 32 x 32 -> 64 multiply by 2^29
-// (IMAD.WIDE on the FMA pipe): the high word is b >> 3 (arithmetic), the low word b << 29.  Per value: FSETP, SEL, LOP3
-// + half an FMNMX3 on the ALU pipe (5.5 before) and one IMAD.WIDE instead of an IMAD.SHL.
-__device__ __forceinline__ double clean_scaled_v2(float x, float marker_or_inf, float& amax) {
-    amax = fmaxf(amax, fabsf(x));
-    uint32_t b;
-    asm("{\n\t.reg .pred p;\n\t"
-        "setp.ne.f32 p, %1, %2;\n\t"
-        "selp.b32 %0, %3, 0, p;\n\t}"
-        : "=r"(b)
-        : "f"(x), "f"(marker_or_inf), "r"(__float_as_uint(x)));
-    long long wide;
-    asm("mul.wide.s32 %0, %1, 0x20000000;" : "=l"(wide) : "r"(b));
-    const uint32_t hi = (uint32_t)((unsigned long long)wide >> 32) & 0x8fffffffu;
-    return __hiloint2double((int)hi, (int)(uint32_t)wide);
-}
-__device__ __forceinline__ double clean_scaled_v2(double x, double, float&) { return x; }   // never used
-
 __device__ __forceinline__ double clean_scaled(double x, double fill, bool has_fill, float&) {
     return clean<double>(x, fill, has_fill);                       // never used: ALU_MASK is 0 for float64 storage
 }

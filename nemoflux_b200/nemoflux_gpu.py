@@ -243,10 +243,12 @@ class PolylineIntegral(object):
                       _t_ptr(out), _stream_ptr())
         return out
 
-    def getNumberOfPanels(self):
-        """(npanels, panel_cells) of the fused pass: batches are (time step, panel) pairs, see fluxSeries(batch_range=)"""
+    def getNumberOfPanels(self, dtype='float64'):
+        """(npanels, panel_cells) of the fused pass for uo/vo stored as `dtype` ('float64' | 'float32' | 'f64' | 'f32'):
+        batches are (time step, panel) pairs, see fluxSeries(batch_range=)"""
+        code = _lib.NFX_F32 if str(dtype) in ('float32', 'f32', 'torch.float32') else _lib.NFX_F64
         n, pc = ctypes.c_int(), ctypes.c_int64()
-        _lib.call('nfx_pli_get_num_panels', ctypes.byref(self._h), ctypes.byref(n), ctypes.byref(pc))
+        _lib.call('nfx_pli_get_num_panels_dtype', ctypes.byref(self._h), code, ctypes.byref(n), ctypes.byref(pc))
         return n.value, pc.value
 
     def seriesStatus(self):

@@ -512,7 +512,7 @@ def test_fast_series_path_matches_classic(gpu, oracle, slot_mb, shape):
                                   order=order, chunk_steps=3)
             assert numpy.array_equal(h32_be, h32)
     finally:
-        _lib.set_option(_lib.NFX_OPT_RING_SLOT_MB, 8)
+        _lib.set_option(_lib.NFX_OPT_RING_SLOT_MB, 0)      # back to automatic
         _lib.set_option(_lib.NFX_OPT_FAST_SERIES, 1)
 
 
@@ -565,7 +565,7 @@ def test_padded_level_planes(gpu, oracle, dtype):
         scale = _l1_scale(oracle, P, transects, u.astype(numpy.float64), v.astype(numpy.float64), g.thickness(), arc, False)
         assert (numpy.abs(s_pad - ref) <= FLUX_RTOL * scale + 1e-300).all()
     finally:
-        _lib.set_option(_lib.NFX_OPT_RING_SLOT_MB, 8)
+        _lib.set_option(_lib.NFX_OPT_RING_SLOT_MB, 0)      # back to automatic
         _lib.set_option(_lib.NFX_OPT_FAST_SERIES, 1)
         _lib.set_option(_lib.NFX_OPT_FUSED_ORDER, 3)
     with pytest.raises(ValueError):
@@ -610,7 +610,7 @@ def test_batch_range_partials_add_up(gpu, oracle):
         with pytest.raises(RuntimeError):
             p.fluxSeries(ud[:2], vd[:2], th, a1, a2, batch_range=(0, 2 * npanels + 1))
     finally:
-        _lib.set_option(_lib.NFX_OPT_RING_SLOT_MB, 8)
+        _lib.set_option(_lib.NFX_OPT_RING_SLOT_MB, 0)      # back to automatic
         _lib.set_option(_lib.NFX_OPT_FAST_SERIES, 1)
 
 
@@ -791,7 +791,7 @@ def test_fused_series_with_scale_factors(gpu, oracle, dtype, e3_nt, padded):
         with pytest.raises(ValueError):
             p.fluxSeries(hu, hv, None, arc[:, 1].copy(), arc[:, 2].copy(), e3u=e3u)
     finally:
-        _lib.set_option(_lib.NFX_OPT_RING_SLOT_MB, 8)
+        _lib.set_option(_lib.NFX_OPT_RING_SLOT_MB, 0)      # back to automatic
         _lib.set_option(_lib.NFX_OPT_FAST_SERIES, 1)
 
 

@@ -55,7 +55,7 @@ for i in range(a.passes + 1):
         ms.append(e0.elapsed_time(e1))
 st = p.seriesStatus() if hasattr(p, 'seriesStatus') else None
 res = dict(workload=a.workload, nt=a.nt, dtype=a.dtype, pad=pad, fused=_lib.get_option(_lib.NFX_OPT_LAST_SERIES_PATH),
-           panels=p.getNumberOfPanels()[0], ms=ms, gbs=[nbytes / m / 1e6 for m in ms], algorithmic_bytes=nbytes,
+           panels=p.getNumberOfPanels(a.dtype)[0], ms=ms, gbs=[nbytes / m / 1e6 for m in ms], algorithmic_bytes=nbytes,
            status=st, finite=bool(torch.isfinite(out).all()))
 print(json.dumps(res))
 if a.out:

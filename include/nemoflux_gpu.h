@@ -83,6 +83,14 @@ int nfx_set_option(int option, int value);
 int nfx_get_option(int option, int* value);
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 int nfx_launch_count(int64_t* n);
+/* Debug aid (compute-sanitizer is not available on every pool): with NFX_DEBUG_GUARDS=1 in the environment every
+ * device buffer the library owns carries 4 KB guard bands; this call synchronises the device, checks them all and
+ * returns NFX_E_INTERNAL (details in nfx_last_error) when a kernel wrote before the start or past the end of one.
+ * *nbuffers = buffers checked (0 when the guards are off), *ndamaged = buffers with a damaged band. */
+int nfx_debug_check_guards(int64_t* nbuffers, int64_t* ndamaged);
+/* self-test of the above: overwrites the byte right before (where = 0) or right behind (1) the most recently allocated
+ * guarded buffer; refuses to do anything unless NFX_DEBUG_GUARDS is set */
+int nfx_debug_poke_guard(int where);
 
 /* ---- mint.Grid: Grid(), setPoints(points), getNumberOfCells()  (horizgrid.py:23-24,30) ---------- */
 int nfx_grid_new(nfx_grid** self);
@@ -215,6 +223,11 @@ int nfx_flux_series_range_e3(nfx_pli** self, const void* u, const void* v, const
                              int e3_nt, const double* arc1, const double* arc2, int nt, int nz, int64_t ld, int sverdrup,
                              double fill, int order, int64_t batch_begin, int64_t batch_end, double* series,
                              void* stream);
+/* Threading / stream rules (as for a libmint handle: single-threaded, not re-entrant): a handle owns scratch (ring,
+ * partial sums, counters, staging buffers) that every call on it re-uses, so calls on ONE handle must be issued from
+ * one thread and one stream at a time; different handles are independent.  The host-buffer entry points below run on
+ * two private non-blocking streams of the handle and synchronise them before returning: borrowed DEVICE arrays they
+ * are given (e3_on_device) must be complete when the call is made. */
 /* everything from HOST buffers (the call a non-CUDA host makes): u, v host (nt,nz,ny,nx), thickness
  * host (nz), arc1/arc2 host (ncell); series host (nt, ntransects).  Streams time chunks through
  * double-buffered device staging (host buffers may be pinned or pageable). chunk_steps <= 0 = auto */

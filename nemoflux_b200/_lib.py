@@ -35,6 +35,8 @@ SIGNATURES = {
     'nfx_set_option': [c_int, c_int],
     'nfx_get_option': [c_int, P(c_int)],
     'nfx_launch_count': [P(c_i64)],
+    'nfx_debug_check_guards': [P(c_i64), P(c_i64)],
+    'nfx_debug_poke_guard': [c_int],
     'nfx_grid_new': [P(c_vp)],
     'nfx_grid_del': [P(c_vp)],
     'nfx_grid_set_points': [P(c_vp), c_i64, c_vp],
@@ -130,6 +132,14 @@ def call(name, *args):
 def launch_count():
     n = c_i64()
     call('nfx_launch_count', ctypes.byref(n))
+    return n.value
+
+
+def check_guards():
+    """NFX_DEBUG_GUARDS=1: number of library-owned device buffers checked; raises NemofluxGpuError when a guard band
+    around one of them was overwritten (0 buffers = the guards are off)"""
+    n, bad = c_i64(), c_i64()
+    call('nfx_debug_check_guards', ctypes.byref(n), ctypes.byref(bad))
     return n.value
 
 

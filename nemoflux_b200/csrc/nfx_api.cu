@@ -2,6 +2,7 @@
 #include <atomic>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 
 #include "nfx_common.cuh"
 
@@ -13,6 +14,76 @@ static K2Options g_k2opt;
 static int g_fast_series = 1;             // NFX_OPT_FAST_SERIES
 static int g_last_series_fused = -1;      // NFX_OPT_LAST_SERIES_PATH (read only): path of the last nfx_flux_series* call
 static int64_t g_slot_bytes = 0;          // NFX_OPT_RING_SLOT_MB, 0 = automatic (slot_bytes_for)
+
+// ---- debug guard bands (see nfx_common.cuh) ---------------------------------------------------------------------
+struct GuardRec {
+    void* raw;
+    size_t payload;
+};
+static std::mutex g_guard_mu;
+static std::vector<GuardRec> g_guards;
+
+bool guards_enabled() {
+    static const bool on = [] {
+        const char* e = std::getenv("NFX_DEBUG_GUARDS");
+        return e && std::atoi(e) != 0;
+    }();
+    return on;
+}
+
+void guard_register(void* raw, size_t payload_bytes) {
+    unsigned char* b = static_cast<unsigned char*>(raw);
+    cudaMemset(b, 0xA5, kGuardBytes);
+    // the tail guard starts right behind the payload (not behind its 256-byte rounding): an overrun by one element shows
+    const size_t rounded = (payload_bytes + 255) & ~(size_t)255;
+    cudaMemset(b + kGuardBytes + payload_bytes, 0xA5, rounded - payload_bytes + kGuardBytes);
+    std::lock_guard<std::mutex> lk(g_guard_mu);
+    g_guards.push_back({raw, payload_bytes});
+}
+
+void guard_unregister(void* raw) {
+    std::lock_guard<std::mutex> lk(g_guard_mu);
+    for (size_t i = 0; i < g_guards.size(); ++i)
+        if (g_guards[i].raw == raw) {
+            g_guards[i] = g_guards.back();
+            g_guards.pop_back();
+            return;
+        }
+}
+
+// number of library-owned buffers with a damaged guard band (after a device synchronise); details in *report
+static int64_t guard_check_all(std::string* report, int64_t* nbuffers) {
+    std::lock_guard<std::mutex> lk(g_guard_mu);
+    NFX_CUDA(cudaDeviceSynchronize());
+    int64_t bad = 0;
+    std::vector<unsigned char> h;
+    for (const GuardRec& g : g_guards) {
+        const size_t rounded = (g.payload + 255) & ~(size_t)255;
+        const size_t tail = rounded - g.payload + kGuardBytes;
+        h.resize(kGuardBytes + tail);
+        unsigned char* b = static_cast<unsigned char*>(g.raw);
+        NFX_CUDA(cudaMemcpy(h.data(), b, kGuardBytes, cudaMemcpyDeviceToHost));
+        NFX_CUDA(cudaMemcpy(h.data() + kGuardBytes, b + kGuardBytes + g.payload, tail, cudaMemcpyDeviceToHost));
+        int64_t first = -1, count = 0;
+        for (size_t i = 0; i < h.size(); ++i)
+            if (h[i] != 0xA5) {
+                if (first < 0) first = (int64_t)i;
+                ++count;
+            }
+        if (count) {
+            ++bad;
+            if (report && report->size() < 2000) {
+                const bool head = first < (int64_t)kGuardBytes;
+                *report += "buffer of " + std::to_string(g.payload) + " bytes: " + std::to_string(count) +
+                           " guard bytes overwritten, first " +
+                           (head ? std::to_string((int64_t)kGuardBytes - first) + " bytes BEFORE the start"
+                                 : std::to_string(first - (int64_t)kGuardBytes) + " bytes PAST the end") + "; ";
+            }
+        }
+    }
+    if (nbuffers) *nbuffers = (int64_t)g_guards.size();
+    return bad;
+}
 
 void set_last_error(const std::string& m) { g_last_error = m; }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
@@ -222,6 +293,31 @@ int nfx_get_option(int option, int* value) {
             case NFX_OPT_RING_SLOT_MB: *value = (int)(g_slot_bytes >> 20); break;
             default: throw Error(NFX_E_INVALID, "unknown option");
         }
+    });
+}
+
+int nfx_debug_check_guards(int64_t* nbuffers, int64_t* ndamaged) {
+    return guarded([&] {
+        NFX_REQUIRE(ndamaged, "NULL pointer");
+        if (nbuffers) *nbuffers = 0;
+        *ndamaged = 0;
+        if (!guards_enabled()) return;
+        int dev;
+        require_gpu(&dev);
+        std::string report;
+        *ndamaged = guard_check_all(&report, nbuffers);
+        if (*ndamaged) throw Error(NFX_E_INTERNAL, "guard bands damaged: " + report);
+    });
+}
+
+int nfx_debug_poke_guard(int where) {
+    return guarded([&] {
+        NFX_REQUIRE(guards_enabled(), "NFX_DEBUG_GUARDS is not set");
+        std::lock_guard<std::mutex> lk(g_guard_mu);
+        NFX_REQUIRE(!g_guards.empty(), "no guarded buffer yet");
+        const GuardRec& g = g_guards.back();
+        unsigned char* b = static_cast<unsigned char*>(g.raw);
+        NFX_CUDA(cudaMemset(where == 0 ? b + kGuardBytes - 1 : b + kGuardBytes + g.payload, 0, 1));
     });
 }
 

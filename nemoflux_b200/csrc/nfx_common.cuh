@@ -32,27 +32,50 @@ void count_launch(int n = 1);
         if (!(cond)) throw nfx::Error(NFX_E_INVALID, (msg));        \
     } while (0)
 
+// Debug guard bands (NFX_DEBUG_GUARDS=1 in the environment): every DevBuf is allocated with kGuardBytes of 0xA5 on
+// both sides and registered; nfx_debug_check_guards() synchronises the device and reports every guard byte that was
+// overwritten.  The pool's boxes refuse compute-sanitizer (profiles/r2_sanitizer_closed.log); this catches what its
+// memcheck would catch for writes past either end of a library-owned buffer.
+constexpr size_t kGuardBytes = 4096;
+bool guards_enabled();
+void guard_register(void* raw, size_t payload_bytes);
+void guard_unregister(void* raw);
+
 // owning device buffer
 template <typename T>
 struct DevBuf {
     T* p = nullptr;
     size_t n = 0;
+    void* raw = nullptr;   // what cudaMalloc returned (differs from p only with guard bands)
     DevBuf() = default;
     DevBuf(const DevBuf&) = delete;
     DevBuf& operator=(const DevBuf&) = delete;
     ~DevBuf() { release(); }
     void release() {
-        if (p) cudaFree(p);
+        if (raw) {
+            if (raw != (void*)p) guard_unregister(raw);
+            cudaFree(raw);
+        }
         p = nullptr;
+        raw = nullptr;
         n = 0;
     }
     void alloc(size_t count) {
         release();
         if (count == 0) count = 1;
-        cudaError_t e = cudaMalloc((void**)&p, count * sizeof(T));
+        const size_t bytes = count * sizeof(T);
+        const bool guard = guards_enabled();
+        const size_t payload = guard ? (bytes + 255) & ~(size_t)255 : bytes;
+        cudaError_t e = cudaMalloc(&raw, payload + (guard ? 2 * kGuardBytes : 0));
         if (e != cudaSuccess) {
-            p = nullptr;
+            raw = nullptr;
             throw Error(NFX_E_ALLOC, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+        }
+        if (guard) {
+            p = reinterpret_cast<T*>(static_cast<unsigned char*>(raw) + kGuardBytes);
+            guard_register(raw, bytes);
+        } else {
+            p = static_cast<T*>(raw);
         }
         n = count;
     }

@@ -1052,6 +1052,7 @@ void pli_compute_weights(PliDev& p, int ntransects, const int* offsets, const do
         NFX_CUDA(cudaStreamSynchronize(s));
         std::swap(bigger.p, p.scratch.p);
         std::swap(bigger.n, p.scratch.n);
+        std::swap(bigger.raw, p.scratch.raw);
         const size_t used = ar.used;
         ar = Arena{p.scratch.p, p.scratch.n, used};
         auto rebase = [&](auto& view) {   // same offset in the new buffer (bigger.p is the old one after the swap)

@@ -186,16 +186,23 @@ class Field(object):
         datagen.py:191) is not decoded on the host -- K2 maps it (and NaN) to 0, which is what xarray's decoding
         followed by fillna(0.0) does in the reference (field.py:149-157)"""
         var = nc[fieldName]
+        # packed variables (scale_factor / add_offset) or two different missing-value markers: decoded values (NaN for
+        # missing data) instead of the raw fast path -- what xarray hands the reference (field.py:149)
+        get = (lambda i: var[i]) if self._decoded(var) else var.raw
         try:
             if len(var.shape) == 4:
-                a = var.raw(slice(t0, t0 + n))
+                a = get(slice(t0, t0 + n))
             elif len(var.shape) == 3:
-                a = var.raw()[None]
+                a = get(Ellipsis)[None]
             else:
-                a = var.raw()[None, None]
+                a = get(Ellipsis)[None, None]
         except Exception:
             raise RuntimeError(f'ERROR: could not read {fieldName} field')
         return numpy.ascontiguousarray(a)
+
+    @staticmethod
+    def _decoded(var):
+        return var.packed or len(var.fill_values()) > 1
 
     def _uv_slabs(self, t0, n):
         """u, v blocks and the one missing-value marker K2 is given; if vo uses another marker than uo it is
@@ -208,6 +215,8 @@ class Field(object):
         return u, v, fu
 
     def _fill(self, nc, fieldName):
+        if self._decoded(nc[fieldName]):
+            return float('nan')                    # decoded on the host: missing data are NaN already
         fv = nc[fieldName].fill_value()
         if nc[fieldName].dtype.itemsize == 4 and fv == fv:
             fv = float(numpy.float32(fv))          # compare in the storage precision
@@ -308,10 +317,13 @@ class Field(object):
         views = [tuple(b.numpy().view(raw_u) if as_stored else b.numpy() for b in pair) for pair in bufs]
 
         fill_u, fill_v = self._fill(self.ncU, 'uo'), self._fill(self.ncV, 'vo')
-        four_d = len(self.ncU['uo'].shape) == 4 and len(self.ncV['vo'].shape) == 4
+        four_d = len(self.ncU['uo'].shape) == 4 and len(self.ncV['vo'].shape) == 4 and \
+            not self._decoded(self.ncU['uo']) and not self._decoded(self.ncV['vo'])
         from concurrent.futures import ThreadPoolExecutor
         import os as _os
         workers = max(1, min(8, (_os.cpu_count() or 2) // 2))
+        if not (self.ncU['uo'].thread_safe and self.ncV['vo'].thread_safe):
+            workers = 1     # netCDF4 backend: libnetcdf / HDF5 are not thread-safe, reads are serialised by ncio's lock
         pool = ThreadPoolExecutor(max_workers=workers)
 
         def read(i, slot):

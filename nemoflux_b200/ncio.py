@@ -8,14 +8,40 @@ reference's data/sa/T.nc and of real NEMO output.  Missing values (``_FillValue`
 are decoded to NaN like xarray's default ``mask_and_scale`` does, so ``fillna(0)`` semantics
 (field.py:157) carry over.
 """
+import contextlib
+import threading
+
 import numpy
+
+# libnetcdf / HDF5 are not thread-safe and netCDF4-python releases the GIL around nc_get_vara: every read through that
+# backend takes this process-wide lock (the memory-mapped scipy and h5lite backends read in parallel without it)
+_NETCDF4_LOCK = threading.RLock()
 
 
 class Variable(object):
-    def __init__(self, name, data, dims, attrs):
+    def __init__(self, name, data, dims, attrs, lock=None):
         self.name, self._data, self.dimensions, self.attrs = name, data, tuple(dims), dict(attrs)
         self.shape = tuple(data.shape)
         self.dtype = data.dtype
+        self._lock = lock
+
+    @property
+    def thread_safe(self):
+        """False when reads are serialised by the backend's lock (netCDF4): parallel readers gain nothing"""
+        return self._lock is None
+
+    def _guard(self):
+        return self._lock if self._lock is not None else contextlib.nullcontext()
+
+    @property
+    def packed(self):
+        """CF packing (scale_factor / add_offset): the stored values are not the physical ones"""
+        return 'scale_factor' in self.attrs or 'add_offset' in self.attrs
+
+    def _require_unpacked(self, what):
+        if self.packed:
+            raise NotImplementedError(f'{self.name}: {what} hands out the values as stored, but the variable is packed '
+                                      f'(scale_factor / add_offset); index the variable for decoded values')
 
     def __getattr__(self, key):
         try:
@@ -35,28 +61,55 @@ class Variable(object):
 
     def raw(self, idx=Ellipsis):
         """values as stored (native byte order), missing values NOT decoded: pair with fill_value()"""
-        return self._native(numpy.array(self._data[idx]))
+        self._require_unpacked('raw()')
+        with self._guard():
+            return self._native(numpy.array(self._data[idx]))
 
     def read_into(self, dst, idx=Ellipsis):
         """copy the stored values [idx] into dst (same shape), converting the byte order on the way; missing values
-        are NOT decoded.  numpy releases the GIL in the copy loop, so several slices can be read in parallel."""
-        numpy.copyto(dst, self._data[idx], casting='same_kind')
+        are NOT decoded.  numpy releases the GIL in the copy loop, so several slices can be read in parallel
+        (memory-mapped backends; the netCDF4 backend serialises on its lock)."""
+        self._require_unpacked('read_into()')
+        with self._guard():
+            numpy.copyto(dst, self._data[idx], casting='same_kind')
 
-    def fill_value(self):
-        """the value that marks missing data (_FillValue / missing_value), NaN when there is none"""
+    def fill_values(self):
+        """every distinct missing-data marker of the variable (_FillValue and missing_value may both be present)"""
+        out = []
         for key in ('_FillValue', 'missing_value'):
             if key in self.attrs:
-                return float(numpy.asarray(self.attrs[key]).reshape(-1)[0])
-        return float('nan')
+                for fv in numpy.asarray(self.attrs[key]).reshape(-1):
+                    if float(fv) not in out and fv == fv:
+                        out.append(float(fv))
+        return out
+
+    def fill_value(self):
+        """the value that marks missing data (_FillValue / missing_value), NaN when there is none; raises when the two
+        attributes name DIFFERENT markers (the raw fast path handles one: read decoded values instead)"""
+        fvs = self.fill_values()
+        if len(fvs) > 1:
+            raise ValueError(f'{self.name}: _FillValue and missing_value differ ({fvs}); index the variable for decoded values')
+        return fvs[0] if fvs else float('nan')
 
     def __getitem__(self, idx):
-        """values with missing data decoded to NaN (floating point variables only)"""
-        a = self._native(numpy.array(self._data[idx]))
+        """decoded values like xarray's mask_and_scale: missing data (both markers) -> NaN, then scale_factor /
+        add_offset (floating point result)"""
+        with self._guard():
+            a = self._native(numpy.array(self._data[idx]))
+        fvs = self.fill_values()
+        if self.packed:
+            mask = numpy.zeros(a.shape, bool)
+            for fv in fvs:
+                mask |= a == a.dtype.type(fv)
+            scale = numpy.asarray(self.attrs.get('scale_factor', 1.0)).reshape(-1)[0]
+            offset = numpy.asarray(self.attrs.get('add_offset', 0.0)).reshape(-1)[0]
+            out_t = numpy.result_type(numpy.float32 if a.dtype.itemsize <= 2 else numpy.float64, numpy.asarray(scale).dtype)
+            a = a.astype(out_t) * out_t.type(scale) + out_t.type(offset)
+            a[mask] = numpy.nan
+            return a
         if a.dtype.kind == 'f':
-            for key in ('_FillValue', 'missing_value'):
-                if key in self.attrs:
-                    fv = numpy.asarray(self.attrs[key]).reshape(-1)[0]
-                    a[a == a.dtype.type(fv)] = numpy.nan
+            for fv in fvs:
+                a[a == a.dtype.type(fv)] = numpy.nan
         return a
 
 
@@ -133,7 +186,7 @@ class Dataset(object):
             self._h = h
             for name, var in h.variables.items():
                 attrs = {k: var.getncattr(k) for k in var.ncattrs()}
-                self.variables[name] = Variable(name, var, var.dimensions, attrs)
+                self.variables[name] = Variable(name, var, var.dimensions, attrs, lock=_NETCDF4_LOCK)
             self.attrs = {k: h.getncattr(k) for k in h.ncattrs()}
             return
         with open(path, 'rb') as f:

@@ -385,6 +385,9 @@ class PolylineIntegral(object):
                     if t.dtype != want or not t.is_contiguous():
                         raise ValueError(f'{name} must be a contiguous CUDA tensor of the dtype of uo')
                 pu, pv = _t_ptr(e3u), _t_ptr(e3v)
+                # the host path runs on the handle's own streams: whatever produced e3u/e3v on the caller's stream
+                # must be complete before they are read there
+                torch.cuda.current_stream(e3u.device).synchronize()
             else:
                 e3u, e3v = (numpy.asarray(x.numpy() if isinstance(x, torch.Tensor) else x) for x in (e3u, e3v))
                 for name, x in (('e3u', e3u), ('e3v', e3v)):

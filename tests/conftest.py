@@ -29,3 +29,14 @@ def gpu():
     assert torch.cuda.is_available(), 'a CUDA device is required for -m gpu tests'
     from nemoflux_b200 import nemoflux_gpu
     return nemoflux_gpu
+
+
+@pytest.fixture(autouse=True)
+def _guard_bands(request):
+    """NFX_DEBUG_GUARDS=1 (the stand-in for compute-sanitizer memcheck, which this pool refuses): after every GPU test
+    the guard bands around every device buffer the library owns must be intact"""
+    yield
+    if os.environ.get('NFX_DEBUG_GUARDS', '0') not in ('', '0') and request.node.get_closest_marker('gpu') is not None:
+        from nemoflux_b200 import _lib
+        n = _lib.check_guards()
+        assert n > 0, 'NFX_DEBUG_GUARDS is set but no buffer carries guard bands'

@@ -863,3 +863,42 @@ def test_series_edge_cases(gpu, oracle):
         p.fluxSeries(args[0][:, :, :10], args[1][:, :, :10], *args[2:])         # wrong grid size
     with pytest.raises(TypeError):
         p.fluxSeries(args[0], args[1].cpu(), *args[2:])
+
+
+@pytest.mark.gpu
+def test_guard_bands_catch_an_overrun(gpu):
+    """NFX_DEBUG_GUARDS=1 (the stand-in for compute-sanitizer memcheck on pools that refuse it): a byte written right
+    before or right behind a library-owned device buffer is reported by nfx_debug_check_guards; a clean run passes"""
+    import subprocess
+    import sys
+    from conftest import ROOT
+    code = r'''
+import sys
+sys.path.insert(0, %r)
+import torch
+from nemoflux_b200 import _lib, nemoflux_gpu, synth
+syn = synth.make('tiny')
+g = nemoflux_gpu.Grid(); g.setPoints(syn.points); g.setCGridShape(syn.ny, syn.nx)
+p = nemoflux_gpu.PolylineIntegral(); p.build(g); p.computeWeights(syn.transects)
+dev = torch.device('cuda', 0)
+u, v = syn.fill_device(0, syn.nt, dev)
+s = p.fluxSeries(u, v, *(torch.from_numpy(x).to(dev) for x in (syn.thickness, syn.arc1, syn.arc2)))
+assert torch.isfinite(s).all()
+n = _lib.check_guards()
+assert n >= 10, n
+for where in (0, 1):
+    _lib.call('nfx_debug_poke_guard', where)
+    try:
+        _lib.check_guards()
+    except _lib.NemofluxGpuError as e:
+        assert 'guard bytes overwritten' in str(e) and ('BEFORE the start' if where == 0 else 'PAST the end') in str(e), e
+    else:
+        raise SystemExit('a damaged guard band went unnoticed')
+    break       # the band stays damaged: one direction per process
+print('ok', n)
+''' % ROOT
+    for where_first in (0, 1):
+        c = code if where_first == 0 else code.replace('for where in (0, 1):', 'for where in (1, 0):')
+        out = subprocess.run([sys.executable, '-c', c], capture_output=True, text=True, timeout=300,
+                             env=dict(os.environ, NFX_DEBUG_GUARDS='1'))
+        assert out.returncode == 0 and out.stdout.startswith('ok'), out.stderr[-2000:] + out.stdout[-500:]

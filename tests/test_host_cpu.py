@@ -593,3 +593,85 @@ def test_apportion_by_rate():
         nd.apportion_by_rate(3, [])
     with pytest.raises(ValueError):
         nd.apportion_by_rate(3, [1.0, float('nan')])
+
+
+def test_ncio_decoding_matches_xarray_conventions():
+    """ncio.Variable: scale_factor / add_offset and BOTH missing-value attributes are honoured when decoded values are
+    asked for (xarray.open_dataset's mask_and_scale, which the reference relies on, field.py:22-35); the raw fast path
+    refuses packed data instead of handing out counts as metres per second"""
+    from nemoflux_b200 import ncio
+    raw = numpy.array([[1, 2, -32767], [4, -999, 6]], numpy.int16)
+    v = ncio.Variable('uo', raw, ('y', 'x'), {'scale_factor': numpy.float32(0.01), 'add_offset': numpy.float32(1.5),
+                                              '_FillValue': numpy.int16(-32767), 'missing_value': numpy.int16(-999)})
+    assert v.packed and v.fill_values() == [-32767.0, -999.0]
+    d = v[...]
+    assert d.dtype == numpy.float32
+    assert numpy.isnan(d[0, 2]) and numpy.isnan(d[1, 1])
+    assert numpy.allclose(d[0, :2], [1.51, 1.52]) and numpy.allclose(d[1, ::2], [1.54, 1.56])
+    with pytest.raises(NotImplementedError):
+        v.raw()
+    with pytest.raises(NotImplementedError):
+        v.read_into(numpy.zeros((2, 3), numpy.int16))
+    with pytest.raises(ValueError):
+        v.fill_value()
+    f = ncio.Variable('vo', numpy.array([1.0, 1e20, -9e33, 4.0], numpy.float32), ('x',),
+                      {'_FillValue': numpy.float32(1e20), 'missing_value': numpy.float32(-9e33)})
+    assert not f.packed and numpy.array_equal(numpy.isnan(f[...]), [False, True, True, False])
+    g = ncio.Variable('wo', numpy.array([1.0, 1e20], numpy.float32), ('x',),
+                      {'_FillValue': numpy.float32(1e20), 'missing_value': numpy.float32(1e20)})
+    assert g.fill_value() == float(numpy.float32(1e20)) and numpy.array_equal(g.raw(), [1.0, numpy.float32(1e20)])
+
+
+def test_ncio_serialises_reads_of_a_thread_unsafe_backend():
+    """netCDF4-python releases the GIL around nc_get_vara and libnetcdf / HDF5 are not thread-safe: Variables of that
+    backend carry ncio's process-wide lock, every read takes it, and Field reads them with one worker"""
+    import threading
+    import time
+    from nemoflux_b200 import ncio
+
+    class Unsafe(object):           # raises when two reads overlap
+        shape, dtype = (8, 4), numpy.dtype('f8')
+
+        def __init__(self):
+            self.inside, self.max_inside = 0, 0
+
+        def __getitem__(self, idx):
+            self.inside += 1
+            self.max_inside = max(self.max_inside, self.inside)
+            time.sleep(0.005)
+            self.inside -= 1
+            return numpy.zeros(self.shape)[idx]
+
+    for lock, expect in ((ncio._NETCDF4_LOCK, 1), (None, None)):
+        data = Unsafe()
+        v = ncio.Variable('uo', data, ('t', 'x'), {}, lock=lock)
+        assert v.thread_safe == (lock is None)
+        dst = numpy.zeros((8, 4))
+        ths = [threading.Thread(target=v.read_into, args=(dst[i], i)) for i in range(8)]
+        ths += [threading.Thread(target=v.raw, args=(i,)) for i in range(4)]
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join()
+        if expect is not None:
+            assert data.max_inside == expect
+        else:
+            assert data.max_inside > 1          # the mmap-style backends do read in parallel
+
+
+def test_timeobj_calendars():
+    """CF calendars NEMO commonly runs with: noleap has no 29 February, 360_day has twelve 30-day months"""
+    from nemoflux_b200 import ncio, timeobj
+
+    def tobj(values, calendar):
+        attrs = {'standard_name': 'time', 'units': 'days since 2000-01-01'}
+        if calendar:
+            attrs['calendar'] = calendar
+        return timeobj.TimeObj({'time_counter': ncio.Variable('time_counter', numpy.array(values, numpy.float64), ('t',), attrs)})
+
+    assert tobj([59.0, 60.0], None).getTimeAsString(1) == '2000-3-1'              # 2000 is a leap year: day 59 = 29 Feb
+    assert tobj([59.0, 60.0], None).getTimeAsString(0) == '2000-2-29'
+    assert tobj([59.0, 365.0], 'noleap').getTimeAsString(0) == '2000-3-1'
+    assert tobj([59.0, 365.0], 'noleap').getTimeAsString(1) == '2001-1-1'
+    assert tobj([59.0, 360.0], '360_day').getTimeAsString(0) == '2000-2-30'
+    assert tobj([59.0, 360.0], '360_day').getTimeAsString(1) == '2001-1-1'

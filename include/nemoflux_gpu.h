@@ -73,6 +73,8 @@ extern "C" {
 #define NFX_OPT_FUSED_K3_LAG 15    /* fused pass: the K3 items of batch b - lag are queued behind the K2 tiles of batch b
                                       (0 = automatic: one-panel grids the batches the resident CTAs span + 1, else 1) */
 
+#define NFX_OPT_RING_MAX_MB 16      /* fused pass: upper bound of the whole edge-flux ring in MB (0 = default 24) */
+
 typedef struct nfx_grid nfx_grid;
 typedef struct nfx_pli nfx_pli;
 typedef struct nfx_vinterp nfx_vinterp;

@@ -22,6 +22,7 @@ NFX_OPT_LAST_SERIES_PATH = 8
 NFX_OPT_FUSED_ORDER = 9
 NFX_OPT_FUSED_F64_CTAS = 10
 NFX_OPT_FUSED_K3_LAG = 15
+NFX_OPT_RING_MAX_MB = 16
 
 c_i64 = ctypes.c_int64
 c_int = ctypes.c_int

@@ -41,47 +41,66 @@ void guard_register(void* raw, size_t payload_bytes) {
     g_guards.push_back({raw, payload_bytes});
 }
 
+static int64_t g_guard_checked = 0;        // buffers checked so far (alive at a check, or at their release)
+static int64_t g_guard_damaged_freed = 0;  // damaged buffers found at release time, not yet reported
+static std::string g_guard_freed_report;
+
+// one buffer: true when a guard byte was overwritten (the caller synchronised the device)
+static bool guard_damaged(const GuardRec& g, std::string* report) {
+    const size_t rounded = (g.payload + 255) & ~(size_t)255;
+    const size_t tail = rounded - g.payload + kGuardBytes;
+    std::vector<unsigned char> h(kGuardBytes + tail);
+    unsigned char* b = static_cast<unsigned char*>(g.raw);
+    if (cudaMemcpy(h.data(), b, kGuardBytes, cudaMemcpyDeviceToHost) != cudaSuccess ||
+        cudaMemcpy(h.data() + kGuardBytes, b + kGuardBytes + g.payload, tail, cudaMemcpyDeviceToHost) != cudaSuccess) {
+        cudaGetLastError();
+        return false;   // context gone (interpreter shutdown): nothing to check
+    }
+    int64_t first = -1, count = 0;
+    for (size_t i = 0; i < h.size(); ++i)
+        if (h[i] != 0xA5) {
+            if (first < 0) first = (int64_t)i;
+            ++count;
+        }
+    if (count && report && report->size() < 2000) {
+        const bool head = first < (int64_t)kGuardBytes;
+        *report += "buffer of " + std::to_string(g.payload) + " bytes: " + std::to_string(count) +
+                   " guard bytes overwritten, first " +
+                   (head ? std::to_string((int64_t)kGuardBytes - first) + " bytes BEFORE the start"
+                         : std::to_string(first - (int64_t)kGuardBytes) + " bytes PAST the end") + "; ";
+    }
+    return count != 0;
+}
+
+// a buffer that is freed is checked first: a test that drops its handles before the check must not hide an overrun
 void guard_unregister(void* raw) {
     std::lock_guard<std::mutex> lk(g_guard_mu);
     for (size_t i = 0; i < g_guards.size(); ++i)
         if (g_guards[i].raw == raw) {
+            if (cudaDeviceSynchronize() == cudaSuccess) {
+                ++g_guard_checked;
+                if (guard_damaged(g_guards[i], &g_guard_freed_report)) ++g_guard_damaged_freed;
+            } else {
+                cudaGetLastError();
+            }
             g_guards[i] = g_guards.back();
             g_guards.pop_back();
             return;
         }
 }
 
-// number of library-owned buffers with a damaged guard band (after a device synchronise); details in *report
+// number of library-owned buffers with a damaged guard band (after a device synchronise), buffers freed since the last
+// check included; details in *report.  *nbuffers = buffers checked since the last call.
 static int64_t guard_check_all(std::string* report, int64_t* nbuffers) {
     std::lock_guard<std::mutex> lk(g_guard_mu);
     NFX_CUDA(cudaDeviceSynchronize());
-    int64_t bad = 0;
-    std::vector<unsigned char> h;
-    for (const GuardRec& g : g_guards) {
-        const size_t rounded = (g.payload + 255) & ~(size_t)255;
-        const size_t tail = rounded - g.payload + kGuardBytes;
-        h.resize(kGuardBytes + tail);
-        unsigned char* b = static_cast<unsigned char*>(g.raw);
-        NFX_CUDA(cudaMemcpy(h.data(), b, kGuardBytes, cudaMemcpyDeviceToHost));
-        NFX_CUDA(cudaMemcpy(h.data() + kGuardBytes, b + kGuardBytes + g.payload, tail, cudaMemcpyDeviceToHost));
-        int64_t first = -1, count = 0;
-        for (size_t i = 0; i < h.size(); ++i)
-            if (h[i] != 0xA5) {
-                if (first < 0) first = (int64_t)i;
-                ++count;
-            }
-        if (count) {
-            ++bad;
-            if (report && report->size() < 2000) {
-                const bool head = first < (int64_t)kGuardBytes;
-                *report += "buffer of " + std::to_string(g.payload) + " bytes: " + std::to_string(count) +
-                           " guard bytes overwritten, first " +
-                           (head ? std::to_string((int64_t)kGuardBytes - first) + " bytes BEFORE the start"
-                                 : std::to_string(first - (int64_t)kGuardBytes) + " bytes PAST the end") + "; ";
-            }
-        }
-    }
-    if (nbuffers) *nbuffers = (int64_t)g_guards.size();
+    int64_t bad = g_guard_damaged_freed;
+    if (report) *report += g_guard_freed_report;
+    for (const GuardRec& g : g_guards) bad += guard_damaged(g, report) ? 1 : 0;
+    if (nbuffers) *nbuffers = g_guard_checked + (int64_t)g_guards.size();
+    g_guard_checked = 0;
+    g_guard_damaged_freed = 0;
+    g_guard_freed_report.clear();
     return bad;
 }
 
@@ -262,6 +281,10 @@ int nfx_set_option(int option, int value) {
                 NFX_REQUIRE(value >= 0 && value <= 60, "NFX_OPT_FUSED_K3_LAG must be 0..60");
                 g_fused_k3_lag = value;
                 break;
+            case NFX_OPT_RING_MAX_MB:
+                NFX_REQUIRE(value >= 0 && value <= 120, "NFX_OPT_RING_MAX_MB must be 0..120");
+                g_fused_ring_max_mb = value;
+                break;
             case NFX_OPT_LAST_SERIES_PATH: throw Error(NFX_E_INVALID, "NFX_OPT_LAST_SERIES_PATH is read only");
             case NFX_OPT_FAST_SERIES:
                 NFX_REQUIRE(value >= 0 && value <= 2, "NFX_OPT_FAST_SERIES must be 0, 1 or 2");
@@ -288,6 +311,7 @@ int nfx_get_option(int option, int* value) {
             case NFX_OPT_FUSED_ORDER: *value = g_fused_order; break;
             case NFX_OPT_FUSED_F64_CTAS: *value = g_fused_f64_ctas; break;
             case NFX_OPT_FUSED_K3_LAG: *value = g_fused_k3_lag; break;
+            case NFX_OPT_RING_MAX_MB: *value = g_fused_ring_max_mb; break;
             case NFX_OPT_LAST_SERIES_PATH: *value = g_last_series_fused; break;
             case NFX_OPT_FAST_SERIES: *value = g_fast_series; break;
             case NFX_OPT_RING_SLOT_MB: *value = (int)(g_slot_bytes >> 20); break;

@@ -251,6 +251,7 @@ double probe_read_bandwidth(const void* buf, int64_t nbytes, int reps, double* s
 extern int g_fused_f32_shape;
 extern int g_fused_order;
 extern int g_fused_k3_lag;
+extern int g_fused_ring_max_mb;
 extern int g_fused_f64_ctas;
 int k3_group_for(int64_t nnz, int64_t nrows);
 

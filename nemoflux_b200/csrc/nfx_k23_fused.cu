@@ -29,6 +29,7 @@ namespace nfx {
 
 int g_fused_f32_shape = 0;   // NFX_OPT_FUSED_F32_SHAPE (tuning knob)
 int g_fused_f64_ctas = 0;    // NFX_OPT_FUSED_F64_CTAS (tuning knob): 2 or 4 resident CTAs per SM instead of 3
+int g_fused_ring_max_mb = 0;  // NFX_OPT_RING_MAX_MB: upper bound of the whole ring (0 = 24 MB)
 int g_fused_k3_lag = 0;      // NFX_OPT_FUSED_K3_LAG: 0 = automatic, else the lag of the K3 items in batches
 int g_fused_order = 3;       // NFX_OPT_FUSED_ORDER: bit 0 = visit the batches panel-major, bit 1 = K3 gathers unrolled x8
                              // (same-box A/B, profiles/r1_fused_order_ab.md: -3 % and -1 % time on multi-panel grids)
@@ -473,13 +474,17 @@ void flux_series_fused(PliDev& p, const PanelPlan& pl, const void* u, const void
     NFX_REQUIRE(nz <= 3072, "edgeflux: at most 3072 levels (dz and dz * 2^896 live in 48 KB of shared memory)");
     NFX_REQUIRE((int64_t)(a.nbatches + 64) * (a.ntiles + a.nk3) < 2000000000ll, "fused pass: too many work items");
     // enough slots that every resident CTA finds a K2 tile while the K3 of older batches drains (x2 margin),
-    // but no more than ~64 MB of evict-last lines in the 126 MB L2
+    // but no more than ring_max of evict-last lines in the 126 MB L2
     int ctas = 0;   // 0 = the default register budget of the shape
     if (dtype == NFX_F64 && vec == 4 && (g_fused_f64_ctas == 2 || g_fused_f64_ctas == 4)) ctas = g_fused_f64_ctas;
     if (dtype != NFX_F64 && vec == 4 && unroll == 5 && g_fused_f64_ctas == 3) ctas = 3;
     const int resident = e3 ? fused_grid_e3(dtype, vec) : fused_grid_for(dtype, vec, unroll, ctas);
     int slots = (2 * resident + a.ntiles - 1) / a.ntiles + 1;
-    const int64_t cap = std::max<int64_t>(3, ((int64_t)64 << 20) / (a.slot_elems * 8));
+    // the whole ring stays under 24 MB: beyond that (32 MB: float32 storage on ORCA12, 4 slots of 8 MB) L2 starts writing
+    // the evict-last lines back to HBM -- ncu: 228 MB of DRAM writes per 2 time steps -- and the pass loses 2.5 %
+    // (profiles/r2_fused_experiments.md)
+    const int64_t ring_max = (int64_t)(g_fused_ring_max_mb > 0 ? g_fused_ring_max_mb : 24) << 20;
+    const int64_t cap = std::max<int64_t>(3, ring_max / (a.slot_elems * 8));
     slots = (int)std::min<int64_t>(std::max(slots, 3), cap);
     // lag of the K3 items.  One-panel grids (a batch = a whole time step, fewer tiles than resident CTAs): the batches
     // the resident CTAs span + 1, so that a batch's tiles have all FINISHED, not just been handed out, when its K3

@@ -38,5 +38,4 @@ def _guard_bands(request):
     yield
     if os.environ.get('NFX_DEBUG_GUARDS', '0') not in ('', '0') and request.node.get_closest_marker('gpu') is not None:
         from nemoflux_b200 import _lib
-        n = _lib.check_guards()
-        assert n > 0, 'NFX_DEBUG_GUARDS is set but no buffer carries guard bands'
+        _lib.check_guards()        # raises when a band is damaged; buffers freed during the test were checked at release

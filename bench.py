@@ -58,6 +58,8 @@ def parse_args():
     ap.add_argument('--balance', action='store_true',
                     help='shard at (time step, panel of cells) granularity so that every rank gets the same number of '
                          'batches (73 snapshots over 8 GPUs: 9.125 steps each instead of 10,9,..,9); single chunk only')
+    ap.add_argument('--no-rate-balance', action='store_true',
+                    help='--balance: equal batch counts per rank instead of counts proportional to the measured rates')
     ap.add_argument('--dtype', default='f64', choices=['f64', 'f32'], help='storage type of uo/vo (compute is f64)')
     ap.add_argument('--e2e-steps', type=int, default=0, help='time steps of the host-buffer (e2e) sample, all ranks together')
     ap.add_argument('--cpu-steps', type=int, default=0, help='time steps of the cpu_baseline / reference-arm sample')
@@ -401,7 +403,7 @@ def run_passes(cx, args, wl, nt_total, t0_rank, nt_local, counts, steps, warmup,
     series_pad = torch.zeros((cmax, M), dtype=torch.float64, device=cx.dev)       # padded to the largest shard
     gathered = torch.empty((world * cmax, M), dtype=torch.float64, device=cx.dev) if world > 1 else None
     full_series = torch.zeros((nt_total, M), dtype=torch.float64, device=cx.dev) if bal is not None else None
-    shards_all = [nfx_dist.shard_batches(nt_total, bal['npanels'], world, r) for r in range(world)] if bal else None
+    shards_all = [nfx_dist.shard_batches(nt_total, bal['npanels'], world, r, bal.get('weights')) for r in range(world)] if bal else None
     resident = [-1]
 
     def load_chunk(ci):
@@ -582,7 +584,7 @@ def parity_check(cx, args, wl, res, t0_rank, nt_local):
                 iV, _, _ = O.edgeflux_step_c(uh, vh, syn.thickness, syn.arc1, syn.arc2, False)
                 del uh, vh
                 f = iV.reshape(-1)
-                row = res['own_series'][off]
+                row = res['series'][t0_rank + off]     # the gathered series: complete also where ranks share a time step
                 for m, op in enumerate(oplis):
                     keys, ws = op.merged_map()
                     sc = float(numpy.abs(ws * f[keys]).sum())
@@ -633,8 +635,8 @@ def e2e_legs(cx, args, wl):
     step_bytes = 16 * units
     if args.e2e_steps > 0:
         E = args.e2e_steps
-    else:   # about 3.5 GB (C3) .. 7 GB (C4) of pinned memory per rank on average
-        E = world * max(1, min(24, int(round(7.1e9 / step_bytes)))) if world > 1 else max(1, min(24, int(5.2e9 // step_bytes)))
+    else:   # about 3.5 GB (C3) .. 9 GB (C4: 5 time steps) of pinned memory per rank on average: enough steps to apportion
+        E = world * max(1, min(24, int(round(8.9e9 / step_bytes)))) if world > 1 else max(1, min(24, int(5.2e9 // step_bytes)))
     rate = nfx_dist.measure_h2d_rate(cx.dev)
     rates = cx.allgather_floats(rate)
     eq_counts = nfx_dist.shard_counts(E, world)
@@ -749,13 +751,30 @@ def run_config(cx, args, name, nt_total, scaling, steps, warmup, balance, with_e
         counts = nfx_dist.shard_counts(nt_total, world)
         t0_rank, nt_local = nfx_dist.shard_time(nt_total, world, rank)
     bal = None
+    rate_weights = None
     if balance and world > 1:
         npanels, _pc = wl.pli.getNumberOfPanels(args.dtype)
-        bal = nfx_dist.shard_batches(nt_total, npanels, world, rank)
-        bal['npanels'] = npanels
-        t0_rank, nt_local = bal['t_first'], bal['nt_touched']
-        counts = [nfx_dist.shard_batches(nt_total, npanels, world, r)['nt_touched'] for r in range(world)]
         _lib.set_option(_lib.NFX_OPT_FAST_SERIES, 2)
+
+        def shard(weights):
+            b = nfx_dist.shard_batches(nt_total, npanels, world, rank, weights)
+            b['npanels'], b['weights'] = npanels, weights
+            cnt = [nfx_dist.shard_batches(nt_total, npanels, world, r, weights)['nt_touched'] for r in range(world)]
+            return b, cnt
+        bal, counts = shard(None)
+        if not args.no_rate_balance:
+            # the GPUs of one box differ by a few per cent in sustained rate (shared power budget): time a few passes
+            # with equal shares, then cut the batch space in proportion to each rank's measured rate (outside the
+            # timed region, like the H2D probe of the e2e leg)
+            probe = run_passes(cx, args, wl, nt_total, bal['t_first'], bal['nt_touched'], counts, 3, 3, bal)
+            own_batches = bal['b1'] - bal['b0']
+            rate = own_batches / max(probe['k2_ms_step'], 1e-9)
+            probe.clear()
+            torch.cuda.empty_cache()
+            rates = cx.allgather_floats(rate)
+            rate_weights = [r / max(rates) for r in rates]
+            bal, counts = shard(rate_weights)
+        t0_rank, nt_local = bal['t_first'], bal['nt_touched']
     res = run_passes(cx, args, wl, nt_total, t0_rank, nt_local, counts, steps, warmup, bal)
     clocks = None
     if sampler is not None and rank == 0:
@@ -813,6 +832,7 @@ def run_config(cx, args, name, nt_total, scaling, steps, warmup, balance, with_e
                          f'{len(chunks)} resident chunks per rank, regenerated on the device between chunk passes outside '
                          f'the timed region; step time = sum over chunk passes of the max-over-ranks CUDA-event time'),
             'device_layout': f'(nt, nz, ld={ld}) level planes padded to 32 B' if padded else '(nt, nz, ny, nx) dense',
+            'batch_shares_by_measured_rate': rate_weights,
             'summation_order': args.order, 'allgather_ms': keep['gather_ms'],
             'pass': 'classic: K2 -> eflux in HBM -> K3 (two launches)' if args.classic else
                     'PolylineIntegral.fluxSeries (nfx_flux_series, eflux=NULL): fused persistent K2+K3 with the edge '

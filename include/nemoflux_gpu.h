@@ -225,6 +225,24 @@ int nfx_flux_series_range_e3(nfx_pli** self, const void* u, const void* v, const
                              int e3_nt, const double* arc1, const double* arc2, int nt, int nz, int64_t ld, int sverdrup,
                              double fill, int order, int64_t batch_begin, int64_t batch_end, double* series,
                              void* stream);
+/* Chunked NetCDF-4 / HDF5 variables decoded on the device, behind the host-to-device copy of the COMPRESSED bytes
+ * (what subsetNEMO.py:78 `zlib=True` and NEMO's XIOS output produce; the reference inflates them on one host thread
+ * inside netCDF4/HDF5, field.py:22-35,149).  comp: device buffer holding the chunks as stored in the file, chunk c at
+ * byte offset in_off[c] (a multiple of 16), in_size[c] bytes; in_off / in_size / chunk_start are HOST arrays.
+ * filters: NFX_H5_DEFLATE (zlib stream per chunk, RFC 1950/1951: stored, fixed and dynamic blocks; Adler-32 verified),
+ * NFX_H5_SHUFFLE (byte planes -> elements), NFX_H5_FLETCHER32 (the 4-byte trailer is dropped, not verified).
+ * chunk_dims / dst_dims: extents (rank <= 4) of a chunk and of the destination array, a dense C-order array of
+ * elem_size-byte elements at dst; chunk_start[c*rank + d] = index in dst of the chunk's first element along d (may be
+ * negative / beyond the end: elements outside dst -- the padding of edge chunks, time steps outside the slab -- are
+ * dropped).  swap_bytes != 0 reverses the bytes of every element (big-endian data).  status (host, nchunks, may be
+ * NULL): 0 or the reason a chunk was rejected; any rejected chunk makes the call return NFX_E_INVALID.  Synchronises
+ * `stream` before returning. */
+#define NFX_H5_DEFLATE 1
+#define NFX_H5_SHUFFLE 2
+#define NFX_H5_FLETCHER32 4
+int nfx_h5_decode_chunks(const void* comp, int64_t comp_bytes, int64_t nchunks, const int64_t* in_off, const int64_t* in_size,
+                         int filters, int elem_size, int rank, const int64_t* chunk_dims, const int64_t* dst_dims,
+                         const int64_t* chunk_start, int swap_bytes, void* dst, int32_t* status, void* stream);
 /* Threading / stream rules (as for a libmint handle: single-threaded, not re-entrant): a handle owns scratch (ring,
  * partial sums, counters, staging buffers) that every call on it re-uses, so calls on ONE handle must be issued from
  * one thread and one stream at a time; different handles are independent.  The host-buffer entry points below run on

@@ -13,6 +13,7 @@ NFX_OK = 0
 NFX_CELL_BY_CELL_DATA = 0
 NFX_F64, NFX_F32 = 0, 1
 NFX_BIG_ENDIAN = 0x100
+NFX_H5_DEFLATE, NFX_H5_SHUFFLE, NFX_H5_FLETCHER32 = 1, 2, 4
 NFX_ORDER_LIST, NFX_ORDER_MAP = 0, 1
 NFX_K2_AUTO, NFX_K2_LDG, NFX_K2_TMA, NFX_K2_LDG128 = 0, 1, 2, 3
 NFX_OPT_K2_VARIANT, NFX_OPT_K2_UNROLL, NFX_OPT_K2_BLOCK, NFX_OPT_FAST_SERIES, NFX_OPT_RING_SLOT_MB = 1, 2, 3, 4, 5
@@ -84,6 +85,7 @@ SIGNATURES = {
     'nfx_pli_get_num_panels_dtype': [P(c_vp), c_int, P(c_int), P(c_i64)],
     'nfx_pli_series_status': [P(c_vp), c_vp, P(c_int)],
     'nfx_probe_read_bandwidth': [c_vp, c_i64, c_int, P(c_dbl), c_vp],
+    'nfx_h5_decode_chunks': [c_vp, c_i64, c_i64, c_vp, c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_vp],
     'nfx_flux_series_range': [P(c_vp), c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_int, c_i64, c_int, c_dbl, c_int,
                               c_i64, c_i64, c_vp, c_vp],
     'nfx_flux_series_range_e3': [P(c_vp), c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_vp, c_int, c_int, c_i64, c_int,

@@ -813,6 +813,17 @@ int nfx_pli_series_status(nfx_pli** self, void* stream, int* status) {
     });
 }
 
+int nfx_h5_decode_chunks(const void* comp, int64_t comp_bytes, int64_t nchunks, const int64_t* in_off, const int64_t* in_size,
+                         int filters, int elem_size, int rank, const int64_t* chunk_dims, const int64_t* dst_dims,
+                         const int64_t* chunk_start, int swap_bytes, void* dst, int32_t* status, void* stream) {
+    return guarded([&] {
+        int dev;
+        require_gpu(&dev);
+        h5_decode_chunks(comp, comp_bytes, nchunks, in_off, in_size, filters, elem_size, rank, chunk_dims, dst_dims,
+                         chunk_start, swap_bytes, dst, status, (cudaStream_t)stream);
+    });
+}
+
 int nfx_probe_read_bandwidth(const void* buf, int64_t nbytes, int reps, double* gbs, void* stream) {
     return guarded([&] {
         int dev;

@@ -247,6 +247,10 @@ int fused_tile_columns(int dtype, const void* u, const void* v, int64_t ncell, i
                        uintptr_t more_bits = 0);
 int fused_error_flag(PliDev& p, cudaStream_t s);
 void fused_check_sticky_error(PliDev& p);   // throws if a fused pass launched earlier on this handle aborted
+void h5_decode_chunks(const void* comp_dev, int64_t comp_bytes, int64_t nchunks, const int64_t* in_off,
+                      const int64_t* in_size, int filters, int elem_size, int rank, const int64_t* chunk_dims,
+                      const int64_t* dst_dims, const int64_t* chunk_start, int swap_bytes, void* dst_dev,
+                      int32_t* status_host, cudaStream_t s);   // nfx_inflate.cu
 double probe_read_bandwidth(const void* buf, int64_t nbytes, int reps, double* sink, cudaStream_t s);   // nfx_probe.cu
 extern int g_fused_f32_shape;
 extern int g_fused_order;

@@ -56,20 +56,38 @@ def allgather_series(local, nt, group=None):
     return torch.cat([out[r * cmax:r * cmax + counts[r]] for r in range(world)], dim=0)
 
 
-def shard_batches(nt, npanels, world, rank):
+def batch_bounds(total, world, weights=None):
+    """world + 1 boundaries cutting `total` batches into contiguous ranges: equal (+-1) by default, proportional to
+    `weights` (each rank's measured throughput) when given -- GPUs of one box differ by a few per cent in sustained
+    HBM rate under a shared power budget, and the slowest one sets the time of a max-over-ranks pass"""
+    total = int(total)
+    if weights is None:
+        base, rem = divmod(total, world)
+        return [r * base + min(r, rem) for r in range(world)] + [total]
+    w = numpy.asarray(weights, dtype=numpy.float64)
+    if w.shape != (world,) or not numpy.all(numpy.isfinite(w)) or numpy.any(w <= 0):
+        raise ValueError('weights must be `world` positive finite numbers')
+    cum = numpy.concatenate([[0.0], numpy.cumsum(w)]) / w.sum()
+    b = [int(round(total * c)) for c in cum]
+    b[0], b[-1] = 0, total
+    for r in range(1, world + 1):           # monotone
+        b[r] = max(b[r], b[r - 1])
+    return b
+
+
+def shard_batches(nt, npanels, world, rank, weights=None):
     """Balanced sharding at (time step, panel of cells) granularity.
 
     The flattened batch space b = t*npanels + q (nt*npanels batches) is cut into `world` contiguous ranges of
     equal length (+-1 batch): 73 snapshots x 26 panels over 8 ranks -> 237 or 238 batches = 9.125 time steps each
-    instead of 10,9,...,9.  Returns dict(t_first, nt_touched, b0, b1): the rank needs the time steps
-    t_first .. t_first+nt_touched-1 in memory and runs the LOCAL batch range [b0, b1) (indices relative to
-    t_first*npanels) with PolylineIntegral.fluxSeries(batch_range=(b0, b1))."""
+    instead of 10,9,...,9 -- or, with `weights`, of lengths proportional to each rank's measured rate.  Returns
+    dict(t_first, nt_touched, b0, b1): the rank needs the time steps t_first .. t_first+nt_touched-1 in memory and
+    runs the LOCAL batch range [b0, b1) (indices relative to t_first*npanels) with
+    PolylineIntegral.fluxSeries(batch_range=(b0, b1))."""
     if world <= 0 or not (0 <= rank < world):
         raise ValueError(f'bad rank {rank} of {world}')
-    total = int(nt) * int(npanels)
-    base, rem = divmod(total, world)
-    g0 = rank * base + min(rank, rem)
-    g1 = g0 + base + (1 if rank < rem else 0)
+    bounds = batch_bounds(int(nt) * int(npanels), world, weights)
+    g0, g1 = bounds[rank], bounds[rank + 1]
     if g1 == g0:
         return dict(t_first=0, nt_touched=0, b0=0, b1=0, g0=g0, g1=g1)
     t_first = g0 // npanels
@@ -78,7 +96,7 @@ def shard_batches(nt, npanels, world, rank):
                 b1=g1 - t_first * npanels, g0=g0, g1=g1)
 
 
-def combine_partial_series(partial, nt, npanels, group=None):
+def combine_partial_series(partial, nt, npanels, group=None, weights=None):
     """partial: this rank's (nt_touched, M) partial sums from fluxSeries(batch_range=...) for its shard_batches
     range -> the full (nt, M) series on every rank.  One all_gather of the (padded) partial blocks; a time step
     shared by several ranks is summed in rank order (deterministic)."""
@@ -88,7 +106,7 @@ def combine_partial_series(partial, nt, npanels, group=None):
         world, rank = dist.get_world_size(group), dist.get_rank(group)
     else:
         world, rank = 1, 0
-    shards = [shard_batches(nt, npanels, world, r) for r in range(world)]
+    shards = [shard_batches(nt, npanels, world, r, weights) for r in range(world)]
     need = shards[rank]['nt_touched']
     if partial.shape[0] != need:
         raise ValueError(f'rank {rank} must hold {need} time steps, got {partial.shape[0]}')

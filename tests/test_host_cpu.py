@@ -675,3 +675,30 @@ def test_timeobj_calendars():
     assert tobj([59.0, 365.0], 'noleap').getTimeAsString(1) == '2001-1-1'
     assert tobj([59.0, 360.0], '360_day').getTimeAsString(0) == '2000-2-30'
     assert tobj([59.0, 360.0], '360_day').getTimeAsString(1) == '2001-1-1'
+
+
+def test_weighted_batch_sharding_tiles_the_batch_space():
+    """dist.shard_batches(weights=): contiguous ranges proportional to each rank's measured rate that tile the
+    (time step, panel) space exactly; equal weights reproduce the unweighted cut"""
+    from nemoflux_b200 import dist as nd
+    nt, npanels, world = 73, 51, 8
+    for weights in (None, [1.0] * 8, [1.0, 0.97, 1.0, 0.95, 1.0, 1.0, 0.98, 1.0], [3.0, 1, 1, 1, 1, 1, 1, 1]):
+        covered = numpy.zeros(nt * npanels, int)
+        sizes = []
+        for r in range(world):
+            s = nd.shard_batches(nt, npanels, world, r, weights)
+            covered[s['g0']:s['g1']] += 1
+            sizes.append(s['g1'] - s['g0'])
+            assert s['t_first'] * npanels + s['b0'] == s['g0'] and s['t_first'] * npanels + s['b1'] == s['g1']
+            assert s['nt_touched'] == (s['g1'] - 1) // npanels - s['g0'] // npanels + 1
+        assert (covered == 1).all()
+        if weights is not None:
+            w = numpy.array(weights) / sum(weights)
+            assert numpy.abs(numpy.array(sizes) - w * nt * npanels).max() <= 1.0
+    for r in range(world):          # equal weights: the unweighted cut up to the rounding of a boundary
+        a, b = nd.shard_batches(nt, npanels, world, r), nd.shard_batches(nt, npanels, world, r, [2.0] * 8)
+        assert abs(a['g0'] - b['g0']) <= 1 and abs(a['g1'] - b['g1']) <= 1
+    with pytest.raises(ValueError):
+        nd.shard_batches(nt, npanels, world, 0, [1.0] * 7)
+    with pytest.raises(ValueError):
+        nd.batch_bounds(10, 2, [1.0, 0.0])

@@ -326,11 +326,10 @@ k_inflate(const Job* __restrict__ jobs, long long njobs, int* __restrict__ statu
                 }
                 if (!err && L[19 + 256] == 0) err = kInfBadCode;   // no end-of-block code
                 if (!err) {
+                    unsigned char d[30];   // the distance lengths first: their place overlaps what is cleared below
+                    for (int k = 0; k < ndist; ++k) d[k] = L[19 + nlit + k];
                     for (int k = 0; k < nlit; ++k) L[k] = L[19 + k];
                     for (int k = nlit; k < 288; ++k) L[k] = 0;
-                    // distances: move to 288.. (source index 19 + nlit + k >= 288 + k - ... may overlap: go through a copy)
-                    unsigned char d[30];
-                    for (int k = 0; k < ndist; ++k) d[k] = L[19 + nlit + k];
                     for (int k = 0; k < 30; ++k) L[288 + k] = k < ndist ? d[k] : 0;
                 }
             }

@@ -99,6 +99,45 @@ class Dataset(object):
         return out
 
 
+    # ---- what a device-side decoder needs (nemoflux_b200.nemoflux_gpu.H5DeviceReader) ------------------------------
+    def device_filter_flags(self):
+        """bit mask (1 deflate, 2 shuffle, 4 fletcher32) when the filter pipeline is what nfx_h5_decode_chunks undoes --
+        [shuffle,] [deflate,] [fletcher32] in this order, shuffling whole elements --, else None"""
+        flags, order = 0, []
+        for fid, cdata in self._filters:
+            if fid == 1:
+                flags |= 1
+            elif fid == 2 and (not cdata or cdata[0] == self.dtype.itemsize):
+                flags |= 2
+            elif fid == 3:
+                flags |= 4
+            else:
+                return None
+            order.append(fid)
+        return flags if order == sorted(order, key=lambda f: {2: 0, 1: 1, 3: 2}[f]) else None
+
+    def chunk_plan(self, starts, stops):
+        """chunks of a chunked dataset that overlap the block [starts, stops): list of (file offset, bytes, filter
+        mask, chunk origin in the dataset); the chunk extents are self.chunk_dims"""
+        if self._layout[0] != 'chunked':
+            raise H5Error(f'{self.name}: not a chunked dataset')
+        addr, cdims = self._layout[1], self._layout[2]
+        rank = len(self.shape)
+        if addr == UNDEF:
+            return []
+        if self._chunks is None:
+            self._chunks = self._f._chunk_btree(addr, rank)
+        out = []
+        for offsets, nbytes, mask, caddr in self._chunks:
+            if all(max(offsets[d], starts[d]) < min(offsets[d] + cdims[d], stops[d], self.shape[d]) for d in range(rank)):
+                out.append((self._f._base + caddr, nbytes, mask, tuple(offsets[:rank])))
+        return out
+
+    @property
+    def chunk_dims(self):
+        return tuple(self._layout[2]) if self._layout[0] == 'chunked' else None
+
+
 def unshuffle(raw, size, n):
     """HDF5 shuffle filter reversed: `size` planes of n bytes (all first bytes, all second bytes, ...) -> n elements of
     `size` bytes.  For 2/4/8-byte elements the planes are widened and OR-ed together as little-endian integers --

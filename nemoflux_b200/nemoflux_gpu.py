@@ -570,6 +570,127 @@ def edgeFluxToCellByCell(eflux, ny, nx, out=None):
     return out
 
 
+def h5DecodeChunks(comp, in_off, in_size, filters, chunk_dims, dst, chunk_start, swap_bytes=False):
+    """chunked NetCDF-4 / HDF5 data decoded on the device (C ABI nfx_h5_decode_chunks): comp = cuda uint8 tensor with
+    the chunks as stored in the file (chunk c at byte in_off[c], a multiple of 16, in_size[c] bytes), filters = bit mask
+    of NFX_H5_DEFLATE / SHUFFLE / FLETCHER32, chunk_dims = extents of a chunk, dst = dense cuda tensor the chunks are
+    placed into (its shape has the rank of chunk_dims), chunk_start (nchunks, rank) = index in dst of every chunk's first
+    element.  Returns the per-chunk status array (all 0); raises NemofluxGpuError when a chunk is not a valid stream."""
+    torch = _torch()
+    if not (isinstance(comp, torch.Tensor) and comp.is_cuda and comp.dtype == torch.uint8 and comp.is_contiguous()):
+        raise TypeError('comp must be a contiguous CUDA uint8 tensor')
+    if not (isinstance(dst, torch.Tensor) and dst.is_cuda and dst.is_contiguous() and dst.device == comp.device):
+        raise TypeError('dst must be a contiguous CUDA tensor on the device of comp')
+    off = numpy.ascontiguousarray(in_off, numpy.int64).reshape(-1)
+    size = numpy.ascontiguousarray(in_size, numpy.int64).reshape(-1)
+    cdims = numpy.ascontiguousarray(chunk_dims, numpy.int64).reshape(-1)
+    rank = cdims.size
+    if dst.dim() != rank:
+        raise ValueError(f'dst has {dst.dim()} dimensions, the chunks {rank}')
+    ddims = numpy.array(dst.shape, numpy.int64)
+    start = numpy.ascontiguousarray(chunk_start, numpy.int64).reshape(-1, rank)
+    if not (off.size == size.size == start.shape[0]):
+        raise ValueError('in_off, in_size and chunk_start must describe the same number of chunks')
+    status = numpy.zeros(max(off.size, 1), numpy.int32)
+    with torch.cuda.device(comp.device):
+        _lib.call('nfx_h5_decode_chunks', _t_ptr(comp), int(comp.numel()), int(off.size), _np_ptr(off), _np_ptr(size),
+                  int(filters), int(dst.element_size()), rank, _np_ptr(cdims), _np_ptr(ddims), _np_ptr(start),
+                  int(bool(swap_bytes)), _t_ptr(dst), _np_ptr(status), _stream_ptr())
+    return status[:off.size]
+
+
+class H5DeviceReader(object):
+    """Blocks of a chunked (deflate / shuffle) HDF5 variable read straight onto the GPU: the COMPRESSED chunks are
+    copied from the memory-mapped file into a pinned staging buffer, cross PCIe as stored and are inflated, unshuffled
+    and placed by nfx_h5_decode_chunks -- the decompression the reference leaves to one host thread inside
+    netCDF4 / HDF5 (field.py:22-35, 149; subsetNEMO.py:78 writes zlib=True).
+
+        rd = H5DeviceReader(ds, device)        # ds: nemoflux_b200.h5lite.Dataset, chunked
+        block = rd.read(starts, stops)         # cuda tensor of shape stops - starts, native byte order
+    """
+
+    def __init__(self, ds, device, workers=4):
+        torch = _torch()
+        self.ds, self.device = ds, torch.device(device)
+        self.flags = ds.device_filter_flags()
+        if ds.chunk_dims is None or self.flags is None:
+            raise ValueError(f'{ds.name}: not a chunked variable with a [shuffle,] [deflate,] [fletcher32] pipeline')
+        if ds.dtype.kind != 'f' or ds.dtype.itemsize not in (4, 8):
+            raise ValueError(f'{ds.name}: float32 / float64 variables only')
+        self.tdtype = torch.float32 if ds.dtype.itemsize == 4 else torch.float64
+        self.swap = not ds.dtype.isnative
+        self.workers = max(1, int(workers))
+        self._pinned = None
+        self._dev = None
+        self.bytes_compressed = 0          # running totals, for the caller's report
+        self.bytes_decoded = 0
+
+    def stage(self, starts, stops):
+        """host half: the chunks under [starts, stops) copied into the pinned staging buffer; returns the plan the
+        device half (decode) takes.  Runs without the GIL for the copies, so a reader thread can prepare block i + 1
+        while block i is decoded."""
+        torch = _torch()
+        plan = self.ds.chunk_plan(starts, stops)
+        offs, pos = [], 0
+        for _addr, nbytes, _mask, _org in plan:
+            offs.append(pos)
+            pos += (nbytes + 15) & ~15
+        total = pos + 4096                                      # the decoder may look a little past the last stream
+        if self._pinned is None or self._pinned.numel() < total:
+            self._pinned = torch.empty(int(total * 1.25) + 4096, dtype=torch.uint8, pin_memory=True)
+        hbuf = self._pinned.numpy()
+        fbuf = numpy.frombuffer(self.ds._f._buf, numpy.uint8)
+
+        def copy(lo, hi):
+            for k in range(lo, hi):
+                addr, nbytes = plan[k][0], plan[k][1]
+                hbuf[offs[k]:offs[k] + nbytes] = fbuf[addr:addr + nbytes]
+        if len(plan) >= 2 * self.workers and self.workers > 1:
+            from concurrent.futures import ThreadPoolExecutor
+            step = -(-len(plan) // self.workers)
+            with ThreadPoolExecutor(self.workers) as pool:
+                list(pool.map(lambda lo: copy(lo, min(len(plan), lo + step)), range(0, len(plan), step)))
+        else:
+            copy(0, len(plan))
+        return dict(plan=plan, offs=offs, total=total, starts=list(starts), stops=list(stops))
+
+    def decode(self, staged, out=None):
+        """device half: H2D of the staged bytes, inflate + unshuffle + placement; returns the cuda tensor"""
+        torch = _torch()
+        plan, offs, total = staged['plan'], staged['offs'], staged['total']
+        shape = [b - a for a, b in zip(staged['starts'], staged['stops'])]
+        if out is None:
+            out = torch.empty(shape, dtype=self.tdtype, device=self.device)
+        if self.ds.fill is not None:
+            out.fill_(float(numpy.frombuffer(self.ds.fill, self.ds.dtype, 1)[0]))
+        else:
+            out.zero_()
+        if not plan:
+            return out
+        if self._dev is None or self._dev.numel() < total:
+            self._dev = torch.empty(self._pinned.numel(), dtype=torch.uint8, device=self.device)
+        self._dev[:total].copy_(self._pinned[:total], non_blocking=True)
+        nfilters = len(self.ds._filters)
+        groups = {}
+        for k, (_addr, nbytes, mask, org) in enumerate(plan):   # a chunk may have skipped filters (its mask bits)
+            flags = 0
+            for i, (fid, _cd) in enumerate(self.ds._filters):
+                if not (mask >> i) & 1:
+                    flags |= {1: _lib.NFX_H5_DEFLATE, 2: _lib.NFX_H5_SHUFFLE, 3: _lib.NFX_H5_FLETCHER32}[fid]
+            groups.setdefault(flags, []).append(k)
+        del nfilters
+        for flags, ks in groups.items():
+            start = [[plan[k][3][d] - staged['starts'][d] for d in range(len(shape))] for k in ks]
+            h5DecodeChunks(self._dev[:total], [offs[k] for k in ks], [plan[k][1] for k in ks], flags, self.ds.chunk_dims,
+                           out, start, swap_bytes=self.swap)
+        self.bytes_compressed += sum(p[1] for p in plan)
+        self.bytes_decoded += out.numel() * out.element_size()
+        return out
+
+    def read(self, starts, stops, out=None):
+        return self.decode(self.stage(starts, stops), out=out)
+
+
 def probeReadBandwidth(buf, reps=5):
     """read-only HBM ceiling (GB/s) of the device of `buf` (a CUDA tensor of >= 9.3 GB whose contents do not matter)
     with the access pattern of the edge-flux kernels -- the denominator bench.py quotes next to the copy peak"""

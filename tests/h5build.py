@@ -72,7 +72,7 @@ def write(path, variables):
             if shuffle:
                 raw = numpy.frombuffer(raw, numpy.uint8).reshape(-1, data.dtype.itemsize).T.tobytes()
             if deflate:
-                raw = zlib.compress(raw, 5)
+                raw = zlib.compress(raw, deflate if type(deflate) is int else 5)
             items.append((tuple(int(o) for o in offs), len(raw), put(raw)))
 
         def node(level, entries, last_key):
@@ -310,7 +310,7 @@ def _chunk_tree_into(buf, data, cdims, deflate, shuffle):
         if shuffle:
             raw = numpy.frombuffer(raw, numpy.uint8).reshape(-1, data.dtype.itemsize).T.tobytes()
         if deflate:
-            raw = zlib.compress(raw, 5)
+            raw = zlib.compress(raw, deflate if type(deflate) is int else 5)
         items.append((tuple(int(o) for o in offs), len(raw), put(raw)))
 
     def node(level, entries, last_key):

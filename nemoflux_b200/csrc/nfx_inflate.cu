@@ -6,11 +6,13 @@
 // COMPRESSED chunk bytes cross PCIe as stored and are decoded on the GPU:
 //
 //   k_inflate   one warp per chunk (chunks are independent zlib streams, RFC 1950 / 1951).  Lane 0 runs the Huffman state
-//               machine -- bit buffer fed from a 1 KB window of the input that the warp refills cooperatively into shared
+//               machine -- bit buffer fed from a 2 KB window of the input that the warp refills cooperatively into shared
 //               memory, 10-bit / 8-bit direct lookup tables per block with a canonical bit-by-bit decode for longer
 //               codes -- and decodes runs of literals on its own; every match (length, distance) is broadcast and copied
-//               by all 32 lanes.  Stored, fixed and dynamic blocks.  Output: the chunk as the filter pipeline left it
-//               (shuffled), in a scratch buffer.
+//               by all 32 lanes.  The output goes through a 4 KB window in shared memory (matches up to 2.5 KB back never
+//               leave it: shared-memory latency in the decoder's dependency chain instead of an L2 round trip per match)
+//               and reaches global memory in 1 KB pieces written by the whole warp.  Stored, fixed and dynamic blocks.
+//               Output: the chunk as the filter pipeline left it (shuffled), in a scratch buffer.
 //   k_unshuffle undoes the HDF5 shuffle filter (byte planes -> elements), verifies nothing it cannot (see status) and
 //               writes the elements to their place in the destination slab; edge chunks are clipped.  Coalesced.
 //
@@ -26,6 +28,11 @@ namespace {
 constexpr int kInfWarps = 4;        // chunks (warps) per CTA
 constexpr int kInRing = 2048;       // bytes of the input window in shared memory (two halves)
 constexpr int kInHalf = kInRing / 2; // >= the longest dynamic block header (about 570 bytes)
+constexpr int kWin = 4096;          // output window in shared memory per warp
+constexpr int kFlush = 1024;        // ... written to the chunk in pieces of this size
+constexpr int kNear = kWin - 258 - kFlush - 258;   // matches up to this far back are copied inside the window: their source is
+                                    // neither overwritten by the copy (258 bytes) nor by what lane 0 may have written since the
+                                    // last flush (< kFlush + 258)
 constexpr int kLitBits = 10;        // direct lookup of literal/length codes up to this length
 constexpr int kDistBits = 8;
 
@@ -41,17 +48,21 @@ enum InflateStatus {
     kInfBadAdler = 8,      // Adler-32 of the output differs from the trailer
 };
 
-__constant__ unsigned short c_len_base[29] = {3,  4,  5,  6,  7,  8,  9,  10, 11,  13,  15,  17,  19,  23, 27,
-                                              31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
-__constant__ unsigned char c_len_extra[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
-__constant__ unsigned short c_dist_base[30] = {1,   2,   3,   4,   5,   7,    9,    13,   17,   25,   33,   49,   65,    97,    129,
-                                               193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
-__constant__ unsigned char c_dist_extra[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
+// base | extra bits << 16: one constant load per length / distance symbol
+__constant__ unsigned c_len_tab[29] = {
+    3 | 0 << 16,  4 | 0 << 16,  5 | 0 << 16,  6 | 0 << 16,  7 | 0 << 16,  8 | 0 << 16,  9 | 0 << 16,   10 | 0 << 16,  11 | 1 << 16, 13 | 1 << 16,
+    15 | 1 << 16, 17 | 1 << 16, 19 | 2 << 16, 23 | 2 << 16, 27 | 2 << 16, 31 | 2 << 16, 35 | 3 << 16,  43 | 3 << 16,  51 | 3 << 16, 59 | 3 << 16,
+    67 | 4 << 16, 83 | 4 << 16, 99 | 4 << 16, 115 | 4 << 16, 131 | 5 << 16, 163 | 5 << 16, 195 | 5 << 16, 227 | 5 << 16, 258 | 0 << 16};
+__constant__ unsigned c_dist_tab[30] = {
+    1 | 0 << 16,    2 | 0 << 16,    3 | 0 << 16,    4 | 0 << 16,     5 | 1 << 16,     7 | 1 << 16,     9 | 2 << 16,     13 | 2 << 16,    17 | 3 << 16,    25 | 3 << 16,
+    33 | 4 << 16,   49 | 4 << 16,   65 | 5 << 16,   97 | 5 << 16,    129 | 6 << 16,   193 | 6 << 16,   257 | 7 << 16,   385 | 7 << 16,   513 | 8 << 16,   769 | 8 << 16,
+    1025 | 9 << 16, 1537 | 9 << 16, 2049 | 10 << 16, 3073 | 10 << 16, 4097 | 11 << 16, 6145 | 11 << 16, 8193 | 12 << 16, 12289 | 12 << 16, 16385 | 13 << 16, 24577 | 13 << 16};
 __constant__ unsigned char c_clen_order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
 
 // per-warp decoder state in shared memory
-struct WarpTables {
+struct __align__(16) WarpTables {
     unsigned char ring[kInRing];              // input window: bytes [ring_base, ring_base + kInRing) of the stream
+    unsigned char win[kWin];                  // output window: the last kWin bytes of the inflated chunk
     unsigned short lit_lut[1 << kLitBits];    // (symbol << 4) | length, 0 = not a short code
     unsigned short dist_lut[1 << kDistBits];
     unsigned short lit_cnt[16], dist_cnt[16]; // canonical decode (codes longer than the lookup)
@@ -115,16 +126,19 @@ __device__ bool build_tables(const unsigned char* lens, int n, unsigned short* l
 struct BitReader {
     unsigned long long buf;   // bits not yet consumed, LSB first
     int cnt;                  // valid bits in buf
-    long long pos;            // bytes of the stream already moved into buf
+    int pos;                  // bytes of the stream already moved into buf (always a multiple of 4)
 };
 
-// move bytes from the shared-memory window into the bit buffer (lane 0); the caller guarantees the window covers
-// [pos, pos + 8) -- bytes past the end of the stream read as 0 and are caught by the `pos - cnt/8 > in_size` check
+// move aligned 32-bit words from the shared-memory window into the bit buffer until it holds more than 32 bits
+// (lane 0); the caller guarantees the window covers [pos, pos + 8) -- bytes past the end of the stream read as 0 and
+// are caught by the `pos - cnt/8 > in_size` check.  33 bits cover a literal/length code with its extra bits (20) or a
+// distance code with its extra bits (28).
 __device__ __forceinline__ void refill(BitReader& br, const unsigned char* ring) {
-    while (br.cnt <= 56) {
-        br.buf |= (unsigned long long)ring[br.pos & (kInRing - 1)] << br.cnt;
-        br.cnt += 8;
-        ++br.pos;
+    const unsigned* r32 = reinterpret_cast<const unsigned*>(ring);
+    while (br.cnt <= 32) {
+        br.buf |= (unsigned long long)r32[(br.pos >> 2) & (kInRing / 4 - 1)] << br.cnt;
+        br.cnt += 32;
+        br.pos += 4;
     }
 }
 
@@ -135,13 +149,15 @@ __device__ __forceinline__ unsigned take(BitReader& br, int n) {
     return v;
 }
 
-// canonical decode, one bit at a time (codes longer than the lookup); returns -1 on an invalid code
-__device__ int decode_slow(BitReader& br, const unsigned short* cnt, const unsigned short* sym) {
+// canonical decode, one bit at a time (codes longer than the lookup), on the low bits of the bit buffer (>= 15 valid):
+// returns (bits used << 16) | symbol, -1 on an invalid code.  Takes values, not the reader: the reader stays in registers.
+__device__ __noinline__ int decode_slow(unsigned bits, const unsigned short* cnt, const unsigned short* sym) {
     int code = 0, first = 0, index = 0;
     for (int l = 1; l <= 15; ++l) {
-        code |= (int)take(br, 1);
+        code |= (int)(bits & 1u);
+        bits >>= 1;
         const int c = cnt[l];
-        if (code - c < first) return sym[index + (code - first)];
+        if (code - c < first) return (l << 16) | sym[index + (code - first)];
         index += c;
         first += c;
         first <<= 1;
@@ -158,14 +174,18 @@ __device__ __forceinline__ int decode(BitReader& br, const unsigned short* lut, 
         br.cnt -= (e & 15);
         return e >> 4;
     }
-    return decode_slow(br, cnt, sym);
+    const int r = decode_slow((unsigned)br.buf, cnt, sym);
+    if (r < 0) return -1;
+    br.buf >>= (r >> 16);
+    br.cnt -= (r >> 16);
+    return r & 0xffff;
 }
 
 // the warp loads one half of the window: stream bytes [base, base + kInHalf), zeros past the end of the stream
-__device__ __forceinline__ void load_half(const Job& j, unsigned char* ring, long long base, int lane) {
+__device__ __forceinline__ void load_half(const Job& j, unsigned char* ring, int base, int lane) {
 #pragma unroll
     for (int q = 0; q < kInHalf / 512; ++q) {
-        const long long off = base + q * 512 + lane * 16;
+        const int off = base + q * 512 + lane * 16;
         uint4 v = make_uint4(0, 0, 0, 0);
         if (off + 16 <= j.in_size) {
             v = *reinterpret_cast<const uint4*>(j.in + off);
@@ -178,6 +198,16 @@ __device__ __forceinline__ void load_half(const Job& j, unsigned char* ring, lon
     }
 }
 
+// flush output bytes [from, to) (from a multiple of 16, the warp's window holds them) from shared memory to the chunk
+__device__ __forceinline__ void flush_window(const unsigned char* win, unsigned char* out, int from, int to, int lane) {
+    int p = from + lane * 16;
+    for (; p + 16 <= to; p += 32 * 16)
+        *reinterpret_cast<uint4*>(out + p) = *reinterpret_cast<const uint4*>(win + (p & (kWin - 1)));
+    // tail of fewer than 16 bytes (end of the chunk): byte by byte
+    const int tail = from + ((to - from) & ~15);
+    if (tail + lane < to && lane < 16) out[tail + lane] = win[(tail + lane) & (kWin - 1)];
+}
+
 __global__ void __launch_bounds__(32 * kInfWarps)
 k_inflate(const Job* __restrict__ jobs, long long njobs, int* __restrict__ status) {
     __shared__ WarpTables s_tab[kInfWarps];
@@ -187,13 +217,17 @@ k_inflate(const Job* __restrict__ jobs, long long njobs, int* __restrict__ statu
     WarpTables& T = s_tab[wid];
     const Job j = jobs[jid];
     constexpr unsigned kFull = 0xffffffffu;
-    // window: bytes [0, kInRing) to start with; `loaded` = end of the loaded range (the window is [loaded - kInRing, loaded))
+    // input window: bytes [0, kInRing) to start with; `loaded` = end of the loaded range (window = [loaded - kInRing, loaded))
     load_half(j, T.ring, 0, lane);
     load_half(j, T.ring, kInHalf, lane);
-    long long loaded = kInRing;
+    int loaded = kInRing;
+    const int in_size = (int)j.in_size, out_size = (int)j.out_size;
     __syncwarp();
     BitReader br{0, 0, 0};
-    long long opos = 0;
+    // output: every byte goes to the shared-memory window T.win (byte p at p mod kWin) and reaches the chunk in
+    // global memory in pieces of kFlush bytes, written by the whole warp; matches up to kNear bytes back are copied
+    // inside the window (shared-memory latency in the decoder's dependency chain instead of an L2 round trip per match)
+    int opos = 0, flushed = 0;
     int err = kInfOk;
     if (lane == 0) {
         refill(br, T.ring);
@@ -206,7 +240,7 @@ k_inflate(const Job* __restrict__ jobs, long long njobs, int* __restrict__ statu
         // at least kInHalf unread bytes in the window before a block header (uniform decision; the half that is
         // overwritten lies entirely behind the reader)
         {
-            const long long rpos = __shfl_sync(kFull, br.pos, 0);
+            const int rpos = __shfl_sync(kFull, br.pos, 0);
             while (loaded - rpos < kInHalf) {
                 load_half(j, T.ring, loaded, lane);
                 loaded += kInHalf;
@@ -228,7 +262,7 @@ k_inflate(const Job* __restrict__ jobs, long long njobs, int* __restrict__ statu
         }
         if (btype == 0) {
             // ---- stored block: byte-align, LEN / NLEN, then a plain copy done by the whole warp ----
-            long long src = 0;
+            int src = 0;
             int len = 0;
             if (lane == 0) {
                 take(br, br.cnt & 7);
@@ -242,26 +276,38 @@ k_inflate(const Job* __restrict__ jobs, long long njobs, int* __restrict__ statu
             len = __shfl_sync(kFull, len, 0);
             src = __shfl_sync(kFull, src, 0);
             if (err) break;
-            if (src + len > j.in_size) {
+            if (src + len > in_size) {
                 err = kInfTruncated;
                 break;
             }
-            if (opos + len > j.out_size) {
+            if (opos + len > out_size) {
                 err = kInfOverrun;
                 break;
             }
-            for (int i = lane; i < len; i += 32) j.out[opos + i] = j.in[src + i];
-            opos += len;
-            // restart the window behind the payload
-            const long long np = src + len;
-            const long long base = np & ~(long long)(kInHalf - 1);
+            // through the window in pieces, so that later matches find these bytes there
+            for (int done = 0; done < len;) {
+                const int piece = min(len - done, kFlush);
+                for (int i = lane; i < piece; i += 32) T.win[(opos + i) & (kWin - 1)] = j.in[src + done + i];
+                __syncwarp();
+                opos += piece;
+                done += piece;
+                while (opos - flushed >= kFlush) {
+                    flush_window(T.win, j.out, flushed, flushed + kFlush, lane);
+                    flushed += kFlush;
+                }
+                __syncwarp();
+            }
+            // restart the input window behind the payload
+            const int np = src + len;
+            const int base = np & ~(kInHalf - 1);
             load_half(j, T.ring, base, lane);
             load_half(j, T.ring, base + kInHalf, lane);
             loaded = base + kInRing;
             __syncwarp();
-            br.buf = 0;
-            br.cnt = 0;
-            br.pos = np;
+            // the reader restarts at byte np: the word that holds it, minus the bytes in front of np
+            br.pos = (np & ~3) + 4;
+            br.cnt = 32 - 8 * (np & 3);
+            br.buf = (unsigned long long)(reinterpret_cast<const unsigned*>(T.ring)[((np & ~3) >> 2) & (kInRing / 4 - 1)] >> (8 * (np & 3)));
             continue;
         }
         // ---- Huffman block: code lengths into T.lens ----
@@ -300,7 +346,7 @@ k_inflate(const Job* __restrict__ jobs, long long njobs, int* __restrict__ statu
                 unsigned char tmp_prev = 0;
                 // decode nlit + ndist lengths; they are written behind the 19 code-length lengths and moved down after
                 while (i < nlit + ndist && !err) {
-                    // the window always holds >= 512 unread bytes here: a dynamic header is at most ~320 symbols * 14 bits
+                    // the window holds >= kInHalf unread bytes at the block start: a dynamic header is at most ~570 bytes
                     refill(br, T.ring);
                     const int s = decode(br, T.dist_lut, kDistBits, T.dist_cnt, T.dist_sym);
                     if (s < 0) {
@@ -338,123 +384,195 @@ k_inflate(const Job* __restrict__ jobs, long long njobs, int* __restrict__ statu
         }
         if (!build_tables(T.lens, 288, T.lit_lut, kLitBits, T.lit_cnt, T.lit_sym, lane) ||
             !build_tables(T.lens + 288, 30, T.dist_lut, kDistBits, T.dist_cnt, T.dist_sym, lane)) {
-            // zlib accepts an incomplete distance code with a single symbol; build_tables only rejects over-subscription
-            err = kInfBadCode;
+            err = kInfBadCode;   // over-subscribed (incomplete codes are accepted; an unused code that turns up is an error)
             break;
         }
         // ---- symbols ----
+        // Every lane keeps opos; lane 0 decodes and reports, in ONE shuffled word per round, how many literals it wrote into
+        // the window and what stopped it: a match (length, distance), the end of the block, an error, or the need for the
+        // warp (input window / flush).  Housekeeping runs only when asked for.
+        bool housekeeping = true;
         for (;;) {
-            // keep the window ahead of the reader (uniform decision): a half is overwritten only when the reader is past it
-            const long long rpos = __shfl_sync(kFull, br.pos, 0);
-            while (loaded - rpos < kInHalf) {
-                load_half(j, T.ring, loaded, lane);
-                loaded += kInHalf;
-            }
-            __syncwarp();
-            int code = 0, len = 0, dist = 0;   // code: 0 = go on, 1 = end of block, 2 = match, 3 = window refill, else error
-            if (lane == 0) {
-                for (;;) {
-                    if (br.pos + 24 > loaded) {   // one symbol pair moves at most 16 bytes into the bit buffer
-                        code = 3;
-                        break;
-                    }
-                    refill(br, T.ring);
-                    int s = decode(br, T.lit_lut, kLitBits, T.lit_cnt, T.lit_sym);
-                    if (s < 0) {
-                        code = 10 + kInfBadCode;
-                        break;
-                    }
-                    if (s < 256) {
-                        if (opos >= j.out_size) {
-                            code = 10 + kInfOverrun;
-                            break;
-                        }
-                        j.out[opos++] = (unsigned char)s;
-                        continue;
-                    }
-                    if (s == 256) {
-                        code = 1;
-                        break;
-                    }
-                    s -= 257;
-                    if (s >= 29) {
-                        code = 10 + kInfBadCode;
-                        break;
-                    }
-                    len = c_len_base[s] + (int)take(br, c_len_extra[s]);
-                    refill(br, T.ring);
-                    const int d = decode(br, T.dist_lut, kDistBits, T.dist_cnt, T.dist_sym);
-                    if (d < 0 || d >= 30) {
-                        code = 10 + kInfBadCode;
-                        break;
-                    }
-                    dist = c_dist_base[d] + (int)take(br, c_dist_extra[d]);
-                    if (dist > opos) {
-                        code = 10 + kInfBadDistance;
-                        break;
-                    }
-                    if (opos + len > j.out_size) {
-                        code = 10 + kInfOverrun;
-                        break;
-                    }
-                    code = 2;
+            if (housekeeping) {
+                const int rpos = __shfl_sync(kFull, br.pos, 0);
+                if (opos > out_size) {   // literals may run up to a piece past the end inside the window; nothing of it is flushed
+                    err = kInfOverrun;
                     break;
                 }
-                if (br.pos - br.cnt / 8 > j.in_size) code = 10 + kInfTruncated;
+                while (loaded - rpos < kInHalf) {
+                    load_half(j, T.ring, loaded, lane);
+                    loaded += kInHalf;
+                }
+                while (opos - flushed >= kFlush) {
+                    flush_window(T.win, j.out, flushed, flushed + kFlush, lane);
+                    flushed += kFlush;
+                }
+                __syncwarp();   // the reader sees the new input, far matches read what was flushed
+                housekeeping = false;
             }
-            code = __shfl_sync(kFull, code, 0);
-            if (code == 3) continue;
+            unsigned long long msg = 3;   // code | literals << 8 | length << 20 | distance << 32; codes: 1 = end of block, 2 = match,
+                                          // 3 = housekeeping, >= 10 = error
+            if (lane == 0) {
+                // the tight loop: literals with short codes, state in registers, ONE counter for everything that needs the
+                // warp (a literal moves at most one word into the bit buffer and one byte into the window)
+                unsigned long long buf = br.buf;
+                int cnt = br.cnt, pos = br.pos, o = opos;
+                int budget = min(kFlush - (o - flushed), (loaded - 24 - pos) >> 2);
+                const unsigned* r32 = reinterpret_cast<const unsigned*>(T.ring);
+                int sym = -1;   // -1 = budget used up, -2 = a code longer than the lookup, >= 256 = a length code or end of block
+                while (budget > 0) {
+                    --budget;
+                    if (cnt <= 32) {
+                        buf |= (unsigned long long)r32[(pos >> 2) & (kInRing / 4 - 1)] << cnt;
+                        cnt += 32;
+                        pos += 4;
+                    }
+                    const unsigned e = T.lit_lut[(unsigned)buf & ((1u << kLitBits) - 1)];
+                    if (e == 0) {
+                        sym = -2;
+                        break;
+                    }
+                    buf >>= (e & 15);
+                    cnt -= (int)(e & 15);
+                    if (e < (256u << 4)) {
+                        T.win[o & (kWin - 1)] = (unsigned char)(e >> 4);
+                        ++o;
+                        continue;
+                    }
+                    sym = (int)(e >> 4);
+                    break;
+                }
+                br.buf = buf;
+                br.cnt = cnt;
+                br.pos = pos;
+                unsigned code = 3, len = 0, dist = 0;
+                if (sym == -2) {   // rare: a literal/length code of more than kLitBits bits
+                    refill(br, T.ring);
+                    const int r = decode_slow((unsigned)br.buf, T.lit_cnt, T.lit_sym);
+                    if (r < 0) {
+                        code = 10 + kInfBadCode;
+                    } else {
+                        br.buf >>= (r >> 16);
+                        br.cnt -= (r >> 16);
+                        sym = r & 0xffff;
+                        if (sym < 256) {
+                            T.win[o & (kWin - 1)] = (unsigned char)sym;
+                            ++o;
+                            sym = -1;
+                        }
+                    }
+                }
+                if (sym == 256) {
+                    code = 1;
+                } else if (sym > 256) {
+                    const int ls = sym - 257;
+                    if (ls >= 29) {
+                        code = 10 + kInfBadCode;
+                    } else {
+                        refill(br, T.ring);
+                        const unsigned lt = c_len_tab[ls];
+                        len = (lt & 0xffffu) + take(br, (int)(lt >> 16));
+                        refill(br, T.ring);
+                        const int d = decode(br, T.dist_lut, kDistBits, T.dist_cnt, T.dist_sym);
+                        if (d < 0 || d >= 30) {
+                            code = 10 + kInfBadCode;
+                        } else {
+                            const unsigned dt = c_dist_tab[d];
+                            dist = (dt & 0xffffu) + take(br, (int)(dt >> 16));
+                            code = 2;
+                            if ((int)dist > o) code = 10 + kInfBadDistance;
+                            else if (o + (int)len > out_size) code = 10 + kInfOverrun;
+                        }
+                    }
+                }
+                if (br.pos - br.cnt / 8 > in_size) code = 10 + kInfTruncated;
+                msg = (unsigned long long)code | ((unsigned long long)(unsigned)(o - opos) << 8) | ((unsigned long long)len << 20) |
+                      ((unsigned long long)dist << 32);
+            }
+            msg = __shfl_sync(kFull, msg, 0);
+            const int code = (int)(msg & 255u);
+            opos += (int)((msg >> 8) & 0xfffu);
+            if (code == 3) {
+                housekeeping = true;
+                continue;
+            }
             if (code == 1) break;
             if (code >= 10) {
                 err = code - 10;
                 break;
             }
-            // ---- match: every lane copies; bytes written by lane 0 as literals are ordered by the shuffle above ----
-            len = __shfl_sync(kFull, len, 0);
-            dist = __shfl_sync(kFull, dist, 0);
-            opos = __shfl_sync(kFull, opos, 0);
-            __syncwarp();
-            unsigned char* o = j.out + opos;
-            if (dist >= len || dist >= 32) {
-                // source and destination of one 32-byte step do not overlap (dist >= 32), or not at all (dist >= len)
-                for (int i = 0; i < len; i += 32) {
-                    unsigned char b = 0;
-                    if (i + lane < len) b = o[i + lane - dist];
-                    __syncwarp();
-                    if (i + lane < len) o[i + lane] = b;
+            // ---- match: every lane copies inside the window ----
+            const int len = (int)((msg >> 20) & 0xfffu), dist = (int)(msg >> 32);
+            __syncwarp();   // lane 0's literals are in the window
+            if (dist <= kNear) {
+                if (dist >= len || dist >= 32) {
+                    // source and destination of one 32-byte step do not overlap (dist >= 32), or not at all (dist >= len)
+                    for (int i = 0; i < len; i += 32) {
+                        unsigned char b = 0;
+                        if (i + lane < len) b = T.win[(opos + i + lane - dist) & (kWin - 1)];
+                        __syncwarp();
+                        if (i + lane < len) T.win[(opos + i + lane) & (kWin - 1)] = b;
+                        __syncwarp();
+                    }
+                } else {
+                    // run of a short pattern: byte i repeats byte i mod dist of the last `dist` bytes
+                    for (int i = lane; i < len; i += 32) T.win[(opos + i) & (kWin - 1)] = T.win[(opos - dist + (i % dist)) & (kWin - 1)];
                     __syncwarp();
                 }
             } else {
-                // run of a short pattern: byte i repeats byte i mod dist of the last `dist` bytes
-                for (int i = lane; i < len; i += 32) o[i] = o[(i % dist) - dist];
+                // far match: its source left the window long ago and is in the chunk already (dist > kNear > the
+                // unflushed part + the longest match), no overlap with the destination
+                for (int i = lane; i < len; i += 32) T.win[(opos + i) & (kWin - 1)] = j.out[opos + i - dist];
                 __syncwarp();
             }
             opos += len;
+            if (opos - flushed >= kFlush) housekeeping = true;
         }
-        opos = __shfl_sync(kFull, opos, 0);   // literals decoded by lane 0 since the last match
         if (err) break;
     }
     opos = __shfl_sync(kFull, opos, 0);
-    if (!err && opos != j.out_size) err = kInfShort;
+    if (!err && opos != out_size) err = opos > out_size ? kInfOverrun : kInfShort;
+    if (!err) {
+        __syncwarp();
+        flush_window(T.win, j.out, flushed, opos, lane);
+    }
     if (lane == 0) status[jid] = err;
 }
 
-// Adler-32 of the inflated chunk against the trailer of its zlib stream: one CTA per chunk
+// Adler-32 of the inflated chunk against the trailer of its zlib stream: one CTA per chunk.
+// s1 = 1 + sum b_i, s2 = n + sum (n - i) b_i  (mod 65521).  The sums are kept exact in 64 bits (a chunk holds less than
+// 2^30 bytes: a thread adds < 2^22 terms below 2^38) and reduced once; the chunk is read 16 bytes per thread and step.
 __global__ void __launch_bounds__(256)
 k_adler(const Job* __restrict__ jobs, int* __restrict__ status) {
     const Job j = jobs[blockIdx.x];
     if (status[blockIdx.x] != kInfOk) return;
-    // s1 = 1 + sum b_i, s2 = n + sum (n - i) b_i  (mod 65521); 64-bit partial sums, reduced per 4096-byte piece
     __shared__ unsigned long long sh1[256], sh2[256];
     unsigned long long a = 0, b = 0;
     const long long n = j.out_size;
-    for (long long i = threadIdx.x; i < n; i += 256) {
+    const long long nvec = n >> 4;                    // the scratch chunk starts 256-byte aligned
+    const uint4* v4 = reinterpret_cast<const uint4*>(j.out);
+    for (long long q = threadIdx.x; q < nvec; q += 256) {
+        const uint4 w = v4[q];
+        const unsigned ws[4] = {w.x, w.y, w.z, w.w};
+        unsigned long long wt = (unsigned long long)(n - q * 16);   // weight of the first byte of this vector
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+#pragma unroll
+            for (int bb = 0; bb < 4; ++bb) {
+                const unsigned long long v = (ws[k] >> (8 * bb)) & 255u;
+                a += v;
+                b += wt * v;
+                --wt;
+            }
+        }
+    }
+    for (long long i = (nvec << 4) + threadIdx.x; i < n; i += 256) {
         const unsigned long long v = j.out[i];
         a += v;
-        b = (b + (unsigned long long)((n - i) % 65521) * v) % 65521ull;
+        b += (unsigned long long)(n - i) * v;
     }
     sh1[threadIdx.x] = a % 65521ull;
-    sh2[threadIdx.x] = b;
+    sh2[threadIdx.x] = b % 65521ull;
     __syncthreads();
     for (int s = 128; s > 0; s >>= 1) {
         if (threadIdx.x < s) {
@@ -479,12 +597,12 @@ struct PlaceArgs {
 
 // chunk bytes (as the filter pipeline left them) -> elements at their place in the destination slab
 __global__ void __launch_bounds__(256)
-k_unshuffle_place(const unsigned char* __restrict__ tmp, long long chunk_bytes, const long long* __restrict__ start,
+k_unshuffle_place(const unsigned char* __restrict__ tmp, long long chunk_stride, const long long* __restrict__ start,
                   const int* __restrict__ status, PlaceArgs a, unsigned char* __restrict__ dst) {
     const long long job = blockIdx.y;
     if (status[job] != kInfOk) return;
     const long long nelem = a.cdim[0] * a.cdim[1] * a.cdim[2] * a.cdim[3];
-    const unsigned char* src = tmp + job * chunk_bytes;
+    const unsigned char* src = tmp + job * chunk_stride;
     const long long* st = start + job * 4;
     for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < nelem; e += (long long)gridDim.x * 256) {
         long long r = e;
@@ -562,6 +680,7 @@ void h5_decode_chunks(const void* comp_dev, int64_t comp_bytes, int64_t nchunks,
     pa.swap = swap_bytes ? 1 : 0;
     const int64_t nelem = pa.cdim[0] * pa.cdim[1] * pa.cdim[2] * pa.cdim[3];
     const int64_t chunk_bytes = nelem * elem_size;
+    NFX_REQUIRE(chunk_bytes < ((int64_t)1 << 30), "h5 decode: a chunk must hold less than 1 GiB");
     int dev = 0;
     NFX_CUDA(cudaGetDevice(&dev));
     std::lock_guard<std::mutex> lk(g_dec_mu);
@@ -571,15 +690,17 @@ void h5_decode_chunks(const void* comp_dev, int64_t comp_bytes, int64_t nchunks,
     const int trailer = (filters & NFX_H5_FLETCHER32) ? 4 : 0;
     std::vector<Job> h_jobs((size_t)nchunks);
     std::vector<long long> h_start((size_t)nchunks * 4, 0);
-    if (deflate) sc.tmp.ensure((size_t)(nchunks * chunk_bytes));
+    const int64_t stride = (chunk_bytes + 255) & ~(int64_t)255;   // inflated chunks start 256-byte aligned in the scratch
+    if (deflate) sc.tmp.ensure((size_t)(nchunks * stride));
     for (int64_t c = 0; c < nchunks; ++c) {
         NFX_REQUIRE(in_off[c] >= 0 && in_size[c] >= trailer && in_off[c] + in_size[c] <= comp_bytes,
                     "h5 decode: a chunk lies outside the staging buffer");
         NFX_REQUIRE((in_off[c] & 15) == 0, "h5 decode: chunk offsets in the staging buffer must be multiples of 16");
+        NFX_REQUIRE(in_size[c] < ((int64_t)1 << 30), "h5 decode: a stored chunk must be smaller than 1 GiB");
         NFX_REQUIRE(deflate || in_size[c] - trailer == chunk_bytes, "h5 decode: an uncompressed chunk has the wrong size");
         h_jobs[(size_t)c].in = static_cast<const unsigned char*>(comp_dev) + in_off[c];
         h_jobs[(size_t)c].in_size = in_size[c] - trailer;
-        h_jobs[(size_t)c].out = deflate ? sc.tmp.p + c * chunk_bytes : nullptr;
+        h_jobs[(size_t)c].out = deflate ? sc.tmp.p + c * stride : nullptr;
         h_jobs[(size_t)c].out_size = chunk_bytes;
         for (int d = 0; d < rank; ++d) h_start[(size_t)c * 4 + 4 - rank + d] = chunk_start[c * rank + d];
     }
@@ -597,18 +718,18 @@ void h5_decode_chunks(const void* comp_dev, int64_t comp_bytes, int64_t nchunks,
         count_launch();
         placed_from = sc.tmp.p;
         const unsigned gx = (unsigned)std::min<int64_t>((nelem + 255) / 256, 1024);
-        k_unshuffle_place<<<dim3(gx, (unsigned)nchunks), 256, 0, s>>>(placed_from, chunk_bytes, sc.start.p, sc.status.p, pa,
+        k_unshuffle_place<<<dim3(gx, (unsigned)nchunks), 256, 0, s>>>(placed_from, stride, sc.start.p, sc.status.p, pa,
                                                                       static_cast<unsigned char*>(dst_dev));
         count_launch();
     } else {
         // no deflate: chunks sit in the staging buffer at arbitrary (16-byte aligned) offsets: one launch per chunk
         // would do, but the offsets differ -- reuse the job table through a tiny indirection: copy to tmp layout first
-        sc.tmp.ensure((size_t)(nchunks * chunk_bytes));
+        sc.tmp.ensure((size_t)(nchunks * stride));
         for (int64_t c = 0; c < nchunks; ++c)
-            NFX_CUDA(cudaMemcpyAsync(sc.tmp.p + c * chunk_bytes, static_cast<const unsigned char*>(comp_dev) + in_off[c],
+            NFX_CUDA(cudaMemcpyAsync(sc.tmp.p + c * stride, static_cast<const unsigned char*>(comp_dev) + in_off[c],
                                      (size_t)chunk_bytes, cudaMemcpyDeviceToDevice, s));
         const unsigned gx = (unsigned)std::min<int64_t>((nelem + 255) / 256, 1024);
-        k_unshuffle_place<<<dim3(gx, (unsigned)nchunks), 256, 0, s>>>(sc.tmp.p, chunk_bytes, sc.start.p, sc.status.p, pa,
+        k_unshuffle_place<<<dim3(gx, (unsigned)nchunks), 256, 0, s>>>(sc.tmp.p, stride, sc.start.p, sc.status.p, pa,
                                                                       static_cast<unsigned char*>(dst_dev));
         count_launch();
     }

@@ -284,16 +284,100 @@ class Field(object):
         txt += "(Sv) " if self.sverdrup else "(A m^2/s) "
         return re.sub(r',\s*\(', ' (', txt)
 
-    def fluxSeries(self, chunk_steps=0, prefetch=True):
+    def _device_readers(self):
+        """(reader of uo, reader of vo) when both are chunked NetCDF-4 variables whose filter pipeline the device undoes
+        (nfx_h5_decode_chunks): 4-D float32/float64, one missing-value marker, not packed; else None"""
+        from . import ncio
+        readers = []
+        for nc, name in ((self.ncU, 'uo'), (self.ncV, 'vo')):
+            var = nc[name]
+            data = getattr(var, '_data', None)
+            if not isinstance(data, ncio._H5Data) or len(var.shape) != 4 or self._decoded(var):
+                return None
+            ds = data._ds
+            if ds.chunk_dims is None or ds.device_filter_flags() is None or ds.dtype.kind != 'f' or \
+                    ds.dtype.itemsize not in (4, 8):
+                return None
+            readers.append(ds)
+        fu, fv = self._fill(self.ncU, 'uo'), self._fill(self.ncV, 'vo')
+        if fv == fv and fv != fu:
+            return None                                 # two different markers: the host path rewrites one of them
+        try:
+            return [nemoflux_gpu.H5DeviceReader(readers, self.device)]       # uo and vo in ONE decode launch
+        except ValueError:
+            if readers[0].dtype.itemsize != readers[1].dtype.itemsize:
+                return None
+            return [nemoflux_gpu.H5DeviceReader(d, self.device) for d in readers]
+
+    def _flux_series_device_decode(self, readers, chunk_steps=0, prefetch=True):
+        """flux series of chunked + deflated uo / vo: the COMPRESSED chunks cross PCIe and are inflated, unshuffled and
+        placed on the device (csrc/nfx_inflate.cu), then K2 + K3 run on the decoded slab.  A reader thread copies the
+        compressed chunks of block i + 1 from the memory-mapped files into pinned staging while block i is decoded."""
+        import threading
+        import torch
+        M = len(self.plis)
+        out = numpy.zeros((self.nt, M))
+        esize = readers[0].ds.dtype.itemsize
+        step_bytes = esize * self.nz * self.ny * self.nx
+        # The decoder works on one chunk per warp and 20 warps fit an SM: a block of as many chunks as the device holds
+        # at once (2 960 on a B200) is decoded in one wave; smaller blocks take as long, larger ones leave a tail wave.
+        # Capped at 3 GB of decoded data per block.
+        ds = readers[0].ds
+        chunks_per_step = len(readers[0].dss) * len(readers) * max(1, int(numpy.prod(
+            [-(-ext // c) for ext, c in zip(ds.shape[1:], ds.chunk_dims[1:])]))) // max(1, ds.chunk_dims[0])
+        wave = 20 * torch.cuda.get_device_properties(self.device).multi_processor_count
+        n = chunk_steps if chunk_steps > 0 else max(1, min(self.nt, wave // max(chunks_per_step, 1),
+                                                           (3 << 30) // max(2 * step_bytes, 1)))
+        blocks = [(t0, min(n, self.nt - t0)) for t0 in range(0, self.nt, n)]
+        fill = self._fill(self.ncU, 'uo')
+        staged = {}
+
+        def stage(i):
+            t0, m = blocks[i]
+            staged[i] = tuple(r.stage([t0, 0, 0, 0], [t0 + m, self.nz, self.ny, self.nx]) for r in readers)
+
+        # the staging buffer of a reader is re-used: block i + 1 may be staged once block i is on the device
+        stage(0)
+        for i, (t0, m) in enumerate(blocks):
+            st = staged.pop(i)
+            if len(readers) == 1:
+                ud, vd = readers[0].decode(st[0])       # decode() synchronises: the staging buffer is free again
+            else:
+                ud, vd = readers[0].decode(st[0]), readers[1].decode(st[1])
+            th = None
+            if i + 1 < len(blocks):
+                if prefetch:
+                    th = threading.Thread(target=stage, args=(i + 1,))
+                    th.start()
+                else:
+                    stage(i + 1)
+            ser = self.pli.fluxSeries(ud, vd, self._d_thickness, self._d_arc1, self._d_arc2, sverdrup=self.sverdrup,
+                                      fill=fill, e3u=self._d_e3u, e3v=self._d_e3v)
+            out[t0:t0 + m] = ser.cpu().numpy()
+            if th is not None:
+                th.join()
+        self.last_ingest = dict(path='device decode', bytes_compressed=sum(r.bytes_compressed for r in readers),
+                                bytes_decoded=sum(r.bytes_decoded for r in readers))
+        return out
+
+    def fluxSeries(self, chunk_steps=0, prefetch=True, device_decode=None):
         """(nt, M) flux of every transect at every time step -- the loop of fluxplot.py:51-59 in a few launches.
 
         The time axis is streamed from the files in chunks: a reader thread fills one of two PINNED host buffers
         (file read, numpy releases the GIL) while the previous chunk goes through the host-buffer entry point of
         the C ABI (double-buffered H2D, K2, K3) -- file I/O, PCIe and the kernels overlap.
         NetCDF classic files are big-endian: the bytes are copied as stored and swapped on the device
-        (NFX_BIG_ENDIAN), so the host does no conversion pass."""
+        (NFX_BIG_ENDIAN), so the host does no conversion pass.
+        Chunked + deflated NetCDF-4 variables (device_decode=None: whenever possible, True: required, False: host zlib)
+        travel COMPRESSED and are inflated / unshuffled on the device, see _flux_series_device_decode."""
         import threading
         import torch
+        if device_decode is not False:
+            readers = self._device_readers()
+            if readers is not None:
+                return self._flux_series_device_decode(readers, chunk_steps, prefetch)
+            if device_decode is True:
+                raise RuntimeError('ERROR: uo / vo are not chunked HDF5 variables with a [shuffle,] [deflate] pipeline')
         out = numpy.zeros((self.nt, len(self.plis)))
         dtype = numpy.dtype(self.ncU['uo'].dtype).newbyteorder('=')
         step_bytes = dtype.itemsize * self.nz * self.ny * self.nx

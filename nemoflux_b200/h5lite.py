@@ -127,11 +127,20 @@ class Dataset(object):
             return []
         if self._chunks is None:
             self._chunks = self._f._chunk_btree(addr, rank)
-        out = []
-        for offsets, nbytes, mask, caddr in self._chunks:
-            if all(max(offsets[d], starts[d]) < min(offsets[d] + cdims[d], stops[d], self.shape[d]) for d in range(rank)):
-                out.append((self._f._base + caddr, nbytes, mask, tuple(offsets[:rank])))
-        return out
+        if getattr(self, '_chunk_arr', None) is None:           # the index as arrays: a block is selected in one pass
+            self._chunk_arr = (numpy.array([c[0][:rank] for c in self._chunks], numpy.int64).reshape(-1, rank),
+                               numpy.array([c[1] for c in self._chunks], numpy.int64),
+                               numpy.array([c[2] for c in self._chunks], numpy.int64),
+                               numpy.array([c[3] for c in self._chunks], numpy.int64))
+        offs, nbytes, mask, caddr = self._chunk_arr
+        if offs.shape[0] == 0:
+            return []
+        lo = numpy.maximum(offs, numpy.asarray(starts, numpy.int64)[None])
+        hi = numpy.minimum(numpy.minimum(offs + numpy.asarray(cdims[:rank], numpy.int64)[None],
+                                         numpy.asarray(stops, numpy.int64)[None]), numpy.asarray(self.shape, numpy.int64)[None])
+        sel = numpy.nonzero((lo < hi).all(axis=1))[0]
+        base = self._f._base
+        return [(base + int(caddr[k]), int(nbytes[k]), int(mask[k]), tuple(int(x) for x in offs[k])) for k in sel]
 
     @property
     def chunk_dims(self):

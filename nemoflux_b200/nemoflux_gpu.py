@@ -600,28 +600,38 @@ def h5DecodeChunks(comp, in_off, in_size, filters, chunk_dims, dst, chunk_start,
 
 
 class H5DeviceReader(object):
-    """Blocks of a chunked (deflate / shuffle) HDF5 variable read straight onto the GPU: the COMPRESSED chunks are
-    copied from the memory-mapped file into a pinned staging buffer, cross PCIe as stored and are inflated, unshuffled
+    """Blocks of chunked (deflate / shuffle) HDF5 variables read straight onto the GPU: the COMPRESSED chunks are
+    copied from the memory-mapped files into a pinned staging buffer, cross PCIe as stored and are inflated, unshuffled
     and placed by nfx_h5_decode_chunks -- the decompression the reference leaves to one host thread inside
     netCDF4 / HDF5 (field.py:22-35, 149; subsetNEMO.py:78 writes zlib=True).
 
-        rd = H5DeviceReader(ds, device)        # ds: nemoflux_b200.h5lite.Dataset, chunked
-        block = rd.read(starts, stops)         # cuda tensor of shape stops - starts, native byte order
+        rd = H5DeviceReader(ds, device)            # ds: nemoflux_b200.h5lite.Dataset, chunked
+        block = rd.read(starts, stops)             # cuda tensor of shape stops - starts, native byte order
+        rd = H5DeviceReader([ds_u, ds_v], device)  # variables of one shape / chunking / type: ONE decode launch for
+        u, v = rd.read(starts, stops)              # both (twice the chunks in flight), block[0], block[1]
     """
 
-    def __init__(self, ds, device, workers=4):
+    def __init__(self, ds, device, workers=8):
         torch = _torch()
-        self.ds, self.device = ds, torch.device(device)
-        self.flags = ds.device_filter_flags()
-        if ds.chunk_dims is None or self.flags is None:
-            raise ValueError(f'{ds.name}: not a chunked variable with a [shuffle,] [deflate,] [fletcher32] pipeline')
-        if ds.dtype.kind != 'f' or ds.dtype.itemsize not in (4, 8):
-            raise ValueError(f'{ds.name}: float32 / float64 variables only')
-        self.tdtype = torch.float32 if ds.dtype.itemsize == 4 else torch.float64
-        self.swap = not ds.dtype.isnative
+        self.many = isinstance(ds, (list, tuple))
+        self.dss = list(ds) if self.many else [ds]
+        self.ds = self.dss[0]
+        self.device = torch.device(device)
+        self.flags = self.ds.device_filter_flags()
+        for d in self.dss:
+            if d.chunk_dims is None or d.device_filter_flags() is None:
+                raise ValueError(f'{d.name}: not a chunked variable with a [shuffle,] [deflate,] [fletcher32] pipeline')
+            if d.dtype.kind != 'f' or d.dtype.itemsize not in (4, 8):
+                raise ValueError(f'{d.name}: float32 / float64 variables only')
+            if (d.shape, d.chunk_dims, d.dtype, [f[0] for f in d._filters]) != \
+                    (self.ds.shape, self.ds.chunk_dims, self.ds.dtype, [f[0] for f in self.ds._filters]):
+                raise ValueError('variables decoded together must share shape, chunking, type and filters')
+        self.tdtype = torch.float32 if self.ds.dtype.itemsize == 4 else torch.float64
+        self.swap = not self.ds.dtype.isnative
         self.workers = max(1, int(workers))
         self._pinned = None
         self._dev = None
+        self._copy_stream = None
         self.bytes_compressed = 0          # running totals, for the caller's report
         self.bytes_decoded = 0
 
@@ -630,21 +640,23 @@ class H5DeviceReader(object):
         device half (decode) takes.  Runs without the GIL for the copies, so a reader thread can prepare block i + 1
         while block i is decoded."""
         torch = _torch()
-        plan = self.ds.chunk_plan(starts, stops)
+        plan = []                                               # (variable, file offset, bytes, mask, origin)
+        for iv, d in enumerate(self.dss):
+            plan += [(iv,) + c for c in d.chunk_plan(starts, stops)]
         offs, pos = [], 0
-        for _addr, nbytes, _mask, _org in plan:
+        for _iv, _addr, nbytes, _mask, _org in plan:
             offs.append(pos)
             pos += (nbytes + 15) & ~15
         total = pos + 4096                                      # the decoder may look a little past the last stream
         if self._pinned is None or self._pinned.numel() < total:
             self._pinned = torch.empty(int(total * 1.25) + 4096, dtype=torch.uint8, pin_memory=True)
         hbuf = self._pinned.numpy()
-        fbuf = numpy.frombuffer(self.ds._f._buf, numpy.uint8)
+        fbufs = [numpy.frombuffer(d._f._buf, numpy.uint8) for d in self.dss]
 
         def copy(lo, hi):
             for k in range(lo, hi):
-                addr, nbytes = plan[k][0], plan[k][1]
-                hbuf[offs[k]:offs[k] + nbytes] = fbuf[addr:addr + nbytes]
+                iv, addr, nbytes = plan[k][0], plan[k][1], plan[k][2]
+                hbuf[offs[k]:offs[k] + nbytes] = fbufs[iv][addr:addr + nbytes]
         if len(plan) >= 2 * self.workers and self.workers > 1:
             from concurrent.futures import ThreadPoolExecutor
             step = -(-len(plan) // self.workers)
@@ -655,37 +667,65 @@ class H5DeviceReader(object):
         return dict(plan=plan, offs=offs, total=total, starts=list(starts), stops=list(stops))
 
     def decode(self, staged, out=None):
-        """device half: H2D of the staged bytes, inflate + unshuffle + placement; returns the cuda tensor"""
+        """device half: H2D of the staged bytes, inflate + unshuffle + placement; returns the cuda tensor (with a
+        leading axis over the variables when the reader was built from a list)"""
         torch = _torch()
         plan, offs, total = staged['plan'], staged['offs'], staged['total']
         shape = [b - a for a, b in zip(staged['starts'], staged['stops'])]
+        nvar = len(self.dss)
         if out is None:
-            out = torch.empty(shape, dtype=self.tdtype, device=self.device)
-        if self.ds.fill is not None:
-            out.fill_(float(numpy.frombuffer(self.ds.fill, self.ds.dtype, 1)[0]))
-        else:
-            out.zero_()
-        if not plan:
-            return out
-        if self._dev is None or self._dev.numel() < total:
-            self._dev = torch.empty(self._pinned.numel(), dtype=torch.uint8, device=self.device)
-        self._dev[:total].copy_(self._pinned[:total], non_blocking=True)
-        nfilters = len(self.ds._filters)
-        groups = {}
-        for k, (_addr, nbytes, mask, org) in enumerate(plan):   # a chunk may have skipped filters (its mask bits)
-            flags = 0
-            for i, (fid, _cd) in enumerate(self.ds._filters):
-                if not (mask >> i) & 1:
-                    flags |= {1: _lib.NFX_H5_DEFLATE, 2: _lib.NFX_H5_SHUFFLE, 3: _lib.NFX_H5_FLETCHER32}[fid]
-            groups.setdefault(flags, []).append(k)
-        del nfilters
-        for flags, ks in groups.items():
-            start = [[plan[k][3][d] - staged['starts'][d] for d in range(len(shape))] for k in ks]
-            h5DecodeChunks(self._dev[:total], [offs[k] for k in ks], [plan[k][1] for k in ks], flags, self.ds.chunk_dims,
-                           out, start, swap_bytes=self.swap)
-        self.bytes_compressed += sum(p[1] for p in plan)
+            out = torch.empty([nvar] + shape, dtype=self.tdtype, device=self.device)
+        full = out.view([nvar * shape[0]] + shape[1:]) if shape else out          # variables stacked along axis 0
+        for iv, d in enumerate(self.dss):
+            blk = out[iv] if nvar > 1 or out.dim() == len(shape) + 1 else out
+            if d.fill is not None:
+                blk.fill_(float(numpy.frombuffer(d.fill, d.dtype, 1)[0]))
+            else:
+                blk.zero_()
+        if plan:
+            if self._dev is None or self._dev.numel() < total:
+                self._dev = torch.empty(self._pinned.numel(), dtype=torch.uint8, device=self.device)
+            # the staged bytes cross PCIe in a few pieces on a side stream; piece p is decoded while piece p + 1 travels
+            npiece = max(1, min(4, len(plan) // 1500))
+            cuts = [len(plan) * p // npiece for p in range(npiece + 1)]
+            if self._copy_stream is None:
+                self._copy_stream = torch.cuda.Stream(device=self.device)
+            main = torch.cuda.current_stream(self.device)
+            self._copy_stream.wait_stream(main)                 # the buffer's previous contents have been decoded
+            ready = []
+            with torch.cuda.stream(self._copy_stream):
+                for p in range(npiece):
+                    lo = offs[cuts[p]]
+                    hi = offs[cuts[p + 1]] if cuts[p + 1] < len(plan) else total
+                    self._dev[lo:hi].copy_(self._pinned[lo:hi], non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(self._copy_stream)
+                    ready.append(ev)
+            piece_of = numpy.searchsorted(numpy.array(cuts[1:]), numpy.arange(len(plan)), side='right')
+            groups = {}
+            for k, (iv, _addr, _nbytes, mask, _org) in enumerate(plan):   # a chunk may have skipped filters (its mask bits)
+                flags = 0
+                for i, (fid, _cd) in enumerate(self.dss[iv]._filters):
+                    if not (mask >> i) & 1:
+                        flags |= {1: _lib.NFX_H5_DEFLATE, 2: _lib.NFX_H5_SHUFFLE, 3: _lib.NFX_H5_FLETCHER32}[fid]
+                groups.setdefault((int(piece_of[k]), flags), []).append(k)
+            # one launch for all variables when a chunk is one index thick along axis 0 (NetCDF's usual time chunking):
+            # the variables are stacked along that axis and no chunk can hang over into its neighbour; else a launch
+            # per variable, clipped by its own block
+            together = nvar == 1 or self.ds.chunk_dims[0] == 1
+            for (piece, flags), ks_all in sorted(groups.items()):
+                main.wait_event(ready[piece])
+                for iv in ([None] if together else range(nvar)):
+                    ks = ks_all if together else [k for k in ks_all if plan[k][0] == iv]
+                    if not ks:
+                        continue
+                    start = [[plan[k][4][d] - staged['starts'][d] + (plan[k][0] * shape[0] if d == 0 and together else 0)
+                              for d in range(len(shape))] for k in ks]
+                    h5DecodeChunks(self._dev[:total], [offs[k] for k in ks], [plan[k][2] for k in ks], flags,
+                                   self.ds.chunk_dims, full if together else out[iv], start, swap_bytes=self.swap)
+            self.bytes_compressed += sum(p[2] for p in plan)
         self.bytes_decoded += out.numel() * out.element_size()
-        return out
+        return out if self.many else out[0]
 
     def read(self, starts, stops, out=None):
         return self.decode(self.stage(starts, stops), out=out)

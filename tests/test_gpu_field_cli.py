@@ -275,6 +275,12 @@ def test_field_reads_netcdf4_velocity_files(gpu, oracle, tmp_path):
     f4 = Field(T, U4, V4, lines, verbose=False)
     s4 = f4.fluxSeries(chunk_steps=2)
     assert numpy.array_equal(s4, s3)
+    # deflated chunks travel compressed and are inflated + unshuffled on the device (csrc/nfx_inflate.cu) ...
+    assert f4.last_ingest['path'] == 'device decode'
+    assert 0 < f4.last_ingest['bytes_compressed'] < f4.last_ingest['bytes_decoded'] == 2 * u32.nbytes
+    # ... with the bits of the host decode (zlib + numpy unshuffle on reader threads), whatever the block size
+    assert numpy.array_equal(f4.fluxSeries(chunk_steps=2, device_decode=False), s3)
+    assert numpy.array_equal(f4.fluxSeries(chunk_steps=5, device_decode=True, prefetch=False), s3)
     assert numpy.abs(f4.fluxes - s4[0]).max() <= 1e-13 * numpy.abs(s4).max()
     un, vn = u32.astype(numpy.float64), v32.astype(numpy.float64)
     un[:, land] = numpy.nan

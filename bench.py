@@ -402,8 +402,16 @@ def run_passes(cx, args, wl, nt_total, t0_rank, nt_local, counts, steps, warmup,
     eflux = torch.empty((cap, 2 * syn.ncell), dtype=torch.float64, device=cx.dev) if args.classic else None
     series_pad = torch.zeros((cmax, M), dtype=torch.float64, device=cx.dev)       # padded to the largest shard
     gathered = torch.empty((world * cmax, M), dtype=torch.float64, device=cx.dev) if world > 1 else None
-    full_series = torch.zeros((nt_total, M), dtype=torch.float64, device=cx.dev) if bal is not None else None
+    full_series = None
     shards_all = [nfx_dist.shard_batches(nt_total, bal['npanels'], world, r, bal.get('weights')) for r in range(world)] if bal else None
+    combine_idx = None
+    if bal is not None:
+        # row r*cmax + k of the gathered blocks is time step t_first_r + k (rows past a rank's last step go to a spare row)
+        idx = numpy.full(world * cmax, nt_total, numpy.int64)
+        for r, sh in enumerate(shards_all):
+            idx[r * cmax:r * cmax + sh['nt_touched']] = sh['t_first'] + numpy.arange(sh['nt_touched'])
+        combine_idx = torch.from_numpy(idx).to(cx.dev)
+        full_series = torch.zeros((nt_total + 1, M), dtype=torch.float64, device=cx.dev)
     resident = [-1]
 
     def load_chunk(ci):
@@ -435,14 +443,11 @@ def run_passes(cx, args, wl, nt_total, t0_rank, nt_local, counts, steps, warmup,
         if world == 1:
             return series_pad
         dist.all_gather_into_tensor(gathered, series_pad)
-        if bal is not None:          # time steps shared by two ranks: add the partial sums in rank order
+        if bal is not None:
+            # a time step shared by two ranks: the sum of its two partial rows (two addends: the order cannot matter)
             full_series.zero_()
-            for r in range(world):
-                sh = shards_all[r]
-                if sh['nt_touched']:
-                    full_series[sh['t_first']:sh['t_first'] + sh['nt_touched']] += \
-                        gathered[r * cmax:r * cmax + sh['nt_touched']]
-            return full_series
+            full_series.index_add_(0, combine_idx, gathered)
+            return full_series[:nt_total]
         return gathered
 
     def step(evs=None, eg=None):

@@ -462,6 +462,24 @@ for b in range(s['b0'], s['b1']):
     part[b // npanels] += contrib[s['t_first'] + b // npanels, b % npanels]
 tot = nd.combine_partial_series(part, nt, npanels)
 assert torch.equal(tot, contrib.sum(1)), (rank, tot)
+# the same with shares proportional to each rank's measured rate (every rank passes the same weights)
+weights = [1.0 + 0.25 * r for r in range(world)]
+s = nd.shard_batches(nt, npanels, world, rank, weights)
+part = torch.zeros((s['nt_touched'], m), dtype=torch.float64)
+for b in range(s['b0'], s['b1']):
+    part[b // npanels] += contrib[s['t_first'] + b // npanels, b % npanels]
+tot = nd.combine_partial_series(part, nt, npanels, weights=weights)
+assert torch.equal(tot, contrib.sum(1)), (rank, tot)
+# host-fed time steps apportioned by rate: the blocks tile the series, the gathered result is the 1-rank answer
+counts = nd.apportion_by_rate(nt, [23.0, 35.0][:world] if world == 2 else [1.0] * world)
+t0, n = nd.blocks_from_counts(counts)[rank]
+cm = max(max(counts), 1)
+blk = torch.zeros((cm, m), dtype=torch.float64)
+blk[:n] = full[t0:t0 + n]
+parts = [torch.zeros((cm, m), dtype=torch.float64) for _ in range(world)]
+dist.all_gather(parts, blk)
+got = torch.cat([parts[r][:counts[r]] for r in range(world)], 0)
+assert torch.equal(got, full), (rank, counts)
 dist.barrier()
 dist.destroy_process_group()
 print('ok', rank)

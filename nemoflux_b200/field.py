@@ -328,6 +328,9 @@ class Field(object):
         wave = 20 * torch.cuda.get_device_properties(self.device).multi_processor_count
         n = chunk_steps if chunk_steps > 0 else max(1, min(self.nt, wave // max(chunks_per_step, 1),
                                                            (3 << 30) // max(2 * step_bytes, 1)))
+        if chunk_steps <= 0:                            # blocks of equal size: a short last block costs a full chunk latency
+            nblk = -(-self.nt // n)
+            n = -(-self.nt // nblk)
         blocks = [(t0, min(n, self.nt - t0)) for t0 in range(0, self.nt, n)]
         fill = self._fill(self.ncU, 'uo')
         staged = {}
@@ -336,21 +339,21 @@ class Field(object):
             t0, m = blocks[i]
             staged[i] = tuple(r.stage([t0, 0, 0, 0], [t0 + m, self.nz, self.ny, self.nx]) for r in readers)
 
-        # the staging buffer of a reader is re-used: block i + 1 may be staged once block i is on the device
+        # stage() ends by sending its bytes to one of the reader's two device buffers; the reader thread prepares block
+        # i + 1 (file -> pinned -> device) while block i is inflated and integrated
         stage(0)
         for i, (t0, m) in enumerate(blocks):
             st = staged.pop(i)
+            th = None
+            if i + 1 < len(blocks) and prefetch:
+                th = threading.Thread(target=stage, args=(i + 1,))
+                th.start()
             if len(readers) == 1:
-                ud, vd = readers[0].decode(st[0])       # decode() synchronises: the staging buffer is free again
+                ud, vd = readers[0].decode(st[0])
             else:
                 ud, vd = readers[0].decode(st[0]), readers[1].decode(st[1])
-            th = None
-            if i + 1 < len(blocks):
-                if prefetch:
-                    th = threading.Thread(target=stage, args=(i + 1,))
-                    th.start()
-                else:
-                    stage(i + 1)
+            if i + 1 < len(blocks) and not prefetch:
+                stage(i + 1)
             ser = self.pli.fluxSeries(ud, vd, self._d_thickness, self._d_arc1, self._d_arc2, sverdrup=self.sverdrup,
                                       fill=fill, e3u=self._d_e3u, e3v=self._d_e3v)
             out[t0:t0 + m] = ser.cpu().numpy()

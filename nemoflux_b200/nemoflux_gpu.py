@@ -611,7 +611,7 @@ class H5DeviceReader(object):
         u, v = rd.read(starts, stops)              # both (twice the chunks in flight), block[0], block[1]
     """
 
-    def __init__(self, ds, device, workers=8):
+    def __init__(self, ds, device, workers=0):
         torch = _torch()
         self.many = isinstance(ds, (list, tuple))
         self.dss = list(ds) if self.many else [ds]
@@ -628,9 +628,13 @@ class H5DeviceReader(object):
                 raise ValueError('variables decoded together must share shape, chunking, type and filters')
         self.tdtype = torch.float32 if self.ds.dtype.itemsize == 4 else torch.float64
         self.swap = not self.ds.dtype.isnative
-        self.workers = max(1, int(workers))
+        import os as _os
+        # file -> pinned copies: plain memcpy's that release the GIL; all but a few of the cores this process may use
+        self.workers = max(1, int(workers)) if workers else max(4, min(16, len(_os.sched_getaffinity(0)) - 3))
         self._pinned = None
-        self._dev = None
+        self._dev = [None, None]
+        self._slot = 0
+        self._last_ready = None
         self._copy_stream = None
         self.bytes_compressed = 0          # running totals, for the caller's report
         self.bytes_decoded = 0
@@ -649,7 +653,11 @@ class H5DeviceReader(object):
             pos += (nbytes + 15) & ~15
         total = pos + 4096                                      # the decoder may look a little past the last stream
         if self._pinned is None or self._pinned.numel() < total:
+            if self._last_ready is not None:
+                self._last_ready.synchronize()
             self._pinned = torch.empty(int(total * 1.25) + 4096, dtype=torch.uint8, pin_memory=True)
+        if self._last_ready is not None:
+            self._last_ready.synchronize()                      # the previous block has left the pinned buffer
         hbuf = self._pinned.numpy()
         fbufs = [numpy.frombuffer(d._f._buf, numpy.uint8) for d in self.dss]
 
@@ -664,7 +672,22 @@ class H5DeviceReader(object):
                 list(pool.map(lambda lo: copy(lo, min(len(plan), lo + step)), range(0, len(plan), step)))
         else:
             copy(0, len(plan))
-        return dict(plan=plan, offs=offs, total=total, starts=list(starts), stops=list(stops))
+        # the staged bytes start their way over PCIe right away, on a side stream and into the device buffer the decoder
+        # is NOT reading (two device buffers): the copy of block i + 1 hides behind the decode of block i
+        slot = self._slot = self._slot ^ 1
+        ready = None
+        if plan:
+            with torch.cuda.device(self.device):
+                if self._dev[slot] is None or self._dev[slot].numel() < total:
+                    self._dev[slot] = torch.empty(self._pinned.numel(), dtype=torch.uint8, device=self.device)
+                if self._copy_stream is None:
+                    self._copy_stream = torch.cuda.Stream(device=self.device)
+                with torch.cuda.stream(self._copy_stream):
+                    self._dev[slot][:total].copy_(self._pinned[:total], non_blocking=True)
+                    ready = torch.cuda.Event()
+                    ready.record(self._copy_stream)
+        self._last_ready = ready
+        return dict(plan=plan, offs=offs, total=total, starts=list(starts), stops=list(stops), slot=slot, ready=ready)
 
     def decode(self, staged, out=None):
         """device half: H2D of the staged bytes, inflate + unshuffle + placement; returns the cuda tensor (with a
@@ -683,45 +706,27 @@ class H5DeviceReader(object):
             else:
                 blk.zero_()
         if plan:
-            if self._dev is None or self._dev.numel() < total:
-                self._dev = torch.empty(self._pinned.numel(), dtype=torch.uint8, device=self.device)
-            # the staged bytes cross PCIe in a few pieces on a side stream; piece p is decoded while piece p + 1 travels
-            npiece = max(1, min(4, len(plan) // 1500))
-            cuts = [len(plan) * p // npiece for p in range(npiece + 1)]
-            if self._copy_stream is None:
-                self._copy_stream = torch.cuda.Stream(device=self.device)
-            main = torch.cuda.current_stream(self.device)
-            self._copy_stream.wait_stream(main)                 # the buffer's previous contents have been decoded
-            ready = []
-            with torch.cuda.stream(self._copy_stream):
-                for p in range(npiece):
-                    lo = offs[cuts[p]]
-                    hi = offs[cuts[p + 1]] if cuts[p + 1] < len(plan) else total
-                    self._dev[lo:hi].copy_(self._pinned[lo:hi], non_blocking=True)
-                    ev = torch.cuda.Event()
-                    ev.record(self._copy_stream)
-                    ready.append(ev)
-            piece_of = numpy.searchsorted(numpy.array(cuts[1:]), numpy.arange(len(plan)), side='right')
+            dev = self._dev[staged['slot']]
+            torch.cuda.current_stream(self.device).wait_event(staged['ready'])
             groups = {}
             for k, (iv, _addr, _nbytes, mask, _org) in enumerate(plan):   # a chunk may have skipped filters (its mask bits)
                 flags = 0
                 for i, (fid, _cd) in enumerate(self.dss[iv]._filters):
                     if not (mask >> i) & 1:
                         flags |= {1: _lib.NFX_H5_DEFLATE, 2: _lib.NFX_H5_SHUFFLE, 3: _lib.NFX_H5_FLETCHER32}[fid]
-                groups.setdefault((int(piece_of[k]), flags), []).append(k)
+                groups.setdefault(flags, []).append(k)
             # one launch for all variables when a chunk is one index thick along axis 0 (NetCDF's usual time chunking):
             # the variables are stacked along that axis and no chunk can hang over into its neighbour; else a launch
             # per variable, clipped by its own block
             together = nvar == 1 or self.ds.chunk_dims[0] == 1
-            for (piece, flags), ks_all in sorted(groups.items()):
-                main.wait_event(ready[piece])
+            for flags, ks_all in sorted(groups.items()):
                 for iv in ([None] if together else range(nvar)):
                     ks = ks_all if together else [k for k in ks_all if plan[k][0] == iv]
                     if not ks:
                         continue
                     start = [[plan[k][4][d] - staged['starts'][d] + (plan[k][0] * shape[0] if d == 0 and together else 0)
                               for d in range(len(shape))] for k in ks]
-                    h5DecodeChunks(self._dev[:total], [offs[k] for k in ks], [plan[k][2] for k in ks], flags,
+                    h5DecodeChunks(dev[:total], [offs[k] for k in ks], [plan[k][2] for k in ks], flags,
                                    self.ds.chunk_dims, full if together else out[iv], start, swap_bytes=self.swap)
             self.bytes_compressed += sum(p[2] for p in plan)
         self.bytes_decoded += out.numel() * out.element_size()

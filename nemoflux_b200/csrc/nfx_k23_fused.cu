@@ -573,6 +573,7 @@ void flux_series_fused(PliDev& p, const PanelPlan& pl, const void* u, const void
         NFX_CUDA(cudaMemsetAsync(p.fused_sticky_buf.p, 0, sizeof(int), s));
     }
     k_or_flag<<<1, 1, 0, s>>>(a.sync + 1, p.fused_sticky_buf.p);
+    count_launch();
     NFX_CUDA(cudaMemcpyAsync(p.h_fused_err, p.fused_sticky_buf.p, sizeof(int), cudaMemcpyDeviceToHost, s));
 }
 

@@ -348,18 +348,25 @@ __global__ void k_or_flag(const int* flag, int* sticky) {
     if (*flag != 0) *sticky = 1;
 }
 
+// dynamic shared memory of the launch being prepared (2 * nz doubles): the occupancy query uses the real size; the
+// answer is cached per device for the common case (nz <= 128, where registers, not shared memory, bound the occupancy)
+thread_local size_t t_fused_smem = sizeof(double) * 256;
+
 template <typename T, int VEC, int UNROLL, int CTAS = 0, bool E3 = false>
 int fused_grid() {
     static int grid[64] = {0};   // per device ordinal
     int dev = 0;
     NFX_CUDA(cudaGetDevice(&dev));
+    const bool small = t_fused_smem <= sizeof(double) * 256;
     int& g = grid[dev & 63];
-    if (g == 0) {
+    if (g == 0 || !small) {
         int sms = 0, per_sm = 0;
         NFX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         NFX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k23_fused<T, VEC, UNROLL, CTAS, E3>, kFusedBlock,
-                                                               sizeof(double) * 256));
-        g = sms * std::max(per_sm, 1);
+                                                               std::max(t_fused_smem, sizeof(double) * 256)));
+        const int n = sms * std::max(per_sm, 1);
+        if (!small) return n;
+        g = n;
     }
     return g;
 }
@@ -471,13 +478,14 @@ void flux_series_fused(PliDev& p, const PanelPlan& pl, const void* u, const void
     a.idx = pl.idx.p;
     a.w = pl.w.p;
     a.out = out;
-    NFX_REQUIRE(nz <= 3072, "edgeflux: at most 3072 levels (dz and dz * 2^896 live in 48 KB of shared memory)");
+    NFX_REQUIRE(nz <= 3000, "edgeflux: at most 3000 levels (dz and dz * 2^896 live in 48 KB of shared memory)");
     NFX_REQUIRE((int64_t)(a.nbatches + 64) * (a.ntiles + a.nk3) < 2000000000ll, "fused pass: too many work items");
     // enough slots that every resident CTA finds a K2 tile while the K3 of older batches drains (x2 margin),
     // but no more than ring_max of evict-last lines in the 126 MB L2
     int ctas = 0;   // 0 = the default register budget of the shape
     if (dtype == NFX_F64 && vec == 4 && (g_fused_f64_ctas == 2 || g_fused_f64_ctas == 4)) ctas = g_fused_f64_ctas;
     if (dtype != NFX_F64 && vec == 4 && unroll == 5 && g_fused_f64_ctas == 3) ctas = 3;
+    t_fused_smem = sizeof(double) * (size_t)nz * 2;
     const int resident = e3 ? fused_grid_e3(dtype, vec) : fused_grid_for(dtype, vec, unroll, ctas);
     int slots = (2 * resident + a.ntiles - 1) / a.ntiles + 1;
     // the whole ring stays under 24 MB: beyond that (32 MB: float32 storage on ORCA12, 4 slots of 8 MB) L2 starts writing

@@ -537,7 +537,7 @@ void edgeflux_assemble_panel(const void* u, const void* v, int dtype, const doub
     NFX_REQUIRE(nt >= 0 && nz > 0 && ncols > 0 && ld >= ncols, "edgeflux: bad sizes");
     NFX_REQUIRE(dtype == NFX_F64 || dtype == NFX_F32, "edgeflux: dtype must be NFX_F64 or NFX_F32");
     NFX_REQUIRE(nt <= 65535, "edgeflux: at most 65535 time steps per call");
-    NFX_REQUIRE(nz <= 3072, "edgeflux: at most 3072 levels (dz and dz * 2^896 live in 48 KB of shared memory)");
+    NFX_REQUIRE(nz <= 3000, "edgeflux: at most 3000 levels (dz and dz * 2^896 live in 48 KB of shared memory)");
     if (nt == 0) return;
     const double scale = 6371000.0 / 1.e6;  // field.py:12,226
     const int has_fill = !(fill != fill);

@@ -902,3 +902,42 @@ print('ok', n)
         out = subprocess.run([sys.executable, '-c', c], capture_output=True, text=True, timeout=300,
                              env=dict(os.environ, NFX_DEBUG_GUARDS='1'))
         assert out.returncode == 0 and out.stdout.startswith('ok'), out.stderr[-2000:] + out.stdout[-500:]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('dtype', [numpy.float64, numpy.float32])
+def test_many_levels_up_to_the_shared_memory_limit(gpu, oracle, dtype):
+    """the layer thickness (and its 2^896 multiple for float32 storage) lives in dynamic shared memory: 3000 levels
+    (47 KB) is the documented limit -- both passes work there (same bits as the sequential oracle), one level more is
+    refused with a clear message instead of a launch failure"""
+    import torch
+    from nemoflux_b200 import _lib
+    nx, ny, nt = 24, 12, 2
+    rng = numpy.random.default_rng(8)
+    for nz in (3000, 1000):
+        g = oracle.DataGen(nx=nx, ny=ny, nz=1, nt=1)
+        P, arc = g.points(), oracle.arc_lengths(g.points())
+        u = rng.normal(size=(nt, nz, ny, nx)).astype(dtype)
+        v = rng.normal(size=(nt, nz, ny, nx)).astype(dtype)
+        u[:, :, 3:5, 2:9] = numpy.nan
+        th = rng.uniform(0.5, 2.0, nz)
+        _, p = _build(gpu, P, ny, nx)
+        transects = [tr(README_C1), tr([(-100, -40), (80, 30)])]
+        p.computeWeights(transects)
+        a1, a2 = arc[:, 1].copy(), arc[:, 2].copy()
+        args = [torch.from_numpy(x).cuda() for x in (u, v, th, a1, a2)]
+        fused = p.fluxSeries(*args).cpu().numpy()
+        assert _lib.get_option(_lib.NFX_OPT_LAST_SERIES_PATH) == 1 and p.seriesStatus() == 0
+        ef = torch.empty((nt, 2 * ny * nx), dtype=torch.float64, device='cuda')
+        classic = p.fluxSeries(*args, eflux=ef).cpu().numpy()
+        for t in range(nt):
+            _, eU, eV = oracle.edgeflux_step_c(u[t], v[t], th, a1, a2, False)
+            assert_bitwise(ef[t].cpu().numpy(), numpy.concatenate([eU, eV]), f'eflux nz={nz}')
+        scale = numpy.abs(classic).max()
+        assert numpy.abs(fused - classic).max() <= 1e-12 * scale
+    nz = 3001
+    u = torch.zeros((1, nz, ny, nx), dtype=torch.float64, device='cuda')
+    with pytest.raises(_lib.NemofluxGpuError, match='3000 levels'):
+        p.fluxSeries(u, u, torch.ones(nz, dtype=torch.float64, device='cuda'), args[3], args[4])
+    with pytest.raises(_lib.NemofluxGpuError, match='3000 levels'):
+        gpu.edgeFluxAssemble(u, u, torch.ones(nz, dtype=torch.float64, device='cuda'), args[3], args[4])

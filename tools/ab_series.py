@@ -49,10 +49,10 @@ def main():
     for mb in [int(x) for x in a.slots.split(',')]:
         modes.append((f'fused slot={mb}MB', {}, {_lib.NFX_OPT_RING_SLOT_MB: mb, _lib.NFX_OPT_FAST_SERIES: 2}))
     for shape in [int(x) for x in a.f32_shapes.split(',') if x]:
-        modes.append((f'fused f32 shape={shape}', {}, {_lib.NFX_OPT_RING_SLOT_MB: 8, _lib.NFX_OPT_FAST_SERIES: 2,
+        modes.append((f'fused f32 shape={shape}', {}, {_lib.NFX_OPT_RING_SLOT_MB: 0, _lib.NFX_OPT_FAST_SERIES: 2,
                                                          _lib.NFX_OPT_FUSED_F32_SHAPE: shape}))
     for o in [int(x) for x in a.orders.split(',') if x]:
-        modes.append((f'fused order={o}', {}, {_lib.NFX_OPT_RING_SLOT_MB: 8, _lib.NFX_OPT_FAST_SERIES: 2,
+        modes.append((f'fused order={o}', {}, {_lib.NFX_OPT_RING_SLOT_MB: 0, _lib.NFX_OPT_FAST_SERIES: 2,
                                                _lib.NFX_OPT_FUSED_ORDER: o}))
     for c in [int(x) for x in a.f64_ctas.split(',') if x]:
         modes.append((f'fused f64 ctas/SM={c}', {}, {_lib.NFX_OPT_FUSED_F64_CTAS: c}))
@@ -60,7 +60,7 @@ def main():
     ref = None
     for rnd in range(a.rounds):
         for name, kw, opts in modes:
-            full = {_lib.NFX_OPT_RING_SLOT_MB: 8, _lib.NFX_OPT_FAST_SERIES: 2, _lib.NFX_OPT_FUSED_F32_SHAPE: 0,
+            full = {_lib.NFX_OPT_RING_SLOT_MB: 0, _lib.NFX_OPT_FAST_SERIES: 2, _lib.NFX_OPT_FUSED_F32_SHAPE: 0,
                     _lib.NFX_OPT_FUSED_ORDER: a.base_order, _lib.NFX_OPT_FUSED_F64_CTAS: 0}
             full.update(opts)                       # every mode sets every knob: nothing leaks from the mode before
             for k, val in full.items():

@@ -720,3 +720,29 @@ def test_weighted_batch_sharding_tiles_the_batch_space():
         nd.shard_batches(nt, npanels, world, 0, [1.0] * 7)
     with pytest.raises(ValueError):
         nd.batch_bounds(10, 2, [1.0, 0.0])
+
+
+def test_netcdf4_backend_reads_are_serialised_when_it_is_installed(tmp_path):
+    """with netCDF4-python importable ncio prefers it (what the reference requires): its variables carry the lock, and
+    the parallel readers of Field.fluxSeries (read_into from a thread pool + a prefetch thread) get the right values"""
+    pytest.importorskip('netCDF4')
+    import threading
+    from nemoflux_b200 import ncio
+    path = str(tmp_path / 'U.nc')
+    data = numpy.arange(6 * 5 * 8 * 9, dtype=numpy.float32).reshape(6, 5, 8, 9)
+    w = ncio.Writer(path)
+    for name, n in (('t', 6), ('z', 5), ('y', 8), ('x', 9)):
+        w.createDimension(name, n)
+    w.createVariable('uo', 'float32', ('t', 'z', 'y', 'x'), fill_value=1.e20, data=data)
+    w.close()
+    with ncio.open_dataset(path) as nc:
+        var = nc['uo']
+        assert not var.thread_safe and var._lock is ncio._NETCDF4_LOCK
+        dst = numpy.zeros_like(data)
+        ths = [threading.Thread(target=var.read_into, args=(dst[t, z0:z0 + 1], (t, slice(z0, z0 + 1))))
+               for t in range(6) for z0 in range(5)]
+        for th in ths:
+            th.start()
+        for th in ths:
+            th.join()
+        assert numpy.array_equal(dst, data)

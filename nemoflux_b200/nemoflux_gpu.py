@@ -730,7 +730,7 @@ class H5DeviceReader(object):
                                    self.ds.chunk_dims, full if together else out[iv], start, swap_bytes=self.swap)
             self.bytes_compressed += sum(p[2] for p in plan)
         self.bytes_decoded += out.numel() * out.element_size()
-        return out if self.many else out[0]
+        return out if self.many or out.dim() == len(shape) else out[0]
 
     def read(self, starts, stops, out=None):
         return self.decode(self.stage(starts, stops), out=out)

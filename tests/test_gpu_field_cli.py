@@ -235,16 +235,6 @@ def test_field_with_mesh_file_scale_factors(gpu, oracle, tmp_path, capsys):
     assert f32.e3u.dtype == numpy.float32
     s32 = f32.fluxSeries(chunk_steps=4)
     assert numpy.abs(s32 - ref).max() <= 1e-5 * numpy.abs(ref).max()
-    # the same float32 data in chunked + shuffled + deflated NetCDF-4 files: decoded on the device, scale factors applied
-    # by the same fused pass -> the bits of the classic-file series
-    import h5build
-    U4, V4 = str(sub / 'U4.nc'), str(sub / 'V4.nc')
-    for fname, vname, a in ((U4, 'uo', u), (V4, 'vo', v)):
-        h5build.write(fname, {vname: dict(data=a.astype(numpy.float32), chunks=(1, 1, 36, 72), deflate=4, shuffle=True,
-                                          attrs={'_FillValue': numpy.float32(1.e20), 'units': 'm/s'})})
-    f4 = Field(T, U4, V4, lines, sverdrup=True, verbose=False, meshFile=mesh)
-    assert numpy.array_equal(f4.fluxSeries(chunk_steps=4), s32) and f4.last_ingest['path'] == 'device decode'
-    assert numpy.array_equal(f4.fluxSeries(), s32)
     # the command-line flag
     out = fluxplot.main(['-t', T, '-u', U, '-v', V, '-s', '--meshFile', mesh,
                          '-l', '[(-100,-70),(100,-70),(0,70)],[(-150,-20),(-20,35),(60,-40)]'])

@@ -746,3 +746,77 @@ def test_netcdf4_backend_reads_are_serialised_when_it_is_installed(tmp_path):
         for th in ths:
             th.join()
         assert numpy.array_equal(dst, data)
+
+
+def test_fused_pass_queue_order_cannot_deadlock():
+    """csrc/nfx_k23_fused.cu hands out work items from one counter in the order
+        ... | K2 tiles of batch b | K3 items of batch b - lag | K2 tiles of batch b + 1 | ...
+    A K2 tile of batch b waits for the K3 items of batch b - R (its ring slot), a K3 item of batch b for the K2 tiles of
+    batch b.  The pass cannot deadlock, whatever the number of resident CTAs, iff every wait targets items with a SMALLER
+    id (items a running CTA already holds) -- which needs R > lag.  This model restates the host-side choice of
+    (ring slots R, lag) of flux_series_fused and checks the invariant, then runs the queue with 1..many CTAs."""
+    def choose(resident, ntiles, slot_bytes, npanels, ring_max=24 << 20, lag_opt=0):
+        slots = (2 * resident + ntiles - 1) // ntiles + 1
+        cap = max(3, ring_max // slot_bytes)
+        slots = min(max(slots, 3), cap)
+        lag = lag_opt if lag_opt > 0 else ((resident + ntiles - 1) // ntiles + 1 if npanels == 1 else 1)
+        lag = max(1, min(lag, cap - 2))
+        slots = min(max(slots, lag + 2), cap)
+        return slots, lag
+
+    def item_ids(nb, ntiles, nk3, lag):
+        per = ntiles + nk3
+        k2 = lambda b: range(b * per, b * per + ntiles)                               # noqa: E731
+        k3 = lambda b: range((b + lag) * per + ntiles, (b + lag) * per + per)         # noqa: E731
+        return k2, k3, (nb + lag) * per
+
+    rng = numpy.random.default_rng(17)
+    shapes = [(444, 118, 1923 * 1024, 1), (592, 118, 1923 * 1024, 1), (444, 256, 4 << 20, 51), (592, 512, 8 << 20, 26),
+              (444, 480, 8 << 20, 3), (3, 1, 64, 1), (1, 7, 1 << 20, 4)]
+    shapes += [(int(rng.integers(1, 700)), int(rng.integers(1, 600)), int(rng.integers(1, 9)) << 20, int(rng.integers(1, 60)))
+               for _ in range(40)]
+    for resident, ntiles, slot_bytes, npanels in shapes:
+        for lag_opt in (0, 1, 5, 60):
+            R, lag = choose(resident, ntiles, slot_bytes, npanels, lag_opt=lag_opt)
+            assert R > lag >= 1 and R * slot_bytes <= max(24 << 20, 3 * slot_bytes)
+            nb, nk3 = 40, 3
+            k2, k3, nitems = item_ids(nb, ntiles, nk3, lag)
+            for b in range(nb):
+                assert max(k2(b)) < min(k3(b))                                         # K3 of b waits for K2 of b
+                if b >= R:
+                    assert max(k3(b - R)) < min(k2(b))                                 # K2 of b waits for K3 of b - R
+    # the queue itself, event by event, with few and many CTAs (a CTA holds one item and blocks until its counter is full)
+    for ncta in (1, 2, 5, 64):
+        for ntiles, nk3, nb, (R, lag) in ((3, 2, 12, (3, 1)), (2, 1, 9, (4, 2)), (5, 3, 7, (9, 7)), (1, 1, 30, (3, 1))):
+            per = ntiles + nk3
+            nitems = (nb + lag) * per
+            k2done, k3done = [0] * nb, [0] * nb
+            nxt, running, finished = 0, {}, 0
+            for _ in range(100000):
+                for c in range(ncta):                                                   # idle CTAs take the next item
+                    if c not in running and nxt < nitems:
+                        running[c] = nxt
+                        nxt += 1
+                progressed = False
+                for c, it in sorted(running.items(), key=lambda kv: -kv[1]):          # worst case: newest item first
+                    bb, r = divmod(it, per)
+                    if r < ntiles:
+                        b = bb
+                        ok = b >= nb or b < R or k3done[b - R] == nk3
+                        if ok:
+                            if b < nb:
+                                k2done[b] += 1
+                    else:
+                        b = bb - lag
+                        ok = not (0 <= b < nb) or k2done[b] == ntiles
+                        if ok and 0 <= b < nb:
+                            k3done[b] += 1
+                    if ok:
+                        del running[c]
+                        finished += 1
+                        progressed = True
+                        break
+                if finished == nitems:
+                    break
+                assert progressed, (ncta, ntiles, nk3, nb, R, lag, running)
+            assert finished == nitems and k2done == [ntiles] * nb and k3done == [nk3] * nb

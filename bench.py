@@ -233,7 +233,7 @@ def all_host_threads():
 def default_cpu_steps(args, syn):
     if args.cpu_steps > 0:
         return args.cpu_steps
-    return max(1, min(24, int(5.2e9 // (16 * syn.units_per_step()))))     # C3: 24 steps, C4: 3, C5: 1
+    return max(1, min(24, int(5.2e9 // (16 * syn.units_per_step()))))     # C3: 24 steps, C4: 2, C5: 1
 
 
 def run_reference(args):
